@@ -1,0 +1,72 @@
+"""ctypes binding of include/cbx_b200.h.  Fails loudly when the CUDA library is missing:
+there is no CPU or PyTorch fallback for the hot path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcbx_b200.so")
+
+
+class CbxConfig(C.Structure):
+    _fields_ = [("t3_layers", C.c_int), ("enc_blocks", C.c_int), ("up_blocks", C.c_int), ("cfm_blocks", C.c_int),
+                ("cfm_mid", C.c_int), ("cfm_steps", C.c_int), ("cfm_cfg_rate", C.c_float), ("max_streams", C.c_int),
+                ("max_seq", C.c_int), ("max_text", C.c_int), ("max_s3_tokens", C.c_int), ("max_prompt_tokens", C.c_int),
+                ("n_voices", C.c_int), ("n_lanes", C.c_int)]
+
+
+# every exported symbol of include/cbx_b200.h: name -> (restype, argtypes)
+_P, _I, _F, _L, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
+SIGNATURES = {
+    "cbx_abi_version": (_I, []),
+    "cbx_last_error": (C.c_char_p, []),
+    "cbx_engine_create": (_I, [C.POINTER(CbxConfig), _I, C.POINTER(_P)]),
+    "cbx_engine_destroy": (None, [_P]),
+    "cbx_manifest_create": (_I, [C.POINTER(CbxConfig), C.POINTER(_P)]),
+    "cbx_tensor_count": (_I, [_P]),
+    "cbx_tensor_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_I)]),
+    "cbx_tensor_upload": (_I, [_P, C.c_char_p, _P, _L]),
+    "cbx_finalize": (_I, [_P]),
+    "cbx_voice_put": (_I, [_P, _I, _P, _P, _I, _F, _P, _I, _P, _I, _P, _P]),
+    "cbx_voice_drop": (_I, [_P, _I]),
+    "cbx_t3_open": (_I, [_P, _I, _P, _I, _F, _F, _F, _F, _F, _U64, _I, C.POINTER(_I), _P]),
+    "cbx_t3_step": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cbx_t3_poll": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _P]),
+    "cbx_t3_tokens": (_I, [_P, _I, _I, _I, _P, _P]),
+    "cbx_t3_logits": (_I, [_P, _I, _P, _P]),
+    "cbx_t3_close": (_I, [_P, _I]),
+    "cbx_s3gen_infer": (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P, _P, _U64, _P]),
+    "cbx_flow_infer": (_I, [_P, _I, _P, _I, _P, _P]),
+    "cbx_hift_infer": (_I, [_P, _P, _I, _P, _L, _P, _P, _P, _P, _U64, _P]),
+    "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
+    "cbx_gpu_launches": (_L, [_P]),
+    "cbx_op_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "cbx_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libcbx_b200.so and attach signatures.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  The Chatterbox hot path has no CPU/PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class CbxError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise CbxError(load().cbx_last_error().decode())

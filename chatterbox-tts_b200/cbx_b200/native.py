@@ -1,0 +1,196 @@
+"""Thin Python object over the C-ABI engine.  torch is used only for device buffers and streams;
+every computation happens inside libcbx_b200.so."""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .config import ModelConfig
+from .pack import pack_state_dict
+
+SPEECH_V = 8194
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def _f32(a):
+    if torch.is_tensor(a):
+        a = a.detach().cpu().float().numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+class NativeEngine:
+    """One engine per GPU (reference: one worker process per device, src/master.py:56-77)."""
+
+    def __init__(self, cfg: ModelConfig = None, device: int = 0, max_streams=8, max_seq=1536, max_text=512,
+                 max_s3_tokens=1056, max_prompt_tokens=250, n_voices=8, n_lanes=2):
+        if not torch.cuda.is_available():
+            raise RuntimeError("NativeEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg or ModelConfig()
+        self.lib = L.load()
+        self.device = device
+        torch.cuda.set_device(device)
+        f = self.cfg.flow
+        self.ccfg = L.CbxConfig(self.cfg.t3.n_layers, f.enc_blocks, f.up_blocks, f.n_blocks, f.n_mid, f.n_timesteps, f.cfg_rate,
+                                max_streams, max_seq, max_text, max_s3_tokens, max_prompt_tokens, n_voices, n_lanes)
+        h = C.c_void_p()
+        L.check(self.lib.cbx_engine_create(C.byref(self.ccfg), device, C.byref(h)))
+        self.h = h
+        self._voice_ids = {}
+        self._voice_lock = threading.Lock()
+        self.n_voices = n_voices
+        self.max_s3_tokens = max_s3_tokens
+
+    # ------------------------------------------------------------------ checkpoint
+    def tensor_manifest(self):
+        out = []
+        name = C.create_string_buffer(256)
+        numel, dt = C.c_int64(), C.c_int()
+        for i in range(self.lib.cbx_tensor_count(self.h)):
+            L.check(self.lib.cbx_tensor_info(self.h, i, name, 256, C.byref(numel), C.byref(dt)))
+            out.append((name.value.decode(), numel.value, dt.value))
+        return out
+
+    def load_state_dict(self, sd):
+        packed = pack_state_dict(sd, self.cfg)
+        for name, numel, dt in self.tensor_manifest():
+            if name not in packed:
+                raise KeyError(f"checkpoint packer produced no tensor named {name}")
+            t = packed[name]
+            want = torch.float32 if dt == 0 else torch.bfloat16
+            if t.dtype != want or t.numel() != numel:
+                raise ValueError(f"{name}: packer gave {t.dtype} x{t.numel()}, engine wants {want} x{numel}")
+            t = t.contiguous()
+            L.check(self.lib.cbx_tensor_upload(self.h, name.encode(), C.c_void_p(t.data_ptr()), t.numel() * t.element_size()))
+        L.check(self.lib.cbx_finalize(self.h))
+
+    # ------------------------------------------------------------------ voices
+    def voice_put(self, key, t3_cond: dict, gen: dict) -> int:
+        """Caches one voice's conditioning on the device; returns its slot (reference voice_cache, tts_streaming.py:178)."""
+        with self._voice_lock:
+            if key in self._voice_ids:
+                slot = self._voice_ids[key]
+            else:
+                used = set(self._voice_ids.values())
+                free = [i for i in range(self.n_voices) if i not in used]
+                if not free:
+                    raise RuntimeError("voice cache is full")
+                slot = free[0]
+            spk = _f32(t3_cond["speaker_emb"]).reshape(-1)
+            ct = _i32(torch.as_tensor(t3_cond["cond_prompt_speech_tokens"]).cpu().numpy().reshape(-1))
+            emo = float(torch.as_tensor(t3_cond["emotion_adv"]).reshape(-1)[0])
+            pt = _i32(torch.as_tensor(gen["prompt_token"]).cpu().numpy().reshape(-1))
+            pf = _f32(gen["prompt_feat"]).reshape(-1, 80)
+            xv = _f32(gen["embedding"]).reshape(-1)
+            L.check(self.lib.cbx_voice_put(self.h, slot, spk.ctypes.data, ct.ctypes.data, len(ct), emo, pt.ctypes.data, len(pt),
+                                           pf.ctypes.data, pf.shape[0], xv.ctypes.data, _stream_ptr()))
+            self._voice_ids[key] = slot
+            return slot
+
+    def voice_slot(self, key):
+        return self._voice_ids.get(key)
+
+    def voice_drop(self, key):
+        with self._voice_lock:
+            slot = self._voice_ids.pop(key, None)
+            if slot is not None:
+                L.check(self.lib.cbx_voice_drop(self.h, slot))
+
+    # ------------------------------------------------------------------ T3
+    def t3_open(self, voice, text_ids, cfg_weight=0.5, temperature=0.8, rep_penalty=1.2, min_p=0.05, top_p=0.95, seed=0, max_new=1000):
+        ids = _i32(text_ids).reshape(-1)
+        slot = C.c_int()
+        L.check(self.lib.cbx_t3_open(self.h, voice, ids.ctypes.data, len(ids), cfg_weight, temperature, rep_penalty, min_p, top_p,
+                                     seed, max_new, C.byref(slot), _stream_ptr()))
+        return slot.value
+
+    def t3_step(self, slots, n_steps=1, noise=None):
+        s = _i32(slots)
+        nptr = C.c_void_p(noise.data_ptr()) if noise is not None else None
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.numel() == n_steps * len(s) * SPEECH_V
+        L.check(self.lib.cbx_t3_step(self.h, s.ctypes.data, len(s), n_steps, nptr, _stream_ptr()))
+
+    def t3_poll(self, slot):
+        n, d = C.c_int(), C.c_int()
+        L.check(self.lib.cbx_t3_poll(self.h, slot, C.byref(n), C.byref(d), _stream_ptr()))
+        return n.value, bool(d.value)
+
+    def t3_tokens(self, slot, start, count):
+        out = np.empty(count, dtype=np.int32)
+        L.check(self.lib.cbx_t3_tokens(self.h, slot, start, count, out.ctypes.data, _stream_ptr()))
+        return out
+
+    def t3_logits(self, slot):
+        out = np.empty((2, SPEECH_V), dtype=np.float32)
+        L.check(self.lib.cbx_t3_logits(self.h, slot, out.ctypes.data, _stream_ptr()))
+        return out
+
+    def t3_close(self, slot):
+        L.check(self.lib.cbx_t3_close(self.h, slot))
+
+    # ------------------------------------------------------------------ S3Gen
+    def s3gen_infer(self, voice, tokens, cache_source=None, seed=0, phase=None, noise=None, return_mel=False):
+        tok = _i32(tokens).reshape(-1)
+        n = len(tok)
+        dev = torch.device("cuda", self.device)
+        wav = torch.empty(1, 960 * n, device=dev, dtype=torch.float32)
+        src = torch.empty(1, 1, 960 * n, device=dev, dtype=torch.float32)
+        mel = torch.empty(2 * n, 80, device=dev, dtype=torch.float32) if return_mel else None
+        m = 0 if cache_source is None else cache_source.shape[-1]
+        cptr = C.c_void_p(cache_source.contiguous().data_ptr()) if m else None
+        ph = _f32(phase) if phase is not None else None
+        L.check(self.lib.cbx_s3gen_infer(self.h, voice, tok.ctypes.data, n, cptr, m, C.c_void_p(wav.data_ptr()), C.c_void_p(src.data_ptr()),
+                                         C.c_void_p(mel.data_ptr()) if return_mel else None,
+                                         ph.ctypes.data if ph is not None else None,
+                                         C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, _stream_ptr()))
+        return (wav, src, mel) if return_mel else (wav, src)
+
+    def flow_infer(self, voice, tokens):
+        tok = _i32(tokens).reshape(-1)
+        mel = torch.empty(2 * len(tok), 80, device=torch.device("cuda", self.device), dtype=torch.float32)
+        L.check(self.lib.cbx_flow_infer(self.h, voice, tok.ctypes.data, len(tok), C.c_void_p(mel.data_ptr()), _stream_ptr()))
+        return mel
+
+    def hift_infer(self, mel, cache_source=None, seed=0, phase=None, noise=None):
+        mel = mel.contiguous().float()
+        T = mel.shape[0]
+        dev = mel.device
+        wav = torch.empty(1, 480 * T, device=dev, dtype=torch.float32)
+        src = torch.empty(1, 1, 480 * T, device=dev, dtype=torch.float32)
+        m = 0 if cache_source is None else cache_source.shape[-1]
+        cptr = C.c_void_p(cache_source.contiguous().data_ptr()) if m else None
+        ph = _f32(phase) if phase is not None else None
+        L.check(self.lib.cbx_hift_infer(self.h, C.c_void_p(mel.data_ptr()), T, cptr, m, C.c_void_p(wav.data_ptr()), C.c_void_p(src.data_ptr()),
+                                        ph.ctypes.data if ph is not None else None,
+                                        C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, _stream_ptr()))
+        return wav, src
+
+    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0):
+        out = torch.empty(n_out, device=cur.device, dtype=torch.int16)
+        L.check(self.lib.cbx_crossfade_pcm(self.h, C.c_void_p(cur.data_ptr()), n_out,
+                                           C.c_void_p(prev_tail.data_ptr()) if prev_tail is not None else None, fade_len,
+                                           C.c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
+
+    def gpu_launches(self):
+        return int(self.lib.cbx_gpu_launches(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cbx_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

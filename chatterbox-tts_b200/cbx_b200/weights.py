@@ -1,0 +1,265 @@
+"""Checkpoint schema and seeded random initialisation.
+
+Names follow the state-dict keys of the upstream chatterbox checkpoint files
+(`t3_cfg.safetensors`, `s3gen.safetensors`; loaded by `ChatterboxTTS.from_local`,
+reference call site src/tts_streaming.py:254-257) with weight-norm already
+folded into plain conv weights.  There are no checkpoints in this environment
+(BASELINE.json configs: "random-init Chatterbox weights"), so `random_state_dict`
+draws every tensor from a per-name seeded generator.  This file is data only:
+it contains no model arithmetic and is shared by the product packer, the
+benchmark and the test oracle.
+"""
+import zlib
+from collections import OrderedDict
+
+import torch
+
+from .config import ModelConfig, T3Config, FlowConfig, HiFTConfig
+
+# init kinds: ("w", fan_in, gain) normal(0, gain/sqrt(fan_in)); ("b",) small bias;
+# ("g",) norm gain 1+0.1n; ("n", std) normal; ("alpha",) positive snake alpha
+
+
+def _t3_schema(c: T3Config, S):
+    D = c.dim
+    S["t3.text_emb.weight"] = ((c.text_vocab, D), ("n", 0.02))
+    S["t3.speech_emb.weight"] = ((c.speech_vocab, D), ("n", 0.02))
+    S["t3.text_pos_emb.emb.weight"] = ((c.max_text_tokens + 2, D), ("n", 0.02))
+    S["t3.speech_pos_emb.emb.weight"] = ((c.max_speech_tokens + 4, D), ("n", 0.02))
+    S["t3.speech_head.weight"] = ((c.speech_vocab, D), ("n", 0.02))
+    S["t3.cond_enc.spkr_enc.weight"] = ((D, c.speaker_embed_size), ("w", c.speaker_embed_size, 0.3))
+    S["t3.cond_enc.spkr_enc.bias"] = ((D,), ("b",))
+    S["t3.cond_enc.emotion_adv_fc.weight"] = ((D, 1), ("n", 0.05))
+    S["t3.cond_enc.perceiver.pre_attention_query"] = ((1, c.perceiver_queries, D), ("n", 0.05))
+    p = "t3.cond_enc.perceiver.attn."
+    S[p + "norm.weight"] = ((D,), ("g",))
+    S[p + "norm.bias"] = ((D,), ("b",))
+    for n in ("to_q", "to_k", "to_v", "proj_out"):
+        S[p + n + ".weight"] = ((D, D), ("w", D, 0.5 if n == "proj_out" else 1.0))
+        S[p + n + ".bias"] = ((D,), ("b",))
+    for i in range(c.n_layers):
+        p = f"t3.tfmr.layers.{i}."
+        S[p + "input_layernorm.weight"] = ((D,), ("g",))
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            S[p + f"self_attn.{n}.weight"] = ((D, D), ("n", 0.02))
+        S[p + "post_attention_layernorm.weight"] = ((D,), ("g",))
+        S[p + "mlp.gate_proj.weight"] = ((c.ffn, D), ("n", 0.02))
+        S[p + "mlp.up_proj.weight"] = ((c.ffn, D), ("n", 0.02))
+        S[p + "mlp.down_proj.weight"] = ((D, c.ffn), ("n", 0.02))
+    S["t3.tfmr.norm.weight"] = ((D,), ("g",))
+
+
+def _conformer_layer(S, p, D, F, H):
+    S[p + "norm_mha.weight"] = ((D,), ("g",))
+    S[p + "norm_mha.bias"] = ((D,), ("b",))
+    for n in ("linear_q", "linear_k", "linear_v", "linear_out"):
+        S[p + f"self_attn.{n}.weight"] = ((D, D), ("w", D, 0.5 if n == "linear_out" else 1.0))
+        S[p + f"self_attn.{n}.bias"] = ((D,), ("b",))
+    S[p + "self_attn.linear_pos.weight"] = ((D, D), ("w", D, 1.0))
+    S[p + "self_attn.pos_bias_u"] = ((H, D // H), ("n", 0.1))
+    S[p + "self_attn.pos_bias_v"] = ((H, D // H), ("n", 0.1))
+    S[p + "norm_ff.weight"] = ((D,), ("g",))
+    S[p + "norm_ff.bias"] = ((D,), ("b",))
+    S[p + "feed_forward.w_1.weight"] = ((F, D), ("w", D, 1.0))
+    S[p + "feed_forward.w_1.bias"] = ((F,), ("b",))
+    S[p + "feed_forward.w_2.weight"] = ((D, F), ("w", F, 0.5))
+    S[p + "feed_forward.w_2.bias"] = ((D,), ("b",))
+
+
+def _resnet(S, p, cin, cout, tdim):
+    S[p + "mlp.1.weight"] = ((cout, tdim), ("w", tdim, 0.5))
+    S[p + "mlp.1.bias"] = ((cout,), ("b",))
+    for b, ci in (("block1", cin), ("block2", cout)):
+        S[p + f"{b}.block.0.weight"] = ((cout, ci, 3), ("w", 3 * ci, 1.0))
+        S[p + f"{b}.block.0.bias"] = ((cout,), ("b",))
+        S[p + f"{b}.block.2.weight"] = ((cout,), ("g",))
+        S[p + f"{b}.block.2.bias"] = ((cout,), ("b",))
+    S[p + "res_conv.weight"] = ((cout, cin, 1), ("w", cin, 1.0))
+    S[p + "res_conv.bias"] = ((cout,), ("b",))
+
+
+def _tfm_block(S, p, C, inner):
+    S[p + "norm1.weight"] = ((C,), ("g",))
+    S[p + "norm1.bias"] = ((C,), ("b",))
+    for n in ("to_q", "to_k", "to_v"):
+        S[p + f"attn1.{n}.weight"] = ((inner, C), ("w", C, 1.0))
+    S[p + "attn1.to_out.0.weight"] = ((C, inner), ("w", inner, 0.3))
+    S[p + "attn1.to_out.0.bias"] = ((C,), ("b",))
+    S[p + "norm3.weight"] = ((C,), ("g",))
+    S[p + "norm3.bias"] = ((C,), ("b",))
+    S[p + "ff.net.0.proj.weight"] = ((4 * C, C), ("w", C, 1.0))
+    S[p + "ff.net.0.proj.bias"] = ((4 * C,), ("b",))
+    S[p + "ff.net.2.weight"] = ((C, 4 * C), ("w", 4 * C, 0.3))
+    S[p + "ff.net.2.bias"] = ((C,), ("b",))
+
+
+def _flow_schema(c: FlowConfig, S):
+    D = c.enc_dim
+    S["flow.input_embedding.weight"] = ((c.vocab, D), ("n", 1.0))
+    S["flow.spk_embed_affine_layer.weight"] = ((c.mel, c.spk_dim), ("w", c.spk_dim, 4.0))
+    S["flow.spk_embed_affine_layer.bias"] = ((c.mel,), ("b",))
+    S["flow.encoder_proj.weight"] = ((c.mel, D), ("w", D, 1.0))
+    S["flow.encoder_proj.bias"] = ((c.mel,), ("b",))
+    e = "flow.encoder."
+    for emb in ("embed", "up_embed"):
+        S[e + f"{emb}.out.0.weight"] = ((D, D), ("w", D, 1.0))
+        S[e + f"{emb}.out.0.bias"] = ((D,), ("b",))
+        S[e + f"{emb}.out.1.weight"] = ((D,), ("g",))
+        S[e + f"{emb}.out.1.bias"] = ((D,), ("b",))
+    S[e + "pre_lookahead_layer.conv1.weight"] = ((D, D, c.pre_lookahead + 1), ("w", D * (c.pre_lookahead + 1), 1.0))
+    S[e + "pre_lookahead_layer.conv1.bias"] = ((D,), ("b",))
+    S[e + "pre_lookahead_layer.conv2.weight"] = ((D, D, 3), ("w", 3 * D, 1.0))
+    S[e + "pre_lookahead_layer.conv2.bias"] = ((D,), ("b",))
+    for i in range(c.enc_blocks):
+        _conformer_layer(S, e + f"encoders.{i}.", D, c.enc_ffn, c.enc_heads)
+    S[e + "up_layer.conv.weight"] = ((D, D, 5), ("w", 5 * D, 1.0))
+    S[e + "up_layer.conv.bias"] = ((D,), ("b",))
+    for i in range(c.up_blocks):
+        _conformer_layer(S, e + f"up_encoders.{i}.", D, c.enc_ffn, c.enc_heads)
+    S[e + "after_norm.weight"] = ((D,), ("g",))
+    S[e + "after_norm.bias"] = ((D,), ("b",))
+    d = "flow.decoder.estimator."
+    C, T, inner = c.ch, c.time_dim, c.heads * c.head_dim
+    S[d + "time_mlp.linear_1.weight"] = ((T, c.in_ch), ("w", c.in_ch, 1.4))
+    S[d + "time_mlp.linear_1.bias"] = ((T,), ("b",))
+    S[d + "time_mlp.linear_2.weight"] = ((T, T), ("w", T, 1.4))
+    S[d + "time_mlp.linear_2.bias"] = ((T,), ("b",))
+    _resnet(S, d + "down_blocks.0.0.", c.in_ch, C, T)
+    for j in range(c.n_blocks):
+        _tfm_block(S, d + f"down_blocks.0.1.{j}.", C, inner)
+    S[d + "down_blocks.0.2.weight"] = ((C, C, 3), ("w", 3 * C, 1.0))
+    S[d + "down_blocks.0.2.bias"] = ((C,), ("b",))
+    for i in range(c.n_mid):
+        _resnet(S, d + f"mid_blocks.{i}.0.", C, C, T)
+        for j in range(c.n_blocks):
+            _tfm_block(S, d + f"mid_blocks.{i}.1.{j}.", C, inner)
+    _resnet(S, d + "up_blocks.0.0.", 2 * C, C, T)
+    for j in range(c.n_blocks):
+        _tfm_block(S, d + f"up_blocks.0.1.{j}.", C, inner)
+    S[d + "up_blocks.0.2.weight"] = ((C, C, 3), ("w", 3 * C, 1.0))
+    S[d + "up_blocks.0.2.bias"] = ((C,), ("b",))
+    S[d + "final_block.block.0.weight"] = ((C, C, 3), ("w", 3 * C, 1.0))
+    S[d + "final_block.block.0.bias"] = ((C,), ("b",))
+    S[d + "final_block.block.2.weight"] = ((C,), ("g",))
+    S[d + "final_block.block.2.bias"] = ((C,), ("b",))
+    S[d + "final_proj.weight"] = ((c.mel, C, 1), ("w", C, 1.0))
+    S[d + "final_proj.bias"] = ((c.mel,), ("b",))
+    S["flow.decoder.rand_noise"] = ((1, c.mel, c.noise_len), ("n", 1.0))
+
+
+def _resblock(S, p, ch, k):
+    for j in range(3):
+        S[p + f"convs1.{j}.weight"] = ((ch, ch, k), ("w", ch * k, 0.5))
+        S[p + f"convs1.{j}.bias"] = ((ch,), ("b",))
+        S[p + f"convs2.{j}.weight"] = ((ch, ch, k), ("w", ch * k, 0.5))
+        S[p + f"convs2.{j}.bias"] = ((ch,), ("b",))
+        S[p + f"activations1.{j}.alpha"] = ((ch,), ("alpha",))
+        S[p + f"activations2.{j}.alpha"] = ((ch,), ("alpha",))
+
+
+def hift_source_down_specs(c: HiFTConfig):
+    """[(stride, kernel, padding)] of the three source_downs convs (upstream hifigan.py)."""
+    rates = [1] + c.upsample_rates[::-1][:-1]
+    cum = []
+    p = 1
+    for r in rates:
+        p *= r
+        cum.append(p)
+    out = []
+    for u in cum[::-1]:
+        out.append((1, 1, 0) if u == 1 else (u, 2 * u, u // 2))
+    return out
+
+
+def _hift_schema(c: HiFTConfig, S):
+    m = "mel2wav."
+    S[m + "conv_pre.weight"] = ((c.base_ch, c.mel, 7), ("w", 7 * c.mel, 1.0))
+    S[m + "conv_pre.bias"] = ((c.base_ch,), ("b",))
+    nsrc = c.n_fft + 2
+    ch = c.base_ch
+    for i, (u, k) in enumerate(zip(c.upsample_rates, c.upsample_kernels)):
+        cin, ch = c.base_ch >> i, c.base_ch >> (i + 1)
+        S[m + f"ups.{i}.weight"] = ((cin, ch, k), ("w", cin * k / u, 1.0))
+        S[m + f"ups.{i}.bias"] = ((ch,), ("b",))
+        s, ks, _ = hift_source_down_specs(c)[i]
+        S[m + f"source_downs.{i}.weight"] = ((ch, nsrc, ks), ("w", nsrc * ks, 1.0))
+        S[m + f"source_downs.{i}.bias"] = ((ch,), ("b",))
+        _resblock(S, m + f"source_resblocks.{i}.", ch, c.source_resblock_kernels[i])
+        for j, k2 in enumerate(c.resblock_kernels):
+            _resblock(S, m + f"resblocks.{i * len(c.resblock_kernels) + j}.", ch, k2)
+    S[m + "conv_post.weight"] = ((nsrc, ch, 7), ("w", 7 * ch, 0.2))
+    S[m + "conv_post.bias"] = ((nsrc,), ("b",))
+    S[m + "m_source.l_linear.weight"] = ((1, c.nb_harmonics + 1), ("n", 1.0))
+    S[m + "m_source.l_linear.bias"] = ((1,), ("b",))
+    cin = c.mel
+    for l in range(c.f0_layers):
+        S[m + f"f0_predictor.condnet.{2 * l}.weight"] = ((c.f0_ch, cin, 3), ("w", 3 * cin, 1.3))
+        S[m + f"f0_predictor.condnet.{2 * l}.bias"] = ((c.f0_ch,), ("b",))
+        cin = c.f0_ch
+    S[m + "f0_predictor.classifier.weight"] = ((1, c.f0_ch), ("w", c.f0_ch, 120.0))
+    S[m + "f0_predictor.classifier.bias"] = ((1,), ("n", 0.0))
+
+
+def schema(cfg: ModelConfig, parts=("t3", "flow", "hift")) -> "OrderedDict[str, tuple]":
+    """name -> (shape, init) for every tensor the hot path reads."""
+    S = OrderedDict()
+    if "t3" in parts:
+        _t3_schema(cfg.t3, S)
+    if "flow" in parts:
+        _flow_schema(cfg.flow, S)
+    if "hift" in parts:
+        _hift_schema(cfg.hift, S)
+    return S
+
+
+def _draw(name, shape, init, seed):
+    g = torch.Generator()
+    g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+    kind = init[0]
+    if kind == "w":
+        return torch.randn(shape, generator=g) * (init[2] / float(init[1]) ** 0.5)
+    if kind == "n":
+        return torch.randn(shape, generator=g) * init[1]
+    if kind == "b":
+        return torch.randn(shape, generator=g) * 0.02
+    if kind == "g":
+        return 1.0 + 0.1 * torch.randn(shape, generator=g)
+    if kind == "alpha":
+        return (1.0 + 0.2 * torch.randn(shape, generator=g)).abs() + 0.1
+    raise ValueError(kind)
+
+
+def random_state_dict(cfg: ModelConfig, seed: int = 0, parts=("t3", "flow", "hift")):
+    """Seeded random-init checkpoint (fp32, CPU).  Deterministic per (name, seed)."""
+    sd = OrderedDict()
+    for name, (shape, init) in schema(cfg, parts).items():
+        sd[name] = _draw(name, shape, init, seed)
+    if "mel2wav.f0_predictor.classifier.bias" in sd:
+        sd["mel2wav.f0_predictor.classifier.bias"].fill_(90.0)  # keeps f0 around the voiced threshold
+    return sd
+
+
+def synthetic_conditionals(cfg: ModelConfig, seed: int = 1234, prompt_tokens: int = 194):
+    """Voice conditioning of the shapes `prepare_conditionals` yields for
+    preloaded-voices/trump.wav (reference src/tts_streaming.py:357-384):
+    the conditioning encoders are out of scope for this path, so the
+    benchmark and tests use seeded tensors of the same shapes and value ranges."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    t3c, fc = cfg.t3, cfg.flow
+    spk = torch.randn(1, t3c.speaker_embed_size, generator=g)
+    spk = spk / spk.norm(dim=1, keepdim=True)
+    return {
+        "t3": {
+            "speaker_emb": spk,
+            "cond_prompt_speech_tokens": torch.randint(0, fc.vocab, (1, t3c.speech_cond_prompt_len), generator=g),
+            "emotion_adv": 0.5 * torch.ones(1, 1, 1),
+        },
+        "gen": {
+            "prompt_token": torch.randint(0, fc.vocab, (1, prompt_tokens), generator=g),
+            "prompt_token_len": torch.tensor([prompt_tokens]),
+            "prompt_feat": torch.randn(1, 2 * prompt_tokens, fc.mel, generator=g) * 2.0 - 5.0,
+            "prompt_feat_len": None,
+            "embedding": torch.randn(1, fc.spk_dim, generator=g),
+        },
+    }

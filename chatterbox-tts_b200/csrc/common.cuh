@@ -1,0 +1,143 @@
+// Shared device helpers for the Chatterbox B200 hot path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <stdexcept>
+
+typedef __nv_bfloat16 bf16;
+
+#define CBX_CHECK(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + \
+                                     " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define CBX_REQUIRE(cond, msg)                                                             \
+    do {                                                                                  \
+        if (!(cond)) throw std::runtime_error(std::string("cbx: ") + (msg) + " [" #cond "] at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- activations
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4, ACT_ELU = 5, ACT_SNAKE = 6 };
+
+__device__ __forceinline__ float act_apply(int act, float v, float param) {
+    switch (act) {
+        case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+        case ACT_SILU: return v / (1.f + expf(-v));
+        case ACT_MISH: {
+            float sp = v > 20.f ? v : log1pf(expf(v));
+            return v * tanhf(sp);
+        }
+        case ACT_LRELU: return v > 0.f ? v : v * param;
+        case ACT_ELU: return v > 0.f ? v : expm1f(v);
+        case ACT_SNAKE: {
+            float s = sinf(v * param);
+            return v + s * s / (param + 1e-9f);
+        }
+        default: return v;
+    }
+}
+
+// ---------------------------------------------------------------- warp / block reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- async copy / mma primitives
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (counter-based RNG)
+struct Philox {
+    __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    // counter (c0..c3), key (seed lo/hi) -> 4 x u32
+    __host__ __device__ static inline void gen(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+};
+// u32 -> float in (0,1]
+__host__ __device__ static inline float u32_to_unit(uint32_t x) { return ((x >> 8) + 1) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------- GEMM descriptor (implemented in gemm.cu)
+// C[b][m][n] = epilogue( sum_kk A(b,m,kk) * W(b,n,kk) )
+//   A(b,m,kk) = A[b*a_bs + m*lda + (kk/kc)*tap_stride + kk%kc]   (bf16)  -> conv1d over time-major channels-last activations
+//   W(b,n,kk) = W[b*w_bs + n*ldw + kk]                            (bf16)
+struct GemmParams {
+    const bf16* A = nullptr; long lda = 0; int kc = 0; long tap_stride = 0; long a_bs = 0;
+    const bf16* W = nullptr; long ldw = 0; long w_bs = 0;
+    int M = 0, N = 0, K = 0, batch = 1;
+    const float* bias = nullptr;            // [N]
+    const float* bias2 = nullptr; long bias2_bs = 0;   // per-batch [N] added before act (e.g. time embedding)
+    int act = ACT_NONE; float act_param = 0.f; const float* act_alpha = nullptr;  // per-column alpha for snake
+    int glu = 0;                            // columns (2j,2j+1) = (gate,up): out[j] = silu(gate)*up ; output width N/2
+    const float* res = nullptr; long ldr = 0; long r_bs = 0;   // fp32 residual added after act
+    float out_scale = 1.f; int accumulate = 0;                   // outF = (accumulate? outF : 0) + scale*v
+    float* outF = nullptr; bf16* outB = nullptr; long ldc = 0; long c_bs = 0;
+    bf16* outB2 = nullptr; int act2 = ACT_NONE; float act2_param = 0.f; const float* act2_alpha = nullptr; long ldc2 = 0; long c2_bs = 0;
+    // transposed-conv scatter mask: column n belongs to phase n/ct_cout; output time = m*ct_u + phase - ct_pad must be in [0, ct_len)
+    int ct_u = 0, ct_cout = 0, ct_pad = 0, ct_len = 0;
+};
+void launch_gemm(const GemmParams& p, cudaStream_t st);
+
+// flash attention (attention.cu): o[b][t][h*64+d] = softmax_j(scale*(q.k + bias)) v
+struct AttnParams {
+    const bf16 *q = nullptr, *k = nullptr, *v = nullptr; long ldq = 0, ldk = 0, ldv = 0; long q_bs = 0, k_bs = 0, v_bs = 0;
+    bf16* o = nullptr; long ldo = 0; long o_bs = 0;
+    int T = 0, H = 0, batch = 1; int causal = 0; float scale = 0.125f;
+    const float* relbias = nullptr; long rb_ld = 0; long rb_hs = 0;  // bias[h*rb_hs + i*rb_ld + (T-1-i+j)]
+};
+void launch_attention(const AttnParams& p, cudaStream_t st);

@@ -1,0 +1,334 @@
+// C-ABI of libcbx_b200.so (see include/cbx_b200.h): engine lifecycle, checkpoint upload,
+// voice cache, T3 streams, S3Gen calls, PCM conversion.  No torch types, no CPU fallback.
+#include <cstring>
+#include "engine.h"
+
+using namespace dims;
+
+static thread_local std::string g_err;
+#define CBX_API_BEGIN try {
+#define CBX_API_END                                  \
+    return 0;                                        \
+    } catch (const std::exception& ex) {             \
+        g_err = ex.what();                           \
+        return 1;                                    \
+    } catch (...) {                                  \
+        g_err = "unknown error";                     \
+        return 1;                                    \
+    }
+
+namespace {
+
+struct StreamBridge {   // order engine-internal stream `in` after the caller's stream and back
+    cudaStream_t user, in; cudaEvent_t ev_in, ev_out;
+    StreamBridge(cudaStream_t u, cudaStream_t i, cudaEvent_t a, cudaEvent_t b) : user(u), in(i), ev_in(a), ev_out(b) {
+        CBX_CHECK(cudaEventRecord(ev_in, user));
+        CBX_CHECK(cudaStreamWaitEvent(in, ev_in, 0));
+    }
+    void finish() {
+        CBX_CHECK(cudaEventRecord(ev_out, in));
+        CBX_CHECK(cudaStreamWaitEvent(user, ev_out, 0));
+    }
+};
+
+__global__ void crossfade_pcm_kernel(const float* __restrict__ cur, long n, const float* __restrict__ prev, int fade_len, short* out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = cur[i];
+    if (prev && i < fade_len) {
+        // torch.linspace(0, 1, fade_len): t_i = i / (fade_len - 1)
+        float t = fade_len > 1 ? (float)i / (float)(fade_len - 1) : 0.f;
+        float a = t * 0.5f * 3.14159265358979323846f;
+        x = prev[i] * cosf(a) + x * sinf(a);
+    }
+    x = fminf(fmaxf(x, -1.f), 1.f) * 32767.f;
+    out[i] = (short)x;   // truncation toward zero, as torch .to(int16)
+}
+
+Lane& pick_lane(cbx_engine* e) {
+    std::lock_guard<std::mutex> g(e->lane_pick_mu);
+    Lane& L = *e->lanes[e->lane_rr % e->lanes.size()];
+    e->lane_rr++;
+    return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cbx_abi_version(void) { return CBX_ABI_VERSION; }
+const char* cbx_last_error(void) { return g_err.c_str(); }
+
+int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(cfg && out, "null argument");
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    CBX_REQUIRE(err == cudaSuccess && ndev > 0, "no CUDA device: libcbx_b200 has no CPU path");
+    CBX_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    CBX_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CBX_CHECK(cudaGetDeviceProperties(&prop, device));
+    CBX_REQUIRE(prop.major == 10, "libcbx_b200 is built for sm_100a only");
+    CBX_REQUIRE(cfg->t3_layers >= 1 && cfg->cfm_steps >= 1 && cfg->cfm_mid >= 1 && cfg->cfm_blocks >= 1 && cfg->enc_blocks >= 1 && cfg->up_blocks >= 1, "bad depth config");
+    CBX_REQUIRE(cfg->max_streams >= 1 && cfg->max_streams <= 64 && cfg->n_lanes >= 1 && cfg->n_voices >= 1, "bad capacity config");
+    CBX_REQUIRE(cfg->max_prompt_tokens >= 1 && cfg->max_s3_tokens >= 3 && 2 * (cfg->max_prompt_tokens + cfg->max_s3_tokens) <= NOISE_LEN, "bad s3gen capacity");
+    cbx_engine* e = new cbx_engine();
+    e->cfg = *cfg; e->device = device;
+    t3_build(e); flow_build(e); hift_build(e);
+    t3_alloc(e);
+    CBX_CHECK(cudaStreamCreateWithFlags(&e->t3_st, cudaStreamNonBlocking));
+    CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_in, cudaEventDisableTiming));
+    CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_out, cudaEventDisableTiming));
+    e->voices.resize(cfg->n_voices);
+    for (auto& v : e->voices) {
+        v.prefix = e->scratch<float>((long)T3_COND * T3_D);
+        v.prompt_token = e->scratch<int>(cfg->max_prompt_tokens);
+        v.prompt_feat = e->scratch<float>(2L * cfg->max_prompt_tokens * MEL);
+        v.spks = e->scratch<float>(MEL);
+    }
+    for (int i = 0; i < cfg->n_lanes; i++) { Lane* L = new Lane(); lane_alloc(e, *L); e->lanes.push_back(L); }
+    CBX_CHECK(cudaDeviceSynchronize());
+    *out = e;
+    CBX_API_END
+}
+
+int cbx_manifest_create(const cbx_config* cfg, cbx_engine** out) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(cfg && out, "null argument");
+    cbx_engine* e = new cbx_engine();
+    e->cfg = *cfg; e->dry = true;
+    t3_build(e); flow_build(e); hift_build(e);
+    *out = e;
+    CBX_API_END
+}
+
+void cbx_engine_destroy(cbx_engine* e) {
+    if (!e) return;
+    if (e->dry) { delete e; return; }
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : e->t3.step_graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& t : e->tensors) cudaFree(t.ptr);
+    for (void* p : e->scratch_allocs) cudaFree(p);
+    for (Lane* L : e->lanes) { cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
+    cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
+    delete e;
+}
+
+int cbx_tensor_count(cbx_engine* e) { return e ? (int)e->tensors.size() : -1; }
+
+int cbx_tensor_info(cbx_engine* e, int idx, char* name, int name_cap, int64_t* numel, int* dtype) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && idx >= 0 && idx < (int)e->tensors.size(), "tensor index out of range");
+    const TensorRec& t = e->tensors[idx];
+    CBX_REQUIRE((int)t.name.size() + 1 <= name_cap, "name buffer too small");
+    std::strcpy(name, t.name.c_str());
+    *numel = t.numel; *dtype = t.dtype;
+    CBX_API_END
+}
+
+int cbx_tensor_upload(cbx_engine* e, const char* name, const void* data_h, int64_t nbytes) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && name && data_h, "null argument");
+    auto it = e->index.find(name);
+    CBX_REQUIRE(it != e->index.end(), std::string("unknown tensor ") + name);
+    TensorRec& t = e->tensors[it->second];
+    const int64_t want = t.numel * (t.dtype == DT_F32 ? 4 : 2);
+    CBX_REQUIRE(nbytes == want, std::string("size mismatch for ") + name + ": got " + std::to_string(nbytes) + " want " + std::to_string(want));
+    CBX_CHECK(cudaSetDevice(e->device));
+    CBX_CHECK(cudaMemcpy(t.ptr, data_h, nbytes, cudaMemcpyHostToDevice));
+    t.loaded = true;
+    CBX_API_END
+}
+
+int cbx_finalize(cbx_engine* e) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e, "null engine");
+    for (auto& t : e->tensors) CBX_REQUIRE(t.loaded, "tensor not uploaded: " + t.name);
+    CBX_CHECK(cudaSetDevice(e->device));
+    flow_finalize(e, e->t3_st);
+    e->finalized = true;
+    CBX_API_END
+}
+
+int cbx_voice_put(cbx_engine* e, int voice, const float* speaker_emb_h, const int32_t* cond_tokens_h, int n_cond, float emotion_adv,
+                  const int32_t* prompt_token_h, int n_prompt, const float* prompt_feat_h, int n_feat, const float* xvector_h, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized, "engine not finalized");
+    CBX_REQUIRE(voice >= 0 && voice < e->cfg.n_voices, "voice slot out of range");
+    CBX_REQUIRE(n_prompt >= 1 && n_prompt <= e->cfg.max_prompt_tokens && n_feat == 2 * n_prompt, "prompt_feat must hold 2 mel frames per prompt token");
+    for (int i = 0; i < n_cond; i++) CBX_REQUIRE(cond_tokens_h[i] >= 0 && cond_tokens_h[i] < T3_V, "cond token out of range");
+    for (int i = 0; i < n_prompt; i++) CBX_REQUIRE(prompt_token_h[i] >= 0 && prompt_token_h[i] < F_V, "prompt token out of range");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->voice_mu);
+    std::lock_guard<std::mutex> g2(e->t3_mu);
+    Voice& v = e->voices[voice];
+    v.valid = false;
+    StreamBridge br((cudaStream_t)stream, e->t3_st, e->t3_ev_in, e->t3_ev_out);
+    t3_voice_prefix(e, v, speaker_emb_h, cond_tokens_h, n_cond, emotion_adv, e->t3_st);
+    float* xv; CBX_CHECK(cudaMalloc(&xv, F_SPK * 4));
+    CBX_CHECK(cudaMemcpyAsync(xv, xvector_h, F_SPK * 4, cudaMemcpyHostToDevice, e->t3_st));
+    CBX_CHECK(cudaMemcpyAsync(v.prompt_token, prompt_token_h, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, e->t3_st));
+    CBX_CHECK(cudaMemcpyAsync(v.prompt_feat, prompt_feat_h, (size_t)n_feat * MEL * 4, cudaMemcpyHostToDevice, e->t3_st));
+    launch_spk_affine(xv, F_SPK, e->flow.spk_w, e->flow.spk_b, v.spks, MEL, e->t3_st);
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    cudaFree(xv);
+    v.n_prompt = n_prompt; v.n_feat = n_feat; v.valid = true;
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_voice_drop(cbx_engine* e, int voice) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && voice >= 0 && voice < e->cfg.n_voices, "voice slot out of range");
+    std::lock_guard<std::mutex> g(e->voice_mu);
+    e->voices[voice].valid = false;
+    CBX_API_END
+}
+
+int cbx_t3_open(cbx_engine* e, int voice, const int32_t* text_ids_h, int n_text, float cfg_weight, float temperature, float repetition_penalty,
+                float min_p, float top_p, uint64_t seed, int max_new_tokens, int* slot_out, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && text_ids_h && slot_out, "bad argument");
+    for (int i = 0; i < n_text; i++) CBX_REQUIRE(text_ids_h[i] >= 0 && text_ids_h[i] < T3_TEXT_V, "text id out of range");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    StreamBridge br((cudaStream_t)stream, e->t3_st, e->t3_ev_in, e->t3_ev_out);
+    *slot_out = t3_open(e, voice, text_ids_h, n_text, cfg_weight, temperature, repetition_penalty, min_p, top_p, seed, max_new_tokens, e->t3_st);
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps, const float* noise_d, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && slots_h && n_steps >= 1, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    StreamBridge br((cudaStream_t)stream, e->t3_st, e->t3_ev_in, e->t3_ev_out);
+    t3_step(e, slots_h, n_slots, n_steps, noise_d, e->t3_st);
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_t3_poll(cbx_engine* e, int slot, int* n_generated, int* done, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && slot >= 0 && slot < e->cfg.max_streams, "slot out of range");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    T3SlotState s;
+    CBX_CHECK(cudaMemcpyAsync(&s, e->t3.slot_state + slot, sizeof(s), cudaMemcpyDeviceToHost, e->t3_st));
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    *n_generated = s.step; *done = s.done;
+    CBX_API_END
+}
+
+int cbx_t3_tokens(cbx_engine* e, int slot, int from, int count, int32_t* out_h, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && slot >= 0 && slot < e->cfg.max_streams && from >= 0 && count >= 0 && from + count <= e->t3.out_stride, "range error");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    if (count) CBX_CHECK(cudaMemcpyAsync(out_h, e->t3.out_tokens + (long)slot * e->t3.out_stride + from, (size_t)count * 4, cudaMemcpyDeviceToHost, e->t3_st));
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    CBX_API_END
+}
+
+int cbx_t3_logits(cbx_engine* e, int slot, float* out_h, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && slot >= 0 && slot < e->cfg.max_streams && out_h, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    CBX_CHECK(cudaMemcpy2DAsync(out_h, T3_V * 4, e->t3.logits + (long)slot * 2 * T3_VPAD, T3_VPAD * 4, T3_V * 4, 2, cudaMemcpyDeviceToHost, e->t3_st));
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    CBX_API_END
+}
+
+int cbx_t3_close(cbx_engine* e, int slot) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e, "null engine");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    t3_close(e, slot);
+    CBX_API_END
+}
+
+int cbx_flow_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, float* mel_out_d, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && tokens_h && mel_out_d, "bad argument");
+    CBX_REQUIRE(voice >= 0 && voice < e->cfg.n_voices && e->voices[voice].valid, "voice slot is empty");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = pick_lane(e);
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    const Voice& v = e->voices[voice];
+    flow_infer(e, L, v, tokens_h, n, L.st);
+    CBX_CHECK(cudaMemcpyAsync(mel_out_d, L.mel, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_hift_infer(cbx_engine* e, const float* mel_d, int frames, const float* cache_source_d, int64_t m, float* wav_out_d, float* source_out_d,
+                   const float* phase_h, const float* noise_d, uint64_t seed, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && mel_d && wav_out_d && source_out_d, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = pick_lane(e);
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    CBX_REQUIRE(frames >= 1 && frames <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
+    CBX_CHECK(cudaMemcpyAsync(L.mel, mel_d, (size_t)frames * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    hift_infer(e, L, frames, cache_source_d, m, wav_out_d, source_out_d, phase_h, noise_d, seed, L.st);
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, const float* cache_source_d, int64_t m, float* wav_out_d,
+                    float* source_out_d, float* mel_out_d, const float* phase_h, const float* noise_d, uint64_t seed, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && tokens_h && wav_out_d && source_out_d, "bad argument");
+    CBX_REQUIRE(voice >= 0 && voice < e->cfg.n_voices && e->voices[voice].valid, "voice slot is empty");
+    CBX_REQUIRE(n >= 3, "s3gen: needs at least 3 tokens (reference pads, src/tts_streaming.py:675-677)");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = pick_lane(e);
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    const Voice& v = e->voices[voice];
+    flow_infer(e, L, v, tokens_h, n, L.st);
+    if (mel_out_d) CBX_CHECK(cudaMemcpyAsync(mel_out_d, L.mel, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    hift_infer(e, L, 2 * n, cache_source_d, m, wav_out_d, source_out_d, phase_h, noise_d, seed, L.st);
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const float* prev_tail_d, int fade_len, int16_t* out_d, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && cur_d && out_d && n_out >= 0, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    if (n_out > 0) {
+        crossfade_pcm_kernel<<<cdiv(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cur_d, n_out, prev_tail_d, fade_len, out_d);
+        CBX_CHECK(cudaGetLastError());
+        e->gpu_launches += 1;
+    }
+    CBX_API_END
+}
+
+int64_t cbx_gpu_launches(cbx_engine* e) { return e ? e->gpu_launches : -1; }
+
+int cbx_op_gemm(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, void* stream) {
+    CBX_API_BEGIN
+    GemmParams g; g.A = (const bf16*)a; g.lda = K; g.kc = K; g.W = (const bf16*)w; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias; g.outF = out; g.ldc = N;
+    launch_gemm(g, (cudaStream_t)stream);
+    CBX_API_END
+}
+
+int cbx_op_attention(const void* qkv, void* out, int T, int H, int batch, int causal, void* stream) {
+    CBX_API_BEGIN
+    const long ld = 3L * H * 64;
+    AttnParams a; a.q = (const bf16*)qkv; a.k = a.q + H * 64; a.v = a.q + 2 * H * 64; a.ldq = a.ldk = a.ldv = ld; a.q_bs = a.k_bs = a.v_bs = (long)T * ld;
+    a.o = (bf16*)out; a.ldo = H * 64; a.o_bs = (long)T * H * 64; a.T = T; a.H = H; a.batch = batch; a.causal = causal; a.scale = 0.125f;
+    launch_attention(a, (cudaStream_t)stream);
+    CBX_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// S3Gen token->mel: UpsampleConformerEncoder + CausalConditionalCFM (10 Euler steps, CFG-batched
+// ConditionalDecoder).  Activations are time-major channels-last; every conv is an implicit GEMM over
+// zero-haloed bf16 buffers; residual streams stay fp32.  Host orchestration only.
+#include <cmath>
+#include "engine.h"
+
+using namespace dims;
+
+static Lin reg_lin(cbx_engine* e, const std::string& n, int N, int K, bool bias = true) {
+    Lin l; l.N = N; l.K = K;
+    l.w = e->reg<bf16>(n + ".w", DT_BF16, (long)N * K);
+    l.b = bias ? e->reg<float>(n + ".b", DT_F32, N) : nullptr;
+    return l;
+}
+static LNp reg_ln(cbx_engine* e, const std::string& n, int C) {
+    LNp l; l.g = e->reg<float>(n + ".g", DT_F32, C); l.b = e->reg<float>(n + ".b", DT_F32, C); return l;
+}
+
+void flow_build(cbx_engine* e) {
+    FlowModel& f = e->flow;
+    const cbx_config& c = e->cfg;
+    f.tok_emb = e->reg<float>("flow.tok_emb", DT_F32, (long)F_V * F_D);
+    f.spk_w = e->reg<float>("flow.spk.w", DT_F32, (long)MEL * F_SPK);
+    f.spk_b = e->reg<float>("flow.spk.b", DT_F32, MEL);
+    f.enc_proj = reg_lin(e, "flow.enc_proj", MEL, F_D);
+    f.embed = reg_lin(e, "flow.embed", F_D, F_D); f.embed_ln = reg_ln(e, "flow.embed_ln", F_D);
+    f.up_embed = reg_lin(e, "flow.up_embed", F_D, F_D); f.up_embed_ln = reg_ln(e, "flow.up_embed_ln", F_D);
+    f.pl1 = reg_lin(e, "flow.pl1", F_D, 4 * F_D); f.pl2 = reg_lin(e, "flow.pl2", F_D, 3 * F_D); f.upconv = reg_lin(e, "flow.upconv", F_D, 5 * F_D);
+    f.after_norm = reg_ln(e, "flow.after_norm", F_D);
+    auto conf = [&](const std::string& p) {
+        ConformerLayer l;
+        l.nm = reg_ln(e, p + "nm", F_D); l.nf = reg_ln(e, p + "nf", F_D);
+        l.qkv4 = reg_lin(e, p + "qkv4", 4 * F_D, F_D); l.pos = reg_lin(e, p + "pos", F_D, F_D, false); l.out = reg_lin(e, p + "out", F_D, F_D);
+        l.w1 = reg_lin(e, p + "w1", F_FFN, F_D); l.w2 = reg_lin(e, p + "w2", F_D, F_FFN);
+        return l;
+    };
+    for (int i = 0; i < c.enc_blocks; i++) f.enc.push_back(conf("flow.enc" + std::to_string(i) + "."));
+    for (int i = 0; i < c.up_blocks; i++) f.up.push_back(conf("flow.up" + std::to_string(i) + "."));
+    f.t1 = reg_lin(e, "cfm.t1", C_TDIM, C_IN); f.t2 = reg_lin(e, "cfm.t2", C_TDIM, C_TDIM);
+    const int nres = c.cfm_mid + 2;
+    for (int r = 0; r < nres; r++) {
+        std::string p = "cfm.r" + std::to_string(r) + ".";
+        int cin = r == 0 ? C_IN : (r == nres - 1 ? 2 * C_CH : C_CH);
+        ResnetP rp; rp.cin = cin;
+        f.tmlp.push_back(reg_lin(e, p + "tmlp", C_CH, C_TDIM));
+        rp.c1 = reg_lin(e, p + "c1", C_CH, 3 * cin); rp.n1 = reg_ln(e, p + "n1", C_CH);
+        rp.c2 = reg_lin(e, p + "c2", C_CH, 3 * C_CH); rp.n2 = reg_ln(e, p + "n2", C_CH);
+        rp.res = reg_lin(e, p + "res", C_CH, cin);
+        f.resnets.push_back(rp);
+        for (int j = 0; j < c.cfm_blocks; j++) {
+            std::string q = p + "t" + std::to_string(j) + ".";
+            TfmP t; t.n1 = reg_ln(e, q + "n1", C_CH); t.qkv = reg_lin(e, q + "qkv", 3 * C_INNER, C_CH, false);
+            t.out = reg_lin(e, q + "out", C_CH, C_INNER); t.n3 = reg_ln(e, q + "n3", C_CH);
+            t.ff0 = reg_lin(e, q + "ff0", C_FF, C_CH); t.ff2 = reg_lin(e, q + "ff2", C_CH, C_FF);
+            f.tfms.push_back(t);
+        }
+    }
+    f.down_conv = reg_lin(e, "cfm.down_conv", C_CH, 3 * C_CH); f.up_conv = reg_lin(e, "cfm.up_conv", C_CH, 3 * C_CH);
+    f.final_conv = reg_lin(e, "cfm.final_conv", C_CH, 3 * C_CH); f.final_ln = reg_ln(e, "cfm.final_ln", C_CH);
+    f.final_proj = reg_lin(e, "cfm.final_proj", MEL, C_CH);
+    f.noise = e->reg<float>("cfm.noise", DT_F32, (long)NOISE_LEN * MEL);
+    f.tproj = e->scratch<float>((long)nres * c.cfm_steps * C_CH);
+}
+
+// plain linear / conv GEMM helper.  A rows are `lda` apart; `taps` taps of `kc` channels `tap_stride` apart.
+static GemmParams mk(const Lin& l, const bf16* A, long lda, int M, int kc, long tap_stride) {
+    GemmParams g; g.A = A; g.lda = lda; g.kc = kc; g.tap_stride = tap_stride; g.W = l.w; g.ldw = l.K; g.M = M; g.N = l.N; g.K = l.K; g.bias = l.b;
+    return g;
+}
+
+void flow_finalize(cbx_engine* e, cudaStream_t st) {
+    FlowModel& f = e->flow;
+    const int n = e->cfg.cfm_steps, half = C_IN / 2;
+    // cosine schedule and the fp32 recurrence of solve_euler (t += dt; dt = t_span[k+1] - t)
+    std::vector<float> ts(n + 1);
+    for (int i = 0; i <= n; i++) ts[i] = 1.f - cosf((float)i / n * 0.5f * 3.14159265358979323846f);
+    f.t_span.assign(2 * n, 0.f);   // [t_k..., dt_k...]
+    float t = ts[0], dt = ts[1] - ts[0];
+    for (int k = 0; k < n; k++) {
+        f.t_span[k] = t; f.t_span[n + k] = dt;
+        t = t + dt;
+        if (k + 1 < n) dt = ts[k + 2] - t;
+    }
+    std::vector<float> sin_h((size_t)n * C_IN);
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < half; i++) {
+            float fr = expf((float)i * -(logf(10000.f) / (half - 1)));
+            float a = 1000.f * f.t_span[k] * fr;
+            sin_h[(size_t)k * C_IN + i] = sinf(a);
+            sin_h[(size_t)k * C_IN + half + i] = cosf(a);
+        }
+    float* sin_d = e->scratch<float>((long)n * C_IN);
+    bf16* sin_b = e->scratch<bf16>((long)n * C_IN);
+    bf16* h1 = e->scratch<bf16>((long)n * C_TDIM);
+    bf16* h2 = e->scratch<bf16>((long)n * C_TDIM);
+    CBX_CHECK(cudaMemcpyAsync(sin_d, sin_h.data(), sin_h.size() * 4, cudaMemcpyHostToDevice, st));
+    launch_f32_to_bf16_rows(sin_d, C_IN, sin_b, C_IN, n, C_IN, ACT_NONE, 0.f, st);
+    GemmParams g = mk(f.t1, sin_b, C_IN, n, C_IN, 0); g.act = ACT_SILU; g.outB = h1; g.ldc = C_TDIM; launch_gemm(g, st);
+    g = mk(f.t2, h1, C_TDIM, n, C_TDIM, 0); g.act = ACT_MISH; g.outB = h2; g.ldc = C_TDIM; launch_gemm(g, st);   // resnets consume mish(temb)
+    for (size_t r = 0; r < f.tmlp.size(); r++) {
+        g = mk(f.tmlp[r], h2, C_TDIM, n, C_TDIM, 0); g.outF = f.tproj + (long)r * n * C_CH; g.ldc = C_CH; launch_gemm(g, st);
+    }
+    CBX_CHECK(cudaStreamSynchronize(st));
+}
+
+static constexpr int CH = 2;   // causal halo rows (k=3)
+
+void lane_alloc(cbx_engine* e, Lane& L) {
+    const cbx_config& c = e->cfg;
+    const long Tt = c.max_prompt_tokens + c.max_s3_tokens, T = 2 * Tt, Tg = 2L * c.max_s3_tokens;
+    CBX_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    CBX_CHECK(cudaEventCreateWithFlags(&L.ev_in, cudaEventDisableTiming));
+    CBX_CHECK(cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
+    L.tok = e->scratch<int>(Tt);
+    L.e_in = e->scratch<bf16>(T * F_D); L.e_xb = e->scratch<bf16>((T + 8) * F_D); L.e_y1 = e->scratch<bf16>((T + 8) * F_D);
+    L.e_xn = e->scratch<bf16>(T * F_D); L.e_qkv = e->scratch<bf16>(T * 4 * F_D); L.e_pos = e->scratch<bf16>(2 * T * F_D); L.e_p = e->scratch<bf16>(2 * T * F_D);
+    L.e_o = e->scratch<bf16>(T * F_D); L.e_ff = e->scratch<bf16>(T * F_FFN); L.e_up = e->scratch<bf16>((T + 8) * F_D); L.e_upc = e->scratch<bf16>(T * F_D);
+    L.e_tmp = e->scratch<float>(T * F_D); L.e_x = e->scratch<float>(T * F_D); L.e_bd = e->scratch<float>((long)F_H * T * 2 * T);
+    L.mu = e->scratch<float>(T * MEL); L.cond = e->scratch<float>(T * MEL); L.x = e->scratch<float>(T * MEL); L.v = e->scratch<float>(2 * T * MEL);
+    const long TH = T + CH;
+    L.c_in = e->scratch<bf16>(2 * TH * C_IN); L.c_hb = e->scratch<bf16>(2 * TH * C_CH); L.c_inb = e->scratch<bf16>(2 * TH * C_CH);
+    L.c_upin = e->scratch<bf16>(2 * TH * 2 * C_CH); L.c_xn = e->scratch<bf16>(2 * T * C_CH); L.c_qkv = e->scratch<bf16>(2 * T * 3 * C_INNER);
+    L.c_o = e->scratch<bf16>(2 * T * C_INNER); L.c_ff = e->scratch<bf16>(2 * T * C_FF); L.c_fb = e->scratch<bf16>(2 * T * C_CH);
+    L.c_tmp = e->scratch<float>(2 * T * C_CH); L.c_tmp2 = e->scratch<float>(2 * T * C_CH); L.c_h = e->scratch<float>(2 * T * C_CH);
+    // hift
+    const long HH = H_HALO;
+    L.mel = e->scratch<float>(Tg * MEL); L.h_mel = e->scratch<bf16>((Tg + 2 * HH) * MEL);
+    L.h_f0a = e->scratch<bf16>((Tg + 2 * HH) * H_F0CH); L.h_f0b = e->scratch<bf16>((Tg + 2 * HH) * H_F0CH);
+    L.h_f0 = e->scratch<float>(Tg); L.h_cum = e->scratch<double>(Tg * H_NHARM); L.h_s = e->scratch<float>(Tg * H_UP);
+    const long F = 120 * Tg + 1;
+    L.h_stft = e->scratch<bf16>((F + 2 * HH) * H_NSRC_PAD);
+    long tlen[4] = {Tg, 8 * Tg, 40 * Tg, F};
+    for (int i = 0; i < 4; i++) L.h_xb[i] = e->scratch<bf16>((tlen[i] + 2 * HH) * (H_BASE >> i));
+    for (int i = 0; i < 3; i++) {
+        long t = tlen[i + 1], ch = H_BASE >> (i + 1);
+        L.h_x[i] = e->scratch<float>(t * ch); L.h_r[i] = e->scratch<float>(t * ch); L.h_acc[i] = e->scratch<float>(t * ch); L.h_si[i] = e->scratch<float>(t * ch);
+        L.h_a[i] = e->scratch<bf16>((t + 2 * HH) * ch); L.h_b[i] = e->scratch<bf16>((t + 2 * HH) * ch);
+    }
+    L.h_post = e->scratch<float>(F * H_NSRC);
+    L.h_phase = e->scratch<float>(16);
+}
+
+// ---------------------------------------------------------------------------------------------- encoder
+static void conformer_layer(cbx_engine* e, Lane& L, const ConformerLayer& l, int T, cudaStream_t st) {
+    NormParams n; n.in = L.e_x; n.ld_in = F_D; n.rows = T; n.C = F_D; n.gain = l.nm.g; n.bias = l.nm.b; n.eps = 1e-12f; n.outB = L.e_xn; n.ld_outB = F_D;
+    launch_norm(n, st);
+    GemmParams g = mk(l.qkv4, L.e_xn, F_D, T, F_D, 0); g.outB = L.e_qkv; g.ldc = 4 * F_D; launch_gemm(g, st);        // [q+u | q+v | k | v]
+    g = mk(l.pos, L.e_pos, F_D, 2 * T - 1, F_D, 0); g.outB = L.e_p; g.ldc = F_D; launch_gemm(g, st);
+    const long ldbd = 2L * T;
+    GemmParams b; b.A = L.e_qkv + F_D; b.lda = 4 * F_D; b.kc = 64; b.a_bs = 64; b.W = L.e_p; b.ldw = F_D; b.w_bs = 64; b.M = T; b.N = 2 * T - 1; b.K = 64;
+    b.batch = F_H; b.outF = L.e_bd; b.ldc = ldbd; b.c_bs = (long)T * ldbd;
+    launch_gemm(b, st);
+    AttnParams a; a.q = L.e_qkv; a.k = L.e_qkv + 2 * F_D; a.v = L.e_qkv + 3 * F_D; a.ldq = a.ldk = a.ldv = 4 * F_D; a.o = L.e_o; a.ldo = F_D;
+    a.T = T; a.H = F_H; a.batch = 1; a.scale = 0.125f; a.relbias = L.e_bd; a.rb_ld = ldbd; a.rb_hs = (long)T * ldbd;
+    launch_attention(a, st);
+    g = mk(l.out, L.e_o, F_D, T, F_D, 0); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
+    n.gain = l.nf.g; n.bias = l.nf.b; launch_norm(n, st);
+    g = mk(l.w1, L.e_xn, F_D, T, F_D, 0); g.act = ACT_SILU; g.outB = L.e_ff; g.ldc = F_FFN; launch_gemm(g, st);
+    g = mk(l.w2, L.e_ff, F_FFN, T, F_FFN, 0); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
+    e->gpu_launches += 9;
+}
+
+static void embed_stage(cbx_engine* e, Lane& L, const Lin& lin, const LNp& ln, const bf16* in, int T, cudaStream_t st) {
+    GemmParams g = mk(lin, in, F_D, T, F_D, 0); g.outF = L.e_tmp; g.ldc = F_D; launch_gemm(g, st);
+    NormParams n; n.in = L.e_tmp; n.ld_in = F_D; n.rows = T; n.C = F_D; n.gain = ln.g; n.bias = ln.b; n.eps = 1e-5f; n.out_scale = sqrtf((float)F_D);
+    n.outF = L.e_x; n.ld_outF = F_D; n.outB = L.e_xb; n.ld_outB = F_D;
+    launch_norm(n, st);
+    launch_relpos_table(L.e_pos, T, F_D, st);
+    e->gpu_launches += 3;
+}
+
+static void encoder(cbx_engine* e, Lane& L, int Tt, cudaStream_t st) {
+    FlowModel& f = e->flow;
+    launch_gather_rows_bf16(f.tok_emb, L.tok, Tt, F_D, L.e_in, F_D, st);
+    embed_stage(e, L, f.embed, f.embed_ln, L.e_in, Tt, st);
+    // PreLookaheadLayer: right-pad 3 -> conv k4 -> leaky_relu -> left-pad 2 -> conv k3 -> + x
+    CBX_CHECK(cudaMemsetAsync(L.e_xb + (long)Tt * F_D, 0, 3L * F_D * 2, st));
+    GemmParams g = mk(f.pl1, L.e_xb, F_D, Tt, F_D, F_D); g.act = ACT_LRELU; g.act_param = 0.01f; g.outB = L.e_y1 + 2 * F_D; g.ldc = F_D; launch_gemm(g, st);
+    CBX_CHECK(cudaMemsetAsync(L.e_y1, 0, 2L * F_D * 2, st));
+    g = mk(f.pl2, L.e_y1, F_D, Tt, F_D, F_D); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
+    for (auto& l : f.enc) conformer_layer(e, L, l, Tt, st);
+    // Upsample1D: nearest x2 -> left-pad 4 -> conv k5
+    const int T = 2 * Tt;
+    CBX_CHECK(cudaMemsetAsync(L.e_up, 0, 4L * F_D * 2, st));
+    launch_upsample2(L.e_x, L.e_up + 4 * F_D, F_D, Tt, F_D, st);
+    g = mk(f.upconv, L.e_up, F_D, T, F_D, F_D); g.outB = L.e_upc; g.ldc = F_D; launch_gemm(g, st);
+    embed_stage(e, L, f.up_embed, f.up_embed_ln, L.e_upc, T, st);
+    for (auto& l : f.up) conformer_layer(e, L, l, T, st);
+    NormParams n; n.in = L.e_x; n.ld_in = F_D; n.rows = T; n.C = F_D; n.gain = f.after_norm.g; n.bias = f.after_norm.b; n.eps = 1e-5f; n.outB = L.e_xn; n.ld_outB = F_D;
+    launch_norm(n, st);
+    g = mk(f.enc_proj, L.e_xn, F_D, T, F_D, 0); g.outF = L.mu; g.ldc = MEL; launch_gemm(g, st);
+    e->gpu_launches += 7;
+}
+
+// ---------------------------------------------------------------------------------------------- estimator
+// all estimator tensors are [2][T(+halo)][C]; batch stride passed explicitly
+static void tfm_block(cbx_engine* e, Lane& L, const TfmP& t, int T, cudaStream_t st) {
+    const long bs = (long)T * C_CH;
+    NormParams n; n.in = L.c_h; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = 2; n.C = C_CH; n.gain = t.n1.g; n.bias = t.n1.b; n.eps = 1e-5f;
+    n.outB = L.c_xn; n.ld_outB = C_CH; n.outB_bs = bs;
+    launch_norm(n, st);
+    GemmParams g = mk(t.qkv, L.c_xn, C_CH, 2 * T, C_CH, 0); g.outB = L.c_qkv; g.ldc = 3 * C_INNER; launch_gemm(g, st);
+    AttnParams a; a.q = L.c_qkv; a.k = L.c_qkv + C_INNER; a.v = L.c_qkv + 2 * C_INNER; a.ldq = a.ldk = a.ldv = 3 * C_INNER;
+    a.q_bs = a.k_bs = a.v_bs = (long)T * 3 * C_INNER; a.o = L.c_o; a.ldo = C_INNER; a.o_bs = (long)T * C_INNER; a.T = T; a.H = 8; a.batch = 2; a.scale = 0.125f;
+    launch_attention(a, st);
+    g = mk(t.out, L.c_o, C_INNER, 2 * T, C_INNER, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
+    n.gain = t.n3.g; n.bias = t.n3.b; launch_norm(n, st);
+    g = mk(t.ff0, L.c_xn, C_CH, 2 * T, C_CH, 0); g.act = ACT_GELU; g.outB = L.c_ff; g.ldc = C_FF; launch_gemm(g, st);
+    g = mk(t.ff2, L.c_ff, C_FF, 2 * T, C_FF, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
+    e->gpu_launches += 7;
+}
+
+// resnet: in = haloed bf16 [2][CH+T][cin] -> L.c_h fp32 [2][T][256]
+static void resnet(cbx_engine* e, Lane& L, const ResnetP& r, const float* tproj, const bf16* in, int T, cudaStream_t st) {
+    const long TH = T + CH, bs = (long)T * C_CH;
+    GemmParams g = mk(r.c1, in, r.cin, T, r.cin, r.cin); g.batch = 2; g.a_bs = TH * r.cin; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = 2; n.C = C_CH; n.gain = r.n1.g; n.bias = r.n1.b; n.eps = 1e-5f; n.act = ACT_MISH;
+    n.add = tproj; n.add_bs = 0; n.outB = L.c_hb + CH * C_CH; n.ld_outB = C_CH; n.outB_bs = TH * C_CH;
+    launch_norm(n, st);
+    g = mk(r.c2, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    NormParams n2; n2.in = L.c_tmp; n2.ld_in = C_CH; n2.in_bs = bs; n2.rows = T; n2.batch = 2; n2.C = C_CH; n2.gain = r.n2.g; n2.bias = r.n2.b; n2.eps = 1e-5f; n2.act = ACT_MISH;
+    n2.outF = L.c_tmp2; n2.ld_outF = C_CH; n2.outF_bs = bs;
+    launch_norm(n2, st);
+    g = mk(r.res, in + CH * r.cin, r.cin, T, r.cin, 0); g.batch = 2; g.a_bs = TH * r.cin; g.res = L.c_tmp2; g.ldr = C_CH; g.r_bs = bs; g.outF = L.c_h; g.ldc = C_CH; g.c_bs = bs;
+    launch_gemm(g, st);
+    e->gpu_launches += 5;
+}
+
+static void to_bf16_haloed(cbx_engine* e, Lane& L, bf16* dst, int ld, int col0, int T, cudaStream_t st) {
+    // L.c_h fp32 [2][T][256] -> dst [2][CH+T][ld] columns [col0, col0+256)
+    for (int b = 0; b < 2; b++)
+        launch_f32_to_bf16_rows(L.c_h + (long)b * T * C_CH, C_CH, dst + ((long)b * (T + CH) + CH) * ld + col0, ld, T, C_CH, ACT_NONE, 0.f, st);
+    e->gpu_launches += 2;
+}
+
+static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) {
+    FlowModel& f = e->flow;
+    const int nb = e->cfg.cfm_blocks, nmid = e->cfg.cfm_mid, nsteps = e->cfg.cfm_steps, nres = nmid + 2;
+    const long TH = T + CH, bs = (long)T * C_CH;
+    auto tp = [&](int r) { return f.tproj + ((long)r * nsteps + step) * C_CH; };
+    // down stage
+    resnet(e, L, f.resnets[0], tp(0), L.c_in, T, st);
+    for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[j], T, st);
+    to_bf16_haloed(e, L, L.c_upin, 2 * C_CH, C_CH, T, st);          // skip connection -> channels [256,512) of the up-stage input
+    to_bf16_haloed(e, L, L.c_hb, C_CH, 0, T, st);
+    GemmParams g = mk(f.down_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
+    launch_gemm(g, st);
+    for (int i = 0; i < nmid; i++) {
+        resnet(e, L, f.resnets[1 + i], tp(1 + i), L.c_inb, T, st);
+        for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[(1 + i) * nb + j], T, st);
+        if (i + 1 < nmid) to_bf16_haloed(e, L, L.c_inb, C_CH, 0, T, st);
+        else to_bf16_haloed(e, L, L.c_upin, 2 * C_CH, 0, T, st);
+    }
+    resnet(e, L, f.resnets[nres - 1], tp(nres - 1), L.c_upin, T, st);
+    for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[(nres - 1) * nb + j], T, st);
+    to_bf16_haloed(e, L, L.c_hb, C_CH, 0, T, st);
+    g = mk(f.up_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
+    launch_gemm(g, st);
+    g = mk(f.final_conv, L.c_inb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = 2; n.C = C_CH; n.gain = f.final_ln.g; n.bias = f.final_ln.b; n.eps = 1e-5f; n.act = ACT_MISH;
+    n.outB = L.c_fb; n.ld_outB = C_CH; n.outB_bs = bs;
+    launch_norm(n, st);
+    g = mk(f.final_proj, L.c_fb, C_CH, 2 * T, C_CH, 0); g.outF = L.v; g.ldc = MEL; launch_gemm(g, st);
+    e->gpu_launches += 5;
+}
+
+void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st) {
+    FlowModel& f = e->flow;
+    const cbx_config& c = e->cfg;
+    CBX_REQUIRE(n >= 1 && n <= c.max_s3_tokens, "s3gen: token count out of range");
+    const int Tt = v.n_prompt + n, T = 2 * Tt, L1 = v.n_feat;
+    CBX_REQUIRE(L1 <= T, "s3gen: prompt_feat longer than the encoded sequence");
+    CBX_REQUIRE(T <= NOISE_LEN, "s3gen: sequence exceeds the CFM noise buffer");
+    for (int i = 0; i < n; i++) CBX_REQUIRE(tokens_h[i] >= 0 && tokens_h[i] < F_V, "s3gen: token id out of range");
+    CBX_CHECK(cudaMemcpyAsync(L.tok, v.prompt_token, (size_t)v.n_prompt * 4, cudaMemcpyDeviceToDevice, st));
+    CBX_CHECK(cudaMemcpyAsync(L.tok + v.n_prompt, tokens_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CBX_CHECK(cudaStreamSynchronize(st));   // tokens_h may be a transient host buffer
+    encoder(e, L, Tt, st);
+    CBX_CHECK(cudaMemsetAsync(L.cond, 0, (size_t)T * MEL * 4, st));
+    CBX_CHECK(cudaMemcpyAsync(L.cond, v.prompt_feat, (size_t)L1 * MEL * 4, cudaMemcpyDeviceToDevice, st));
+    CBX_CHECK(cudaMemcpyAsync(L.x, f.noise, (size_t)T * MEL * 4, cudaMemcpyDeviceToDevice, st));
+    // causal halos of the estimator inputs
+    const long TH = T + CH;
+    for (int b = 0; b < 2; b++) {
+        CBX_CHECK(cudaMemsetAsync(L.c_in + b * TH * C_IN, 0, (size_t)CH * C_IN * 2, st));
+        CBX_CHECK(cudaMemsetAsync(L.c_hb + b * TH * C_CH, 0, (size_t)CH * C_CH * 2, st));
+        CBX_CHECK(cudaMemsetAsync(L.c_inb + b * TH * C_CH, 0, (size_t)CH * C_CH * 2, st));
+        CBX_CHECK(cudaMemsetAsync(L.c_upin + b * TH * 2 * C_CH, 0, (size_t)CH * 2 * C_CH * 2, st));
+    }
+    const int ns = c.cfm_steps;
+    for (int k = 0; k < ns; k++) {
+        launch_pack_cfm_input(L.x, L.mu, v.spks, L.cond, L.c_in + CH * C_IN, TH * C_IN, T, MEL, st);
+        estimator(e, L, T, k, st);
+        launch_euler_update(L.x, L.v, (long)T * MEL, (long)T * MEL, f.t_span[ns + k], c.cfm_cfg_rate, st);
+        e->gpu_launches += 2;
+    }
+    CBX_CHECK(cudaMemcpyAsync(L.mel, L.x + (long)L1 * MEL, (size_t)(T - L1) * MEL * 4, cudaMemcpyDeviceToDevice, st));
+}

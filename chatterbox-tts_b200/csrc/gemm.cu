@@ -1,0 +1,215 @@
+// bf16 GEMM / implicit-GEMM conv1d with fused epilogues (sm_100a).
+// Baseline tensor path: mma.sync m16n8k16 fed by a 4-stage cp.async ring.  The tcgen05/TMA
+// variant (gemm_tc.cu) replaces it for the large CFM / HiFT shapes once validated against this one.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BK = 32;
+constexpr int STAGES = 4;
+
+template <int BM, int BN, int WM, int WN>  // WM: m16 tiles per warp, WN: n8 tiles per warp (even)
+struct Cfg {
+    static constexpr int WARPS_M = BM / (16 * WM);
+    static constexpr int WARPS_N = BN / (8 * WN);
+    static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES);
+};
+
+// 64-byte rows (BK=32 bf16), 16B chunk index XOR-swizzled by (row>>1)&3 -> conflict-free ldmatrix
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void epilogue_pair(const GemmParams& p, int b, int m, int n, float v0, float v1) {
+    // n is even; handles columns n, n+1 of row m
+    if (m >= p.M || n >= p.N) return;
+    const bool has1 = (n + 1) < p.N;
+    if (p.ct_u) {
+        int ph = n / p.ct_cout;
+        int t = m * p.ct_u + ph - p.ct_pad;
+        if (t < 0 || t >= p.ct_len) return;
+    }
+    if (p.bias) { v0 += p.bias[n]; if (has1) v1 += p.bias[n + 1]; }
+    if (p.bias2) { const float* b2 = p.bias2 + (long)b * p.bias2_bs; v0 += b2[n]; if (has1) v1 += b2[n + 1]; }
+    if (p.glu) {
+        float g = v0 / (1.f + expf(-v0)) * v1;
+        long o = (long)b * p.c_bs + (long)m * p.ldc + (n >> 1);
+        if (p.outB) p.outB[o] = __float2bfloat16(g);
+        if (p.outF) p.outF[o] = g;
+        return;
+    }
+    if (p.act) {
+        float a0 = p.act_alpha ? p.act_alpha[n] : p.act_param;
+        float a1 = (p.act_alpha && has1) ? p.act_alpha[n + 1] : p.act_param;
+        v0 = act_apply(p.act, v0, a0);
+        v1 = act_apply(p.act, v1, a1);
+    }
+    if (p.res) {
+        const float* r = p.res + (long)b * p.r_bs + (long)m * p.ldr + n;
+        v0 += r[0]; if (has1) v1 += r[1];
+    }
+    long o = (long)b * p.c_bs + (long)m * p.ldc + n;
+    if (p.outF) {
+        float w0 = p.out_scale * v0, w1 = p.out_scale * v1;
+        if (p.accumulate) { w0 += p.outF[o]; if (has1) w1 += p.outF[o + 1]; }
+        p.outF[o] = w0; if (has1) p.outF[o + 1] = w1;
+        v0 = w0; v1 = w1;
+    } else {
+        v0 *= p.out_scale; v1 *= p.out_scale;
+    }
+    if (p.outB) {
+        if (has1 && ((o & 1) == 0)) *reinterpret_cast<uint32_t*>(p.outB + o) = pack_bf16(v0, v1);
+        else { p.outB[o] = __float2bfloat16(v0); if (has1) p.outB[o + 1] = __float2bfloat16(v1); }
+    }
+    if (p.outB2) {
+        float a0 = p.act2_alpha ? p.act2_alpha[n] : p.act2_param;
+        float a1 = (p.act2_alpha && has1) ? p.act2_alpha[n + 1] : p.act2_param;
+        long o2 = (long)b * p.c2_bs + (long)m * p.ldc2 + n;
+        float u0 = act_apply(p.act2, v0, a0), u1 = act_apply(p.act2, v1, a1);
+        if (has1 && ((o2 & 1) == 0)) *reinterpret_cast<uint32_t*>(p.outB2 + o2) = pack_bf16(u0, u1);
+        else { p.outB2[o2] = __float2bfloat16(u0); if (has1) p.outB2[o2 + 1] = __float2bfloat16(u1); }
+    }
+}
+
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__(Cfg<BM, BN, WM, WN>::THREADS) gemm_mma_kernel(const GemmParams p) {
+    using C = Cfg<BM, BN, WM, WN>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const bf16* Ab = p.A + (long)b * p.a_bs;
+    const bf16* Wb = p.W + (long)b * p.w_bs;
+    const uint32_t sbase = smem_u32(smem);
+
+    constexpr int A_CH = BM * 4 / C::THREADS;  // 16B chunks per thread per stage
+    constexpr int B_CH = BN * 4 / C::THREADS;
+    static_assert(A_CH >= 1 && B_CH >= 1, "tile too small for thread count");
+    // per-thread loader state
+    const bf16* a_row[A_CH]; int a_tap[A_CH], a_ci[A_CH]; bool a_ok[A_CH];
+    const bf16* w_row[B_CH]; bool w_ok[B_CH];
+#pragma unroll
+    for (int i = 0; i < A_CH; i++) {
+        int c = tid + i * C::THREADS, row = c >> 2, ch = c & 3;
+        int m = m0 + row;
+        a_ok[i] = m < p.M;
+        a_row[i] = Ab + (long)(a_ok[i] ? m : 0) * p.lda;
+        int kk = ch * 8;
+        a_tap[i] = kk / p.kc; a_ci[i] = kk % p.kc;
+    }
+#pragma unroll
+    for (int i = 0; i < B_CH; i++) {
+        int c = tid + i * C::THREADS, row = c >> 2;
+        int n = n0 + row;
+        w_ok[i] = n < p.N;
+        w_row[i] = Wb + (long)(w_ok[i] ? n : 0) * p.ldw;
+    }
+    const int KT = (p.K + BK - 1) / BK;
+
+    auto load_stage = [&](int kt, int stage) {
+        uint32_t sa = sbase + stage * (C::A_BYTES + C::B_BYTES), sb = sa + C::A_BYTES;
+#pragma unroll
+        for (int i = 0; i < A_CH; i++) {
+            int c = tid + i * C::THREADS, row = c >> 2, ch = c & 3;
+            int kk = kt * BK + ch * 8;
+            bool ok = a_ok[i] && kk < p.K;
+            const bf16* src = a_row[i] + (long)a_tap[i] * p.tap_stride + a_ci[i];
+            cp_async16(sa + swz(row, ch), ok ? src : Ab, ok ? 16 : 0);
+            a_ci[i] += BK;
+            while (a_ci[i] >= p.kc) { a_ci[i] -= p.kc; a_tap[i]++; }
+        }
+#pragma unroll
+        for (int i = 0; i < B_CH; i++) {
+            int c = tid + i * C::THREADS, row = c >> 2, ch = c & 3;
+            int kk = kt * BK + ch * 8;
+            bool ok = w_ok[i] && kk < p.K;
+            cp_async16(sb + swz(row, ch), ok ? (w_row[i] + kk) : Wb, ok ? 16 : 0);
+        }
+    };
+
+    float acc[WM][WN][4];
+#pragma unroll
+    for (int i = 0; i < WM; i++)
+#pragma unroll
+        for (int j = 0; j < WN; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[i][j][r] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk, nk % STAGES);
+            cp_async_commit();
+        }
+        const int stage = kt % STAGES;
+        const uint32_t sa = sbase + stage * (C::A_BYTES + C::B_BYTES), sb = sa + C::A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+            uint32_t af[WM][4];
+#pragma unroll
+            for (int i = 0; i < WM; i++) {
+                int row = wm * (16 * WM) + i * 16 + (lane & 15);
+                ldmatrix_x4(af[i], sa + swz(row, ks * 2 + (lane >> 4)));
+            }
+#pragma unroll
+            for (int j = 0; j < WN; j += 2) {
+                uint32_t bfr[4];
+                int row = wn * (8 * WN) + j * 8 + (lane & 7) + ((lane >> 4) << 3);
+                ldmatrix_x4(bfr, sb + swz(row, ks * 2 + ((lane >> 3) & 1)));
+#pragma unroll
+                for (int i = 0; i < WM; i++) {
+                    mma_bf16(acc[i][j], af[i], bfr[0], bfr[1]);
+                    mma_bf16(acc[i][j + 1], af[i], bfr[2], bfr[3]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < WM; i++)
+#pragma unroll
+        for (int j = 0; j < WN; j++) {
+            int m = m0 + wm * (16 * WM) + i * 16 + g;
+            int n = n0 + wn * (8 * WN) + j * 8 + tg * 2;
+            epilogue_pair(p, b, m, n, acc[i][j][0], acc[i][j][1]);
+            epilogue_pair(p, b, m + 8, n, acc[i][j][2], acc[i][j][3]);
+        }
+}
+
+template <int BM, int BN, int WM, int WN>
+void launch_cfg(const GemmParams& p, cudaStream_t st) {
+    using C = Cfg<BM, BN, WM, WN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN), p.batch);
+    gemm_mma_kernel<BM, BN, WM, WN><<<grid, C::THREADS, C::SMEM, st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void launch_gemm(const GemmParams& p, cudaStream_t st) {
+    CBX_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.batch > 0, "gemm: empty problem");
+    CBX_REQUIRE(p.kc % 8 == 0 && p.K % 8 == 0 && p.lda % 8 == 0 && p.ldw % 8 == 0 && p.tap_stride % 8 == 0 &&
+                p.a_bs % 8 == 0 && p.w_bs % 8 == 0, "gemm: operands must be 16-byte aligned per 8-element chunk");
+    CBX_REQUIRE(((uintptr_t)p.A & 15) == 0 && ((uintptr_t)p.W & 15) == 0, "gemm: base pointers must be 16-byte aligned");
+    CBX_REQUIRE(!p.glu || (p.N % 2 == 0), "gemm: glu needs even N");
+    // pick the tile so the grid covers the 148 SMs: big tiles only when they still give >= ~2 waves
+    long big = (long)cdiv(p.M, 128) * cdiv(p.N, 128) * p.batch;
+    if (big >= 296) launch_cfg<128, 128, 4, 4>(p, st);
+    else launch_cfg<64, 64, 2, 4>(p, st);
+}

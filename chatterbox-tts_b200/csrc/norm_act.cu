@@ -1,0 +1,155 @@
+// Row-wise normalisation and small elementwise kernels shared by T3 prefill, the flow encoder,
+// the CFM estimator and HiFT (sm_100a).  All activations are time-major, channels-last.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+// one warp per row; C <= 2048
+__global__ void norm_kernel(NormParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const long total = (long)p.rows * p.batch;
+    if (warp >= total) return;
+    const int b = warp / p.rows, r = warp % p.rows;
+    const float* x = p.in + (long)b * p.in_bs + (long)r * p.ld_in;
+    float mean = 0.f;
+    if (!p.rms) {
+        float s = 0.f;
+        for (int c = lane; c < p.C; c += 32) s += x[c];
+        mean = warp_sum(s) / p.C;
+    }
+    float v = 0.f;
+    for (int c = lane; c < p.C; c += 32) { float d = x[c] - mean; v += d * d; }
+    const float rstd = rsqrtf(warp_sum(v) / p.C + p.eps);
+    const float* add = p.add ? p.add + (long)b * p.add_bs : nullptr;
+    for (int c = lane; c < p.C; c += 32) {
+        float y = (x[c] - mean) * rstd * p.gain[c];
+        if (p.bias) y += p.bias[c];
+        y = act_apply(p.act, y, 0.f);
+        if (add) y += add[c];
+        y *= p.out_scale;
+        if (p.outF) p.outF[(long)b * p.outF_bs + (long)r * p.ld_outF + c] = y;
+        if (p.outB) p.outB[(long)b * p.outB_bs + (long)r * p.ld_outB + c] = __float2bfloat16(y);
+    }
+}
+
+__global__ void gather_rows_bf16_kernel(const float* __restrict__ table, const int* __restrict__ idx, int n, int C, bf16* out, long ld) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * C) return;
+    int r = i / C, c = i % C;
+    int t = idx[r];
+    out[(long)r * ld + c] = __float2bfloat16(table[(long)t * C + c]);
+}
+
+__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ in, long ld_in, bf16* out, long ld_out, int rows, int C, int act, float act_param) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)rows * C) return;
+    int r = i / C, c = i % C;
+    out[(long)r * ld_out + c] = __float2bfloat16(act_apply(act, in[(long)r * ld_in + c], act_param));
+}
+
+__global__ void add_rows_kernel(float* a, long lda, const float* b, long ldb, int rows, int C) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)rows * C) return;
+    int r = i / C, c = i % C;
+    a[(long)r * lda + c] += b[(long)r * ldb + c];
+}
+
+// nearest x2 upsample along time, fp32 [T][C] -> bf16 [2T][C]
+__global__ void upsample2_kernel(const float* __restrict__ in, bf16* out, long ld_out, int T, int C) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)2 * T * C) return;
+    int r = i / C, c = i % C;
+    out[(long)r * ld_out + c] = __float2bfloat16(in[(long)(r >> 1) * C + c]);
+}
+
+// CFM estimator input: rows [x | mu | spks | cond] (cond row) and [x | 0 | 0 | 0] (uncond row), bf16, 4*mel channels
+__global__ void pack_cfm_input_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ spks,
+                                      const float* __restrict__ cond, bf16* out, long out_bs, int T, int mel) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = 4 * mel;
+    if (i >= (long)2 * T * C) return;
+    int b = i / ((long)T * C);
+    long rem = i % ((long)T * C);
+    int t = rem / C, c = rem % C;
+    int part = c / mel, cc = c % mel;
+    float v;
+    if (part == 0) v = x[(long)t * mel + cc];
+    else if (b == 1) v = 0.f;
+    else if (part == 1) v = mu[(long)t * mel + cc];
+    else if (part == 2) v = spks[cc];
+    else v = cond[(long)t * mel + cc];
+    out[(long)b * out_bs + (long)t * C + c] = __float2bfloat16(v);
+}
+
+// x += dt * ((1+r) v_c - r v_u)
+__global__ void euler_update_kernel(float* x, const float* __restrict__ v, long v_bs, long n, float dt, float r) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] += dt * ((1.f + r) * v[i] - r * v[v_bs + i]);
+}
+
+// one CTA per (query row, head); generic head_dim (perceiver: 256).  q [Tq][ldq], k/v [Tk][ldk]
+__global__ void small_attention_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ k, const bf16* __restrict__ v, long ldk,
+                                       bf16* out, long ldo, int Tk, int hd, float scale) {
+    extern __shared__ float sm[];  // scores [Tk]
+    const int qi = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const bf16* qr = q + (long)qi * ldq + h * hd;
+    for (int j = warp; j < Tk; j += nw) {
+        const bf16* kr = k + (long)j * ldk + h * hd;
+        float s = 0.f;
+        for (int d = lane; d < hd; d += 32) s += __bfloat162float(qr[d]) * __bfloat162float(kr[d]);
+        s = warp_sum(s);
+        if (lane == 0) sm[j] = s * scale;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = 0; j < Tk; j++) mx = fmaxf(mx, sm[j]);
+    float den = 0.f;
+    for (int j = 0; j < Tk; j++) den += expf(sm[j] - mx);
+    for (int d = tid; d < hd; d += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < Tk; j++) acc += expf(sm[j] - mx) * __bfloat162float(v[(long)j * ldk + h * hd + d]);
+        out[(long)qi * ldo + h * hd + d] = __float2bfloat16(acc / den);
+    }
+}
+
+}  // namespace
+
+static inline dim3 g1(long n, int t = 256) { return dim3((unsigned)((n + t - 1) / t)); }
+
+void launch_norm(const NormParams& p, cudaStream_t st) {
+    long warps = (long)p.rows * p.batch;
+    if (warps == 0) return;
+    norm_kernel<<<g1(warps * 32, 256), 256, 0, st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_gather_rows_bf16(const float* table, const int* idx, int n, int C, bf16* out, long ld, cudaStream_t st) {
+    gather_rows_bf16_kernel<<<g1((long)n * C), 256, 0, st>>>(table, idx, n, C, out, ld);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_f32_to_bf16_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, int act, float act_param, cudaStream_t st) {
+    if (rows == 0) return;
+    f32_to_bf16_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(in, ld_in, out, ld_out, rows, C, act, act_param);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_add_rows(float* a, long lda, const float* b, long ldb, int rows, int C, cudaStream_t st) {
+    add_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(a, lda, b, ldb, rows, C);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_upsample2(const float* in, bf16* out, long ld_out, int T, int C, cudaStream_t st) {
+    upsample2_kernel<<<g1((long)2 * T * C), 256, 0, st>>>(in, out, ld_out, T, C);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_pack_cfm_input(const float* x, const float* mu, const float* spks, const float* cond, bf16* out, long out_bs, int T, int mel, cudaStream_t st) {
+    pack_cfm_input_kernel<<<g1((long)2 * T * 4 * mel), 256, 0, st>>>(x, mu, spks, cond, out, out_bs, T, mel);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_euler_update(float* x, const float* v, long v_bs, long n, float dt, float r, cudaStream_t st) {
+    euler_update_kernel<<<g1(n), 256, 0, st>>>(x, v, v_bs, n, dt, r);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_small_attention(const bf16* q, long ldq, const bf16* k, const bf16* v, long ldk, bf16* out, long ldo, int Tq, int Tk, int H, int hd, float scale, cudaStream_t st) {
+    small_attention_kernel<<<dim3(Tq, H), 128, Tk * sizeof(float), st>>>(q, ldq, k, v, ldk, out, ldo, Tk, hd, scale);
+    CBX_CHECK(cudaGetLastError());
+}

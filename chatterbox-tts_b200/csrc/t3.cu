@@ -1,0 +1,272 @@
+// T3 speech-token decoder: weight registration, voice prefix (T3CondEnc + Perceiver), prefill,
+// batched decode steps (CUDA-graph replayed) and KV page management.  Host orchestration only;
+// the arithmetic is in gemm.cu / attention.cu / norm_act.cu / t3_kernels.cu.
+#include "engine.h"
+
+using namespace dims;
+
+static Lin reg_lin(cbx_engine* e, const std::string& n, int N, int K, bool bias) {
+    Lin l; l.N = N; l.K = K;
+    l.w = e->reg<bf16>(n + ".w", DT_BF16, (long)N * K);
+    l.b = bias ? e->reg<float>(n + ".b", DT_F32, N) : nullptr;
+    return l;
+}
+
+void t3_build(cbx_engine* e) {
+    T3Model& m = e->t3;
+    m.text_emb = e->reg<float>("t3.text_emb", DT_F32, (long)T3_TEXT_V * T3_D);
+    m.speech_emb = e->reg<float>("t3.speech_emb", DT_F32, (long)T3_V * T3_D);
+    m.text_pos = e->reg<float>("t3.text_pos", DT_F32, (long)T3_TEXT_POS * T3_D);
+    m.speech_pos = e->reg<float>("t3.speech_pos", DT_F32, (long)T3_SPEECH_POS * T3_D);
+    m.final_norm = e->reg<float>("t3.final_norm", DT_F32, T3_D);
+    m.inv_freq = e->reg<float>("t3.inv_freq", DT_F32, 32);
+    m.head_f = e->reg<bf16>("t3.head_f", DT_BF16, (long)T3_VPAD * T3_D);
+    m.spkr = reg_lin(e, "t3.spkr", T3_D, T3_SPK, true);
+    m.emo_w = e->reg<float>("t3.emo_w", DT_F32, T3_D);
+    m.perc_query = e->reg<float>("t3.perc_query", DT_F32, (long)T3_PQ * T3_D);
+    m.pnorm.g = e->reg<float>("t3.pnorm.g", DT_F32, T3_D);
+    m.pnorm.b = e->reg<float>("t3.pnorm.b", DT_F32, T3_D);
+    m.pq = reg_lin(e, "t3.pq", T3_D, T3_D, true);
+    m.pkv = reg_lin(e, "t3.pkv", 2 * T3_D, T3_D, true);
+    m.po = reg_lin(e, "t3.po", T3_D, T3_D, true);
+    m.layers.resize(e->cfg.t3_layers);
+    for (int i = 0; i < e->cfg.t3_layers; i++) {
+        T3Layer& l = m.layers[i];
+        std::string p = "t3.l" + std::to_string(i) + ".";
+        l.ln1 = e->reg<float>(p + "ln1", DT_F32, T3_D);
+        l.ln2 = e->reg<float>(p + "ln2", DT_F32, T3_D);
+        l.wqkv = e->reg<bf16>(p + "wqkv", DT_BF16, 3L * T3_D * T3_D);
+        l.wo = e->reg<bf16>(p + "wo", DT_BF16, (long)T3_D * T3_D);
+        l.wgu = e->reg<bf16>(p + "wgu", DT_BF16, 2L * T3_FFN * T3_D);
+        l.wd = e->reg<bf16>(p + "wd", DT_BF16, (long)T3_D * T3_FFN);
+        l.wqkv_f = e->reg<bf16>(p + "wqkv_f", DT_BF16, 3L * T3_D * T3_D);
+        l.wo_f = e->reg<bf16>(p + "wo_f", DT_BF16, (long)T3_D * T3_D);
+        l.wgu_f = e->reg<bf16>(p + "wgu_f", DT_BF16, 2L * T3_FFN * T3_D);
+        l.wd_f = e->reg<bf16>(p + "wd_f", DT_BF16, (long)T3_D * T3_FFN);
+    }
+}
+
+void t3_alloc(cbx_engine* e) {
+    T3Model& m = e->t3;
+    const cbx_config& c = e->cfg;
+    const int S = c.max_streams, R = 2 * S;
+    m.max_pages = cdiv(c.max_seq, PAGE);
+    m.total_pages = R * m.max_pages;
+    m.kv_half = (long)m.total_pages * T3_H * PAGE * 64;
+    m.kv_layer_stride = 2 * m.kv_half;
+    m.kv = e->scratch<bf16>(m.kv_layer_stride * c.t3_layers);
+    m.page_table = e->scratch<int>((long)R * m.max_pages);
+    m.slot_state = e->scratch<T3SlotState>(S);
+    m.slot_pos = e->scratch<int>(S);
+    m.seen = e->scratch<uint8_t>((long)S * T3_VPAD);
+    m.out_stride = 4096;
+    m.out_tokens = e->scratch<int>((long)S * m.out_stride);
+    m.x = e->scratch<float>((long)R * T3_D);
+    m.qkv = e->scratch<float>((long)R * 3 * T3_D);
+    m.attn = e->scratch<float>((long)R * T3_D);
+    m.act = e->scratch<float>((long)R * T3_FFN);
+    m.logits = e->scratch<float>((long)R * T3_VPAD);
+    m.d_slots = e->scratch<int>(S);
+    m.d_rowmap = e->scratch<int>(R);
+    m.pf_max = T3_COND + c.max_text + 2;
+    const long M = 2L * m.pf_max;
+    m.pf_x = e->scratch<float>(M * T3_D);
+    m.pf_xn = e->scratch<bf16>(M * T3_D);
+    m.pf_qkv = e->scratch<bf16>(M * 3 * T3_D);
+    m.pf_att = e->scratch<bf16>(M * T3_D);
+    m.pf_act = e->scratch<bf16>(M * T3_FFN);
+    m.pf_text = e->scratch<int>(c.max_text + 8);
+    m.free_pages.clear();
+    for (int i = m.total_pages - 1; i >= 0; i--) m.free_pages.push_back(i);
+    m.slot_used.assign(S, 0);
+    m.slot_pages.assign(S, {});
+    m.slot_maxnew.assign(S, 0);
+    t3_kernels_init();
+}
+
+static void gemm_lin(const Lin& l, const bf16* A, long lda, int M, float* outF, bf16* outB, long ldc, cudaStream_t st,
+                     const float* res = nullptr, long ldr = 0, int act = ACT_NONE) {
+    GemmParams g;
+    g.A = A; g.lda = lda; g.kc = l.K; g.W = l.w; g.ldw = l.K; g.M = M; g.N = l.N; g.K = l.K; g.bias = l.b;
+    g.act = act; g.res = res; g.ldr = ldr; g.outF = outF; g.outB = outB; g.ldc = ldc;
+    launch_gemm(g, st);
+}
+
+// T3CondEnc + Perceiver -> prefix [34][1024] (computed once per voice, cached in the voice slot)
+void t3_voice_prefix(cbx_engine* e, Voice& v, const float* speaker_emb_h, const int* cond_tokens_h, int n_cond, float emotion, cudaStream_t st) {
+    T3Model& m = e->t3;
+    CBX_REQUIRE(n_cond > 0 && n_cond <= 256, "cond prompt length out of range");
+    // temporaries (voice_put is serialised by voice_mu)
+    static thread_local std::vector<void*> tmp;
+    auto dalloc = [&](size_t bytes) { void* p; CBX_CHECK(cudaMalloc(&p, bytes)); tmp.push_back(p); return p; };
+    float* spk_f = (float*)dalloc(T3_SPK * 4); bf16* spk_b = (bf16*)dalloc(T3_SPK * 2);
+    int* ids = (int*)dalloc(n_cond * 4);
+    float* prompt = (float*)dalloc((size_t)n_cond * T3_D * 4);
+    bf16* pn = (bf16*)dalloc((size_t)n_cond * T3_D * 2);
+    bf16* qn = (bf16*)dalloc((size_t)T3_PQ * T3_D * 2);
+    bf16* q = (bf16*)dalloc((size_t)T3_PQ * T3_D * 2);
+    bf16* kv = (bf16*)dalloc((size_t)n_cond * 2 * T3_D * 2);
+    bf16* att = (bf16*)dalloc((size_t)T3_PQ * T3_D * 2);
+    float* pre = (float*)dalloc((size_t)T3_PQ * T3_D * 4);
+    CBX_CHECK(cudaMemcpyAsync(spk_f, speaker_emb_h, T3_SPK * 4, cudaMemcpyHostToDevice, st));
+    CBX_CHECK(cudaMemcpyAsync(ids, cond_tokens_h, n_cond * 4, cudaMemcpyHostToDevice, st));
+    launch_f32_to_bf16_rows(spk_f, T3_SPK, spk_b, T3_SPK, 1, T3_SPK, ACT_NONE, 0.f, st);
+    gemm_lin(m.spkr, spk_b, T3_SPK, 1, v.prefix, nullptr, T3_D, st);
+    launch_prompt_embed(prompt, m.speech_emb, m.speech_pos, ids, n_cond, T3_D, st);
+    auto ln = [&](const float* in, int rows, bf16* out) {
+        NormParams n; n.in = in; n.ld_in = T3_D; n.rows = rows; n.C = T3_D; n.gain = m.pnorm.g; n.bias = m.pnorm.b; n.eps = 1e-5f;
+        n.outB = out; n.ld_outB = T3_D; launch_norm(n, st);
+    };
+    const float scale = 1.f / sqrtf((float)(T3_D / T3_PH));
+    // cross attention: queries = learned, keys/values = prompt
+    ln(m.perc_query, T3_PQ, qn);
+    ln(prompt, n_cond, pn);
+    gemm_lin(m.pq, qn, T3_D, T3_PQ, nullptr, q, T3_D, st);
+    gemm_lin(m.pkv, pn, T3_D, n_cond, nullptr, kv, 2 * T3_D, st);
+    launch_small_attention(q, T3_D, kv, kv + T3_D, 2 * T3_D, att, T3_D, T3_PQ, n_cond, T3_PH, T3_D / T3_PH, scale, st);
+    gemm_lin(m.po, att, T3_D, T3_PQ, pre, nullptr, T3_D, st, m.perc_query, T3_D);
+    // self attention over the result (same block weights)
+    ln(pre, T3_PQ, qn);
+    gemm_lin(m.pq, qn, T3_D, T3_PQ, nullptr, q, T3_D, st);
+    gemm_lin(m.pkv, qn, T3_D, T3_PQ, nullptr, kv, 2 * T3_D, st);
+    launch_small_attention(q, T3_D, kv, kv + T3_D, 2 * T3_D, att, T3_D, T3_PQ, T3_PQ, T3_PH, T3_D / T3_PH, scale, st);
+    gemm_lin(m.po, att, T3_D, T3_PQ, v.prefix + T3_D, nullptr, T3_D, st, pre, T3_D);
+    launch_scale_vec(v.prefix + (long)(T3_COND - 1) * T3_D, m.emo_w, emotion, T3_D, st);
+    CBX_CHECK(cudaStreamSynchronize(st));
+    for (void* p : tmp) cudaFree(p);
+    tmp.clear();
+    e->gpu_launches += 16;
+}
+
+int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w, float temp, float rep, float min_p, float top_p,
+            unsigned long long seed, int max_new, cudaStream_t st) {
+    T3Model& m = e->t3;
+    const cbx_config& c = e->cfg;
+    CBX_REQUIRE(voice >= 0 && voice < c.n_voices && e->voices[voice].valid, "t3_open: voice slot is empty");
+    CBX_REQUIRE(L >= 1 && L <= c.max_text, "t3_open: text length out of range");
+    CBX_REQUIRE(max_new >= 1 && max_new <= m.out_stride, "t3_open: max_new_tokens out of range");
+    CBX_REQUIRE(temp > 0.f, "t3_open: temperature must be positive");
+    const int cfg_on = cfg_w > 0.f ? 1 : 0;
+    const int Lp = T3_COND + L + cfg_on;   // positions prefilled; the last BOS goes through the first decode step
+    CBX_REQUIRE(Lp + 1 + max_new <= c.max_seq, "t3_open: sequence exceeds max_seq");
+    int slot = -1;
+    for (int i = 0; i < c.max_streams; i++) if (!m.slot_used[i]) { slot = i; break; }
+    CBX_REQUIRE(slot >= 0, "t3_open: no free stream slot");
+    const int need = cdiv(Lp + 1 + max_new, PAGE);
+    CBX_REQUIRE((int)m.free_pages.size() >= 2 * need, "t3_open: KV page pool exhausted");
+    std::vector<int> pt(2 * m.max_pages, 0);
+    m.slot_pages[slot].clear();
+    for (int r = 0; r < 2; r++)
+        for (int i = 0; i < need; i++) {
+            int pg = m.free_pages.back(); m.free_pages.pop_back();
+            pt[r * m.max_pages + i] = pg; m.slot_pages[slot].push_back(pg);
+        }
+    m.slot_used[slot] = 1; m.slot_maxnew[slot] = max_new;
+    CBX_CHECK(cudaMemcpyAsync(m.page_table + (long)slot * 2 * m.max_pages, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, st));
+    CBX_CHECK(cudaMemcpyAsync(m.pf_text, text_ids_h, L * 4, cudaMemcpyHostToDevice, st));
+    CBX_CHECK(cudaStreamSynchronize(st));   // pt / text staging are host stack buffers
+
+    AssembleParams a;
+    a.x = m.pf_x; a.prefix = e->voices[voice].prefix; a.text_emb = m.text_emb; a.text_pos = m.text_pos; a.speech_emb = m.speech_emb;
+    a.speech_pos = m.speech_pos; a.text_ids = m.pf_text; a.Lc = T3_COND; a.L = L; a.Lp = Lp; a.dim = T3_D; a.bos = T3_BOS; a.cfg_on = cfg_on;
+    launch_assemble_embeds(a, st);
+    const int M = 2 * Lp;
+    for (int li = 0; li < c.t3_layers; li++) {
+        const T3Layer& l = m.layers[li];
+        NormParams n; n.in = m.pf_x; n.ld_in = T3_D; n.rows = M; n.C = T3_D; n.gain = l.ln1; n.rms = 1; n.eps = 1e-5f; n.outB = m.pf_xn; n.ld_outB = T3_D;
+        launch_norm(n, st);
+        GemmParams g; g.A = m.pf_xn; g.lda = T3_D; g.kc = T3_D; g.W = l.wqkv; g.ldw = T3_D; g.M = M; g.N = 3 * T3_D; g.K = T3_D; g.outB = m.pf_qkv; g.ldc = 3 * T3_D;
+        launch_gemm(g, st);
+        RopeKvParams r; r.qkv = m.pf_qkv; r.Lp = Lp; r.H = T3_H; r.kv = m.kv + li * m.kv_layer_stride; r.kv_half = m.kv_half;
+        r.page_table = m.page_table; r.max_pages = m.max_pages; r.row0 = slot * 2; r.inv_freq = m.inv_freq;
+        launch_rope_kv_prefill(r, st);
+        AttnParams at; at.q = m.pf_qkv; at.k = m.pf_qkv + T3_D; at.v = m.pf_qkv + 2 * T3_D; at.ldq = at.ldk = at.ldv = 3 * T3_D;
+        at.q_bs = at.k_bs = at.v_bs = (long)Lp * 3 * T3_D; at.o = m.pf_att; at.ldo = T3_D; at.o_bs = (long)Lp * T3_D; at.T = Lp; at.H = T3_H; at.batch = 2;
+        at.causal = 1; at.scale = 0.125f;
+        launch_attention(at, st);
+        GemmParams o; o.A = m.pf_att; o.lda = T3_D; o.kc = T3_D; o.W = l.wo; o.ldw = T3_D; o.M = M; o.N = T3_D; o.K = T3_D; o.res = m.pf_x; o.ldr = T3_D; o.outF = m.pf_x; o.ldc = T3_D;
+        launch_gemm(o, st);
+        n.gain = l.ln2; launch_norm(n, st);
+        GemmParams gu; gu.A = m.pf_xn; gu.lda = T3_D; gu.kc = T3_D; gu.W = l.wgu; gu.ldw = T3_D; gu.M = M; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.glu = 1; gu.outB = m.pf_act; gu.ldc = T3_FFN;
+        launch_gemm(gu, st);
+        GemmParams d; d.A = m.pf_act; d.lda = T3_FFN; d.kc = T3_FFN; d.W = l.wd; d.ldw = T3_FFN; d.M = M; d.N = T3_D; d.K = T3_FFN; d.res = m.pf_x; d.ldr = T3_D; d.outF = m.pf_x; d.ldc = T3_D;
+        launch_gemm(d, st);
+    }
+    T3SlotState s{};
+    s.pos = Lp; s.step = 0; s.max_new = max_new; s.done = 0; s.cfg_w = cfg_w; s.temp = temp; s.rep_pen = rep; s.min_p = min_p; s.top_p = top_p; s.seed = seed;
+    launch_init_slot(m.slot_state, s, m.slot_pos, slot, m.seen, T3_VPAD, T3_BOS, m.x, m.speech_emb, m.speech_pos, T3_D, st);
+    e->gpu_launches += 2 + 8L * c.t3_layers;
+    return slot;
+}
+
+static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t st) {
+    T3Model& m = e->t3;
+    const int rows = 2 * n;
+    for (int li = 0; li < e->cfg.t3_layers; li++) {
+        const T3Layer& l = m.layers[li];
+        GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1; q.x = m.x; q.ldx_in = T3_D;
+        q.row_map = m.d_rowmap; q.rows = rows; q.gain = l.ln1; q.eps = 1e-5f; q.out = m.qkv; q.ld_out = 3 * T3_D; q.epi = GEMV_STORE;
+        launch_gemv(q, 8, st);
+        DecodeAttnParams a; a.qkv = m.qkv; a.out = m.attn; a.kv = m.kv + li * m.kv_layer_stride; a.kv_half = m.kv_half; a.page_table = m.page_table;
+        a.max_pages = m.max_pages; a.slot_pos = m.slot_pos; a.row_map = m.d_rowmap; a.inv_freq = m.inv_freq; a.H = T3_H;
+        launch_decode_attn(a, rows, e->cfg.max_seq, st);
+        GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.x = m.attn; o.ldx_in = T3_D;
+        o.row_map = m.d_rowmap; o.rows = rows; o.out = m.x; o.ld_out = T3_D; o.epi = GEMV_RESID;
+        launch_gemv(o, 16, st);
+        GemvParams gu; gu.Wf = l.wgu_f; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.n_strips = 2 * T3_FFN / 16; gu.strips_per_cta = 2; gu.x = m.x; gu.ldx_in = T3_D;
+        gu.row_map = m.d_rowmap; gu.rows = rows; gu.gain = l.ln2; gu.eps = 1e-5f; gu.out = m.act; gu.ld_out = T3_FFN; gu.epi = GEMV_GLU;
+        launch_gemv(gu, 8, st);
+        GemvParams d; d.Wf = l.wd_f; d.N = T3_D; d.K = T3_FFN; d.n_strips = T3_D / 16; d.strips_per_cta = 1; d.x = m.act; d.ldx_in = T3_FFN;
+        d.row_map = m.d_rowmap; d.rows = rows; d.out = m.x; d.ld_out = T3_D; d.epi = GEMV_RESID;
+        launch_gemv(d, 16, st);
+    }
+    GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = 1; h.x = m.x; h.ldx_in = T3_D;
+    h.row_map = m.d_rowmap; h.rows = rows; h.gain = m.final_norm; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
+    launch_gemv(h, 8, st);
+    SamplerParams s; s.slots = m.d_slots; s.state = m.slot_state; s.slot_pos = m.slot_pos; s.logits = m.logits; s.ld_logits = T3_VPAD;
+    s.seen = m.seen; s.seen_stride = T3_VPAD; s.out_tokens = m.out_tokens; s.out_stride = m.out_stride; s.noise = noise; s.noise_stride = T3_V;
+    s.x = m.x; s.speech_emb = m.speech_emb; s.speech_pos = m.speech_pos; s.V = T3_V; s.dim = T3_D; s.eos = T3_EOS;
+    launch_sampler(s, n, st);
+}
+
+void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* noise_dev, cudaStream_t st) {
+    T3Model& m = e->t3;
+    CBX_REQUIRE(n >= 1 && n <= e->cfg.max_streams && 2 * n <= 16, "t3_step: between 1 and 8 streams per call");
+    std::vector<int> act(slots, slots + n);
+    for (int s : act) CBX_REQUIRE(s >= 0 && s < e->cfg.max_streams && m.slot_used[s], "t3_step: slot is not open");
+    if (act != m.h_active) {
+        std::vector<int> rm(2 * n);
+        for (int r = 0; r < 2 * n; r++) rm[r] = act[r / 2] * 2 + (r & 1);
+        CBX_CHECK(cudaMemcpyAsync(m.d_slots, act.data(), n * 4, cudaMemcpyHostToDevice, st));
+        CBX_CHECK(cudaMemcpyAsync(m.d_rowmap, rm.data(), 2 * n * 4, cudaMemcpyHostToDevice, st));
+        CBX_CHECK(cudaStreamSynchronize(st));
+        m.h_active = act;
+    }
+    const long per_step = 5L * e->cfg.t3_layers + 2;
+    if (noise_dev) {
+        for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev + (long)i * n * T3_V, st);
+    } else {
+        auto it = m.step_graphs.find(n);
+        if (it == m.step_graphs.end()) {
+            cudaGraph_t graph;
+            CBX_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            enqueue_step(e, n, nullptr, st);
+            CBX_CHECK(cudaStreamEndCapture(st, &graph));
+            cudaGraphExec_t exec;
+            CBX_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+            CBX_CHECK(cudaGraphDestroy(graph));
+            it = m.step_graphs.emplace(n, exec).first;
+        }
+        for (int i = 0; i < n_steps; i++) CBX_CHECK(cudaGraphLaunch(it->second, st));
+    }
+    e->gpu_launches += per_step * n_steps;
+}
+
+void t3_close(cbx_engine* e, int slot) {
+    T3Model& m = e->t3;
+    CBX_REQUIRE(slot >= 0 && slot < e->cfg.max_streams && m.slot_used[slot], "t3_close: slot is not open");
+    for (int pg : m.slot_pages[slot]) m.free_pages.push_back(pg);
+    m.slot_pages[slot].clear();
+    m.slot_used[slot] = 0;
+    m.h_active.clear();
+}

@@ -1,0 +1,508 @@
+// T3 decode-step kernels (sm_100a): HBM-streaming GEMV over fragment-ordered bf16 weights with
+// fused RMSNorm / residual / SwiGLU epilogues, RoPE + paged-KV decode attention, and the one-kernel
+// CFG-mix -> repetition-penalty -> temperature -> min-p -> top-p -> sample step.
+// Also the prefill helpers (embedding assembly, RoPE + KV page write).
+#include "common.cuh"
+#include "t3_kernels.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// GEMV: y[r][f] = sum_k W[f][k] * xin[r][k] for r < rows (<= 8*NT).  W is stored in mma.m16n8k16
+// A-fragment order: tile (strip s, ktile kt) = 32 lanes x 8 bf16 (512 B, contiguous), tiles ordered
+// [strip][ktile], so every warp streams 512-byte coalesced lines straight into tensor-core fragments.
+// Each CTA owns `strips_per_cta` strips; its warps split K.
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int ldx = p.K + 8;  // bf16 elements per staged row (+8 pad: conflict-free fragment reads)
+    bf16* xs = reinterpret_cast<bf16*>(smem);                                   // [8*NT][ldx]
+    float* part = reinterpret_cast<float*>(smem + (size_t)8 * NT * ldx * 2);    // [nwarps][S][16][8*NT]
+
+    // ---- stage input rows (optionally RMS-normalised) as bf16
+    for (int r = warp; r < 8 * NT; r += nwarps) {
+        bf16* dst = xs + (size_t)r * ldx;
+        if (r < p.rows) {
+            const float* src = p.x + (long)p.row_map[r] * p.ldx_in;
+            float scale = 1.f;
+            if (p.gain) {
+                float ss = 0.f;
+                for (int k = lane; k < p.K; k += 32) { float v = src[k]; ss += v * v; }
+                scale = rsqrtf(warp_sum(ss) / p.K + p.eps);
+            }
+            for (int k = lane; k < p.K; k += 32) {
+                float v = src[k] * scale;
+                if (p.gain) v *= p.gain[k];
+                dst[k] = __float2bfloat16(v);
+            }
+        } else {
+            for (int k = lane; k < p.K; k += 32) dst[k] = __float2bfloat16(0.f);
+        }
+    }
+    __syncthreads();
+
+    const int KT = p.K >> 4;
+    const int kt_per = KT / nwarps;            // host guarantees divisibility
+    const int kt0 = warp * kt_per;
+    const int S = p.strips_per_cta;
+    for (int sl = 0; sl < S; sl++) {
+        const int strip = blockIdx.x * S + sl;
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[j][r] = 0.f;
+        if (strip < p.n_strips) {
+            const uint4* wp = reinterpret_cast<const uint4*>(p.Wf) + ((size_t)strip * KT + kt0) * 32 + lane;
+            for (int kt = 0; kt < kt_per; kt += 8) {
+                uint4 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (kt + u < kt_per) w[u] = __ldg(wp + (size_t)(kt + u) * 32);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (kt + u < kt_per) {
+                        const int k0 = (kt0 + kt + u) << 4;
+                        uint32_t a[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                        for (int j = 0; j < NT; j++) {
+                            const bf16* xr = xs + (size_t)(j * 8 + g) * ldx + k0 + tg * 2;
+                            uint32_t b0 = *reinterpret_cast<const uint32_t*>(xr);
+                            uint32_t b1 = *reinterpret_cast<const uint32_t*>(xr + 8);
+                            mma_bf16(acc[j], a, b0, b1);
+                        }
+                    }
+                }
+            }
+        }
+        float* pw = part + ((size_t)(warp * S + sl) * 16) * (8 * NT);
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            pw[(g) * (8 * NT) + j * 8 + tg * 2] = acc[j][0];
+            pw[(g) * (8 * NT) + j * 8 + tg * 2 + 1] = acc[j][1];
+            pw[(g + 8) * (8 * NT) + j * 8 + tg * 2] = acc[j][2];
+            pw[(g + 8) * (8 * NT) + j * 8 + tg * 2 + 1] = acc[j][3];
+        }
+    }
+    __syncthreads();
+    // ---- cross-warp reduction + epilogue: one thread per (strip_local, f, r)
+    const int per_strip = 16 * 8 * NT;
+    if (p.epi == GEMV_GLU) {
+        // strips come in (gate, up) pairs
+        for (int i = tid; i < (S / 2) * per_strip; i += blockDim.x) {
+            int pr = i / per_strip, e = i % per_strip, f = e / (8 * NT), r = e % (8 * NT);
+            if (r >= p.rows) continue;
+            float gsum = 0.f, usum = 0.f;
+            for (int w = 0; w < nwarps; w++) {
+                gsum += part[((size_t)(w * S + 2 * pr) * 16 + f) * (8 * NT) + r];
+                usum += part[((size_t)(w * S + 2 * pr + 1) * 16 + f) * (8 * NT) + r];
+            }
+            int pair = (blockIdx.x * S) / 2 + pr;
+            if (pair * 2 + 1 < p.n_strips)
+                p.out[(long)p.row_map[r] * p.ld_out + pair * 16 + f] = gsum / (1.f + expf(-gsum)) * usum;
+        }
+    } else {
+        for (int i = tid; i < S * per_strip; i += blockDim.x) {
+            int sl = i / per_strip, e = i % per_strip, f = e / (8 * NT), r = e % (8 * NT);
+            int strip = blockIdx.x * S + sl;
+            if (r >= p.rows || strip >= p.n_strips) continue;
+            float s = 0.f;
+            for (int w = 0; w < nwarps; w++) s += part[((size_t)(w * S + sl) * 16 + f) * (8 * NT) + r];
+            int col = strip * 16 + f;
+            if (col >= p.N) continue;
+            float* o = p.out + (long)p.row_map[r] * p.ld_out + col;
+            if (p.epi == GEMV_RESID) *o += s; else *o = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode attention for one (row, head): RoPE on the new q/k, append k/v to the row's KV pages, then
+// softmax(q K^T / 8) V over positions [0, pos].  KV pool layout per layer: [2][page][H][16][64] bf16.
+// ------------------------------------------------------------------------------------------------
+constexpr int PAGE = 16, HD = 64;
+
+__global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeAttnParams p) {
+    __shared__ float qs[HD];
+    __shared__ float red[128];
+    __shared__ float osm[4][2][32];
+    extern __shared__ float sc[];  // [max positions]
+    const int h = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = p.row_map[r];
+    const int slot = row >> 1;
+    const int pos = p.slot_pos[slot];
+    const int* pt = p.page_table + (long)row * p.max_pages;
+    const float* qkv = p.qkv + (long)row * (3 * p.H * HD);
+    bf16* kpool = p.kv;
+    bf16* vpool = p.kv + p.kv_half;
+    if (tid < 32) {
+        // rotate_half RoPE: pairs (d, d+32)
+        float inv = p.inv_freq[tid];
+        float sn, cs;
+        sincosf((float)pos * inv, &sn, &cs);
+        float q0 = qkv[h * HD + tid], q1 = qkv[h * HD + tid + 32];
+        float k0 = qkv[p.H * HD + h * HD + tid], k1 = qkv[p.H * HD + h * HD + tid + 32];
+        qs[tid] = (q0 * cs - q1 * sn) * 0.125f;
+        qs[tid + 32] = (q1 * cs + q0 * sn) * 0.125f;
+        long base = (((long)pt[pos / PAGE] * p.H + h) * PAGE + (pos % PAGE)) * HD;
+        kpool[base + tid] = __float2bfloat16(k0 * cs - k1 * sn);
+        kpool[base + tid + 32] = __float2bfloat16(k1 * cs + k0 * sn);
+        vpool[base + tid] = __float2bfloat16(qkv[2 * p.H * HD + h * HD + tid]);
+        vpool[base + tid + 32] = __float2bfloat16(qkv[2 * p.H * HD + h * HD + tid + 32]);
+    }
+    __syncthreads();
+    const int n = pos + 1, npages = (n + PAGE - 1) / PAGE;
+    const int pp = lane >> 1, half = lane & 1;
+    for (int pg = warp; pg < npages; pg += 4) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kpool + (((long)pt[pg] * p.H + h) * PAGE + pp) * HD + half * 32);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint4 u = kp[c];
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float2 f = __bfloat1622float2(b2[e]);
+                s += f.x * qs[half * 32 + c * 8 + e * 2] + f.y * qs[half * 32 + c * 8 + e * 2 + 1];
+            }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        int j = pg * PAGE + pp;
+        if (half == 0 && j < n) sc[j] = s;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = tid; j < n; j += 128) mx = fmaxf(mx, sc[j]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < n; j += 128) { float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    float acc[32];
+#pragma unroll
+    for (int d = 0; d < 32; d++) acc[d] = 0.f;
+    for (int pg = warp; pg < npages; pg += 4) {
+        int j = pg * PAGE + pp;
+        if (j >= n) continue;   // stale page tail may hold non-finite values
+        float w = sc[j];
+        const uint4* vp = reinterpret_cast<const uint4*>(vpool + (((long)pt[pg] * p.H + h) * PAGE + pp) * HD + half * 32);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint4 u = vp[c];
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float2 f = __bfloat1622float2(b2[e]);
+                acc[c * 8 + e * 2] += w * f.x;
+                acc[c * 8 + e * 2 + 1] += w * f.y;
+            }
+        }
+    }
+    // reduce over the 16 lanes that share `half`
+#pragma unroll
+    for (int d = 0; d < 32; d++) {
+        float v = acc[d];
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        acc[d] = v;
+    }
+    if (lane < 2) {
+#pragma unroll
+        for (int d = 0; d < 32; d++) osm[warp][lane][d] = acc[d];
+    }
+    __syncthreads();
+    if (tid < HD) {
+        int hf = tid >> 5, d = tid & 31;
+        float v = osm[0][hf][d] + osm[1][hf][d] + osm[2][hf][d] + osm[3][hf][d];
+        p.out[(long)row * (p.H * HD) + h * HD + tid] = v * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sampler: one CTA (1024 threads) per stream.  Order fixed by BASELINE.json north_star:
+// CFG mix -> repetition penalty -> temperature -> min-p -> top-p -> sample (argmax p/q, q~Exp(1)).
+// Also advances the stream state and writes the next input embedding for both CFG rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int SAMP_T = 1024, SAMP_E = 9;  // 9 * 1024 >= 8194
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[threadIdx.x & 31];
+    r = warp_max(r);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[threadIdx.x & 31];
+    r = warp_sum(r);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) {
+    __shared__ float red[32];
+    __shared__ float es[SAMP_T * SAMP_E];
+    __shared__ float wsum[32];
+    __shared__ unsigned int s_lo, s_hi;
+    __shared__ float bestv[32];
+    __shared__ int besti[32];
+    const int slot = p.slots[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    T3SlotState* st = p.state + slot;
+    if (st->done) return;
+    const int V = p.V;
+    const float* lc = p.logits + (long)(slot * 2) * p.ld_logits;
+    const float* lu = lc + p.ld_logits;
+    const float w = st->cfg_w, inv_temp = 1.f / st->temp, rp = st->rep_pen;
+    const uint8_t* seen = p.seen + (long)slot * p.seen_stride;
+    float l[SAMP_E];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < SAMP_E; e++) {
+        int i = tid + e * SAMP_T;
+        float v = -INFINITY;
+        if (i < V) {
+            float c = lc[i];
+            v = w > 0.f ? c + w * (c - lu[i]) : c;
+            if (seen[i]) v = v < 0.f ? v * rp : v / rp;
+            v *= inv_temp;
+        }
+        l[e] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = block_reduce_max(mx, red);
+    float ex[SAMP_E];
+    float z = 0.f;
+#pragma unroll
+    for (int e = 0; e < SAMP_E; e++) { ex[e] = expf(l[e] - mx); z += ex[e]; }
+    z = block_reduce_sum(z, red);
+    // min-p: drop p_i < min_p * p_max, p_max = 1/z
+    if (st->min_p > 0.f) {
+        const float thr = st->min_p * (1.f / z);
+#pragma unroll
+        for (int e = 0; e < SAMP_E; e++)
+            if (ex[e] / z < thr && ex[e] != 1.0f) ex[e] = 0.f;
+    }
+    // top-p: remove the ascending-probability prefix whose cumulative mass <= 1 - top_p
+    if (st->top_p < 1.f) {
+        float z2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < SAMP_E; e++) z2 += ex[e];
+        z2 = block_reduce_sum(z2, red);
+        const float target = (1.f - st->top_p) * z2;
+#pragma unroll
+        for (int e = 0; e < SAMP_E; e++) es[tid + e * SAMP_T] = ex[e];
+        if (tid == 0) { s_lo = 0u; s_hi = 0x3F800000u; }
+        __syncthreads();
+        // 33-way search on the float bit pattern: invariant mass(e <= lo) <= target < mass(e <= hi)
+        while (true) {
+            unsigned int lo = s_lo, hi = s_hi;
+            if (hi - lo <= 1u) break;
+            unsigned long long span = hi - lo;
+            unsigned int t = lo + (unsigned int)((span * (unsigned)(warp + 1)) / 33ull);
+            if (t <= lo) t = lo + 1;
+            if (t >= hi) t = hi - 1;
+            float thr = __uint_as_float(t);
+            float m = 0.f;
+            for (int i = lane; i < SAMP_T * SAMP_E; i += 32) { float v = es[i]; m += (v <= thr) ? v : 0.f; }
+            m = warp_sum(m);
+            if (lane == 0) { wsum[warp] = m; red[warp] = __uint_as_float(t); }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned int nlo = lo, nhi = hi;
+                for (int q = 0; q < 32; q++) {
+                    unsigned int tq = __float_as_uint(red[q]);
+                    if (wsum[q] <= target) { if (tq > nlo) nlo = tq; }
+                    else { if (tq < nhi) nhi = tq; }
+                }
+                s_lo = nlo; s_hi = nhi;
+            }
+            __syncthreads();
+        }
+        const float cut = __uint_as_float(s_lo);
+#pragma unroll
+        for (int e = 0; e < SAMP_E; e++)
+            if (ex[e] <= cut) ex[e] = 0.f;
+    }
+    // sample: argmax e_i / q_i  (normalisation-free form of multinomial(softmax))
+    float bv = -1.f; int bi = 0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < SAMP_E; e++) {
+        int i = tid + e * SAMP_T;
+        if (i < V && ex[e] > 0.f) {
+            float q;
+            if (p.noise) q = p.noise[(long)blockIdx.x * p.noise_stride + i];
+            else {
+                uint32_t r4[4];
+                Philox::gen(st->seed, (uint32_t)i, (uint32_t)st->step, 0x5A4Du, 0u, r4);
+                q = -logf(u32_to_unit(r4[0]));
+            }
+            float val = ex[e] / q;
+            if (val > bv || (val == bv && i < bi)) { bv = val; bi = i; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { bestv[warp] = bv; besti[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bv = bestv[lane]; bi = besti[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) besti[0] = bi;
+    }
+    __syncthreads();
+    const int tok = besti[0];
+    const int step = st->step;
+    // next input embedding (both CFG rows): speech_emb[tok] + speech_pos[step+1]
+    for (int d = tid; d < p.dim; d += SAMP_T) {
+        float v = p.speech_emb[(long)tok * p.dim + d] + p.speech_pos[(long)(step + 1) * p.dim + d];
+        p.x[(long)(slot * 2) * p.dim + d] = v;
+        p.x[(long)(slot * 2 + 1) * p.dim + d] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        p.out_tokens[(long)slot * p.out_stride + step] = tok;
+        p.seen[(long)slot * p.seen_stride + tok] = 1;
+        st->step = step + 1;
+        st->pos = st->pos + 1;
+        if (tok == p.eos || step + 1 >= st->max_new) st->done = 1;
+        p.slot_pos[slot] = st->pos;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prefill helpers
+// ------------------------------------------------------------------------------------------------
+// x[b][t][:] for t < Lp: [cond prefix (Lc) | text_emb[tok]+text_pos[i] (row 1: pos only when cfg>0) | bos ...]
+__global__ void assemble_embeds_kernel(const AssembleParams p) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    float* out = p.x + ((long)b * p.Lp + t) * p.dim;
+    for (int d = threadIdx.x; d < p.dim; d += blockDim.x) {
+        float v;
+        if (t < p.Lc) v = p.prefix[(long)t * p.dim + d];
+        else if (t < p.Lc + p.L) {
+            int i = t - p.Lc;
+            v = p.text_pos[(long)i * p.dim + d];
+            if (!(b == 1 && p.cfg_on)) v += p.text_emb[(long)p.text_ids[i] * p.dim + d];
+        } else v = p.speech_emb[(long)p.bos * p.dim + d] + p.speech_pos[d];
+        out[d] = v;
+    }
+}
+
+// rotate q,k in the fused qkv buffer (bf16 [2][Lp][3*H*64]) and write k,v into the rows' KV pages
+__global__ void rope_kv_prefill_kernel(const RopeKvParams p) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    bf16* row = p.qkv + ((long)b * p.Lp + t) * (3 * p.H * HD);
+    const int* pt = p.page_table + (long)(p.row0 + b) * p.max_pages;
+    bf16* kpool = p.kv; bf16* vpool = p.kv + p.kv_half;
+    for (int i = threadIdx.x; i < p.H * 32; i += blockDim.x) {
+        int h = i >> 5, d = i & 31;
+        float sn, cs;
+        sincosf((float)t * p.inv_freq[d], &sn, &cs);
+        bf16* q = row + h * HD; bf16* k = row + p.H * HD + h * HD; bf16* v = row + 2 * p.H * HD + h * HD;
+        float q0 = __bfloat162float(q[d]), q1 = __bfloat162float(q[d + 32]);
+        float k0 = __bfloat162float(k[d]), k1 = __bfloat162float(k[d + 32]);
+        bf16 kr0 = __float2bfloat16(k0 * cs - k1 * sn), kr1 = __float2bfloat16(k1 * cs + k0 * sn);
+        q[d] = __float2bfloat16(q0 * cs - q1 * sn); q[d + 32] = __float2bfloat16(q1 * cs + q0 * sn);
+        k[d] = kr0; k[d + 32] = kr1;
+        long base = (((long)pt[t / PAGE] * p.H + h) * PAGE + (t % PAGE)) * HD;
+        kpool[base + d] = kr0; kpool[base + d + 32] = kr1;
+        vpool[base + d] = v[d]; vpool[base + d + 32] = v[d + 32];
+    }
+}
+
+__global__ void init_slot_kernel(T3SlotState* st, T3SlotState v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
+                                 float* x, const float* speech_emb, const float* speech_pos, int dim) {
+    for (int i = threadIdx.x; i < seen_stride; i += blockDim.x) seen[(long)slot * seen_stride + i] = (i == bos) ? 1 : 0;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        float e = speech_emb[(long)bos * dim + d] + speech_pos[d];
+        x[(long)(slot * 2) * dim + d] = e;
+        x[(long)(slot * 2 + 1) * dim + d] = e;
+    }
+    if (threadIdx.x == 0) { st[slot] = v; slot_pos[slot] = v.pos; }
+}
+
+__global__ void prompt_embed_kernel(float* out, const float* __restrict__ emb, const float* __restrict__ pos, const int* __restrict__ ids, int n, int D) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * D) return;
+    int r = i / D, c = i % D;
+    out[i] = emb[(long)ids[r] * D + c] + pos[(long)r * D + c];
+}
+__global__ void scale_vec_kernel(float* out, const float* __restrict__ w, float s, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[i] * s;
+}
+
+}  // namespace
+
+void t3_kernels_init() {
+    CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+void launch_prompt_embed(float* out, const float* emb, const float* pos, const int* ids, int n, int D, cudaStream_t st) {
+    prompt_embed_kernel<<<cdiv((long)n * D, 256), 256, 0, st>>>(out, emb, pos, ids, n, D);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_scale_vec(float* out, const float* w, float s, int n, cudaStream_t st) {
+    scale_vec_kernel<<<cdiv(n, 256), 256, 0, st>>>(out, w, s, n);
+    CBX_CHECK(cudaGetLastError());
+}
+
+void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
+    CBX_REQUIRE(p.rows >= 1 && p.rows <= 16, "gemv: rows must be in [1,16]");
+    CBX_REQUIRE(p.K % 16 == 0 && (p.K / 16) % nwarps == 0, "gemv: K/16 must divide by the warp count");
+    const int NT = p.rows <= 8 ? 1 : 2;
+    const int S = p.strips_per_cta;
+    size_t smem = (size_t)8 * NT * (p.K + 8) * 2 + (size_t)nwarps * S * 16 * 8 * NT * 4;
+    int grid = cdiv(p.n_strips, S);
+    CBX_REQUIRE(smem <= 200 * 1024, "gemv: staging exceeds shared memory");
+    if (NT == 1) gemv_kernel<1><<<grid, nwarps * 32, smem, st>>>(p);
+    else gemv_kernel<2><<<grid, nwarps * 32, smem, st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st) {
+    decode_attn_kernel<<<dim3(p.H, rows), 128, (size_t)(max_pos + PAGE) * sizeof(float), st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st) {
+    CBX_REQUIRE(p.V <= SAMP_T * SAMP_E, "sampler: vocabulary too large for the register tile");
+    sampler_kernel<<<n_streams, SAMP_T, 0, st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_assemble_embeds(const AssembleParams& p, cudaStream_t st) {
+    assemble_embeds_kernel<<<dim3(p.Lp, 2), 256, 0, st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_rope_kv_prefill(const RopeKvParams& p, cudaStream_t st) {
+    rope_kv_prefill_kernel<<<dim3(p.Lp, 2), 256, 0, st>>>(p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
+                      float* x, const float* speech_emb, const float* speech_pos, int dim, cudaStream_t st) {
+    init_slot_kernel<<<1, 256, 0, st>>>(st_dev, v, slot_pos, slot, seen, seen_stride, bos, x, speech_emb, speech_pos, dim);
+    CBX_CHECK(cudaGetLastError());
+}

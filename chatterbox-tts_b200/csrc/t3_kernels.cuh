@@ -1,0 +1,74 @@
+// Parameter blocks for the T3 kernels (t3_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+enum GemvEpi { GEMV_STORE = 0, GEMV_RESID = 1, GEMV_GLU = 2 };
+
+struct GemvParams {
+    const bf16* Wf = nullptr;     // fragment-ordered weights [n_strips][K/16][32][8]
+    int N = 0, K = 0, n_strips = 0, strips_per_cta = 1;
+    const float* x = nullptr; long ldx_in = 0;    // fp32 input rows, indexed through row_map
+    const int* row_map = nullptr; int rows = 0;   // compact row -> global row (slot*2 + cfg_row)
+    const float* gain = nullptr; float eps = 1e-5f;   // non-null: RMSNorm the input rows first
+    float* out = nullptr; long ld_out = 0; int epi = GEMV_STORE;
+};
+void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st);
+
+struct T3SlotState {   // device-resident per-stream decode state
+    int pos;        // KV length (positions already cached) of both rows
+    int step;       // tokens generated so far
+    int max_new;
+    int done;
+    float cfg_w, temp, rep_pen, min_p, top_p;
+    int _pad;
+    unsigned long long seed;
+};
+
+struct DecodeAttnParams {
+    const float* qkv = nullptr;          // [rows_total][3*H*64] fp32 (raw projections)
+    float* out = nullptr;                // [rows_total][H*64] fp32
+    bf16* kv = nullptr; long kv_half = 0;   // this layer's pool: K at kv, V at kv + kv_half; [page][H][16][64]
+    const int* page_table = nullptr; int max_pages = 0;   // [rows_total][max_pages]
+    const int* slot_pos = nullptr;       // [slots]
+    const int* row_map = nullptr;
+    const float* inv_freq = nullptr;     // [32]
+    int H = 16;
+};
+void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st);
+
+struct SamplerParams {
+    const int* slots = nullptr;          // [n_streams] active slot ids
+    T3SlotState* state = nullptr;
+    int* slot_pos = nullptr;
+    const float* logits = nullptr; long ld_logits = 0;   // [slots*2][ld]
+    uint8_t* seen = nullptr; int seen_stride = 0;
+    int* out_tokens = nullptr; int out_stride = 0;
+    const float* noise = nullptr; long noise_stride = 0;  // optional explicit Exp(1) noise [n_streams][V]
+    float* x = nullptr;                  // [slots*2][dim] next-step input embeddings
+    const float* speech_emb = nullptr; const float* speech_pos = nullptr;
+    int V = 0, dim = 0, eos = 0;
+};
+void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st);
+
+struct AssembleParams {
+    float* x = nullptr;                  // [2][Lp][dim]
+    const float* prefix = nullptr;       // [Lc][dim]
+    const float* text_emb = nullptr; const float* text_pos = nullptr;
+    const float* speech_emb = nullptr; const float* speech_pos = nullptr;
+    const int* text_ids = nullptr;       // [L] device
+    int Lc = 0, L = 0, Lp = 0, dim = 0, bos = 0, cfg_on = 0;
+};
+void launch_assemble_embeds(const AssembleParams& p, cudaStream_t st);
+
+struct RopeKvParams {
+    bf16* qkv = nullptr; int Lp = 0; int H = 16;
+    bf16* kv = nullptr; long kv_half = 0;
+    const int* page_table = nullptr; int max_pages = 0; int row0 = 0;
+    const float* inv_freq = nullptr;
+};
+void launch_rope_kv_prefill(const RopeKvParams& p, cudaStream_t st);
+void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
+                      float* x, const float* speech_emb, const float* speech_pos, int dim, cudaStream_t st);
+void t3_kernels_init();
+void launch_prompt_embed(float* out, const float* emb, const float* pos, const int* ids, int n, int D, cudaStream_t st);
+void launch_scale_vec(float* out, const float* w, float s, int n, cudaStream_t st);

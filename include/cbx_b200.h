@@ -1,0 +1,111 @@
+/* C-ABI of the B200-native Chatterbox hot path (libcbx_b200.so).
+ *
+ * The reference (akashdeep000/chatterbox-tts) has no FFI: its engine calls a Python object surface
+ * (`chatterbox.*`) from src/tts_streaming.py.  Each entry point below states the reference call
+ * site it replaces; chatterbox-tts_b200/chatterbox/ is the Python shim that binds them with ctypes
+ * so the reference's worker.py / tts_streaming.py keep their interface.
+ *
+ * Conventions: plain pointers and sizes only.  `*_h` pointers are host memory, `*_d` pointers are
+ * device memory on the engine's GPU.  `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy
+ * default stream); work is ordered after everything already enqueued on it, and everything the call
+ * enqueues is visible to later work on it.  Every function returns 0 on success and a non-zero code
+ * on failure; cbx_last_error() then returns a thread-local message.  All functions are thread-safe
+ * and do not touch the Python GIL.  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef CBX_B200_H
+#define CBX_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBX_ABI_VERSION 1
+
+typedef struct cbx_engine cbx_engine;
+
+typedef struct cbx_config {
+    int t3_layers;      /* 30 */
+    int enc_blocks;     /* 6  conformer blocks before the x2 upsample */
+    int up_blocks;      /* 4  conformer blocks after it */
+    int cfm_blocks;     /* 4  transformer blocks per estimator stage */
+    int cfm_mid;        /* 12 mid stages */
+    int cfm_steps;      /* 10 Euler steps */
+    float cfm_cfg_rate; /* 0.7 */
+    int max_streams;    /* concurrent T3 streams (each = 2 CFG rows) */
+    int max_seq;        /* KV positions per row */
+    int max_text;       /* text tokens per T3 call incl. SOT/EOT */
+    int max_s3_tokens;  /* speech tokens per s3gen call (excluding the voice prompt) */
+    int max_prompt_tokens; /* voice prompt tokens (<= 250) */
+    int n_voices;       /* voice-conditioning cache slots */
+    int n_lanes;        /* concurrent s3gen calls */
+} cbx_config;
+
+int cbx_abi_version(void);
+const char* cbx_last_error(void);
+
+/* ChatterboxTTS.from_local(ckpt_dir, device)            -- src/tts_streaming.py:252-258 */
+int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out);
+void cbx_engine_destroy(cbx_engine* e);
+/* registry only, no device needed: lets a host-side packer be checked against cbx_tensor_info (tests) */
+int cbx_manifest_create(const cbx_config* cfg, cbx_engine** out);
+/* checkpoint upload: the engine publishes the packed tensors it wants (name, dtype 0=f32 1=bf16, numel) */
+int cbx_tensor_count(cbx_engine* e);
+int cbx_tensor_info(cbx_engine* e, int idx, char* name, int name_cap, int64_t* numel, int* dtype);
+int cbx_tensor_upload(cbx_engine* e, const char* name, const void* data_h, int64_t nbytes);
+int cbx_finalize(cbx_engine* e); /* fails if any tensor is missing; precomputes CFM time embeddings */
+
+/* voice-conditioning cache: Conditionals(t3_cond, ref_dict) -- src/tts_streaming.py:106-118, :357-384, :386-406 */
+int cbx_voice_put(cbx_engine* e, int voice, const float* speaker_emb_h /*256*/, const int32_t* cond_tokens_h, int n_cond,
+                  float emotion_adv, const int32_t* prompt_token_h, int n_prompt, const float* prompt_feat_h /*n_feat*80*/,
+                  int n_feat, const float* xvector_h /*192*/, void* stream);
+/* clear_voice_cache(voice_id)                            -- src/tts_streaming.py:349-355 */
+int cbx_voice_drop(cbx_engine* e, int voice);
+
+/* T3.inference_stream(t3_cond, text_tokens, max_new_tokens, temperature, cfg_weight)
+ *                                                        -- src/tts_streaming.py:287-292, :420-435
+ * text_ids_h: one row of text ids already framed with SOT/EOT (the engine duplicates it for the CFG row,
+ * :475-478).  Runs the prefill and returns a stream slot. */
+int cbx_t3_open(cbx_engine* e, int voice, const int32_t* text_ids_h, int n_text, float cfg_weight, float temperature,
+                float repetition_penalty, float min_p, float top_p, uint64_t seed, int max_new_tokens, int* slot_out,
+                void* stream);
+/* next() on up to max_streams generators at once: n_steps decode steps for the given slots (batched rows).
+ * noise_d: optional explicit Exp(1) sampling noise [n_steps][n_slots][8194] (parity tests); NULL = Philox(seed). */
+int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps, const float* noise_d, void* stream);
+/* blocking reads of a stream's progress / tokens / last-step logits (2 x 8194: cond row, uncond row) */
+int cbx_t3_poll(cbx_engine* e, int slot, int* n_generated, int* done, void* stream);
+int cbx_t3_tokens(cbx_engine* e, int slot, int from, int count, int32_t* out_h, void* stream);
+int cbx_t3_logits(cbx_engine* e, int slot, float* out_h, void* stream);
+/* generator close()/GC: releases the KV pages             -- cancel path, src/tts_streaming.py:505-519 */
+int cbx_t3_close(cbx_engine* e, int slot);
+
+/* S3Gen.inference(speech_tokens, ref_dict, cache_source) -> (wav, source)
+ *                                                        -- src/tts_streaming.py:316-320, :583-590
+ * tokens_h: n >= 3 ids < 6561.  cache_source_d: m >= 0 samples.  Outputs: 960*n samples each.
+ * mel_out_d (optional, [2n][80]) exposes the CFM result; phase_h[9] / noise_d[9][960n] optionally replace the
+ * SineGen randomness (parity tests); NULL = Philox(seed). */
+int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, const float* cache_source_d, int64_t m,
+                    float* wav_out_d, float* source_out_d, float* mel_out_d, const float* phase_h, const float* noise_d,
+                    uint64_t seed, void* stream);
+/* the two halves of the call above, for teacher-forced parity checks */
+int cbx_flow_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, float* mel_out_d, void* stream);
+int cbx_hift_infer(cbx_engine* e, const float* mel_d /*[frames][80]*/, int frames, const float* cache_source_d, int64_t m,
+                   float* wav_out_d, float* source_out_d, const float* phase_h, const float* noise_d, uint64_t seed, void* stream);
+
+/* equal-power crossfade + clamp + int16 conversion        -- src/tts_streaming.py:710-746 and :149-155
+ * out[i] = int16(clamp(x,-1,1) * 32767) with x = prev_tail[i]*cos + cur[i]*sin for i < fade_len (when prev_tail_d),
+ * x = cur[i] otherwise, for i in [0, n_out). */
+int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const float* prev_tail_d, int fade_len,
+                      int16_t* out_d, void* stream);
+
+/* counters for bench.py: kernels launched by this library since engine creation */
+int64_t cbx_gpu_launches(cbx_engine* e);
+
+/* single-op hooks (kernel unit tests): C[M][N] = A[M][K] * W[N][K]^T (+bias), bf16 in, fp32 out; attention over
+ * fused q|k|v rows; all pointers device. */
+int cbx_op_gemm(const void* a_bf16_d, const void* w_bf16_d, const float* bias_d, float* out_d, int M, int N, int K, void* stream);
+int cbx_op_attention(const void* qkv_bf16_d, void* out_bf16_d, int T, int H, int batch, int causal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

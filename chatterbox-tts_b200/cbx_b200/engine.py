@@ -1,0 +1,500 @@
+"""Streaming engine: the host-side mirror of the reference's `TextToSpeechEngine`
+(src/tts_streaming.py:161-968) over the native B200 path.
+
+Same surface the worker touches (src/worker.py:30-44, :76-77, :100, :113, :129-131):
+`TextToSpeechEngine(device)`, `await ainit()`, `async stream(...)`, `prepare_conditionals(path)`,
+`clear_voice_cache(id)`, `shutdown()`, `.voice_manager`, `.voice_conditioning_executor`.
+Same audio semantics: 35-token slices with a look-ahead of max(3, 0.2*slice) tokens (:499-501, :535),
+"full"/"zero" overlap (:655-659, :694-699), EOS(0) append + <6561 filter + pad to 3 (:661-677),
+lead/trail trim (:702-707), equal-power crossfade state machine (:710-746, :756-760), clamp +
+int16 truncation (:149-155).
+
+What is different (B200-first): T3 decode steps of all concurrent requests are batched
+into one GEMV pass per step by a scheduler thread; S3Gen slices run on engine lanes in parallel with
+T3; crossfade + PCM conversion are one device kernel; there is one thread per request instead of
+three asyncio tasks racing a cancel event per token.
+"""
+import asyncio
+import concurrent.futures
+import os
+import threading
+import time
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import AsyncGenerator, List, Optional
+
+import numpy as np
+import torch
+
+from .config import ModelConfig, S3GEN_SR
+from .native import NativeEngine
+from .text_processing import split_text_into_chunks, SyntheticTokenizer, JsonTokenizer
+
+SPEECH_VOCAB = 6561
+
+
+class CancellationToken:
+    """asyncio.Event-backed token with the reference's interface (src/tts_streaming.py:88-104)."""
+
+    def __init__(self, loop: asyncio.AbstractEventLoop = None):
+        self._event = asyncio.Event()
+        self._flag = threading.Event()
+
+    def cancel(self):
+        self._flag.set()
+        self._event.set()
+
+    def is_cancelled(self) -> bool:
+        return self._flag.is_set()
+
+    async def wait(self):
+        await self._event.wait()
+
+
+class VoiceManager:
+    """voice file lookup: user directory overrides preloaded (reference src/voice_manager.py:39-52)."""
+
+    def __init__(self, voices_dir: str = None, preloaded_voices_dir: str = None):
+        self.voices_dir = voices_dir or os.environ.get("VOICES_DIR", "voices/")
+        self.preloaded_voices_dir = preloaded_voices_dir or os.environ.get("PRELOADED_VOICES_DIR", "preloaded-voices/")
+
+    def get_voice_path(self, voice_id: str):
+        for d in (self.voices_dir, self.preloaded_voices_dir):
+            p = os.path.join(d, voice_id)
+            if os.path.exists(p):
+                return p
+        return None
+
+    def list_voices(self) -> List[str]:
+        out = set()
+        for d in (self.voices_dir, self.preloaded_voices_dir):
+            if os.path.isdir(d):
+                out.update(f for f in os.listdir(d) if os.path.isfile(os.path.join(d, f)))
+        return sorted(out)
+
+
+@dataclass
+class SamplingDefaults:
+    """The reference passes only temperature and cfg_weight (:483-491); the fork's other defaults are
+    unknown, so they are engine settings."""
+    repetition_penalty: float = 1.2
+    min_p: float = 0.05
+    top_p: float = 0.95
+    max_new_tokens: int = 1000
+    tokens_per_word: Optional[int] = None   # benchmark length rule: max_new = tokens_per_word * words
+
+
+class _T3Stream:
+    def __init__(self, slot, max_new):
+        self.slot, self.max_new = slot, max_new
+        self.tokens: List[int] = []
+        self.finished = False
+        self.cancelled = False
+        self.error: Optional[BaseException] = None
+        self.cv = threading.Condition()
+
+
+class T3Scheduler(threading.Thread):
+    """Continuous batching: every round advances all open streams by `steps_per_round` tokens in one
+    batched decode pass (rows = 2 x streams), then hands the new tokens to their requests."""
+
+    def __init__(self, native: NativeEngine, steps_per_round: int = 7, max_batch: int = 8):
+        super().__init__(daemon=True, name="cbx-t3-scheduler")
+        self.native, self.k, self.max_batch = native, steps_per_round, max_batch
+        self.active: List[_T3Stream] = []
+        self.lock = threading.Condition()
+        self.running = True
+        self.rounds = 0
+        self.start()
+
+    def open(self, voice, text_ids, cfg_w, temp, sd: SamplingDefaults, seed, max_new) -> _T3Stream:
+        with torch.cuda.stream(self._stream()):
+            slot = self.native.t3_open(voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new)
+        s = _T3Stream(slot, max_new)
+        with self.lock:
+            self.active.append(s)
+            self.lock.notify_all()
+        return s
+
+    def cancel(self, s: _T3Stream):
+        s.cancelled = True
+
+    _tls = threading.local()
+
+    def _stream(self):
+        if not hasattr(self._tls, "st"):
+            self._tls.st = torch.cuda.Stream()
+        return self._tls.st
+
+    def run(self):
+        torch.cuda.set_device(self.native.device)
+        while self.running:
+            with self.lock:
+                while self.running and not self.active:
+                    self.lock.wait(0.5)
+                if not self.running:
+                    return
+                batch = self.active[: self.max_batch]
+            live = []
+            for s in batch:
+                if s.cancelled:
+                    self._retire(s)
+                else:
+                    live.append(s)
+            if not live:
+                continue
+            try:
+                with torch.cuda.stream(self._stream()):
+                    self.native.t3_step([s.slot for s in live], self.k)
+                    for s in live:
+                        n, done = self.native.t3_poll(s.slot)
+                        new = self.native.t3_tokens(s.slot, len(s.tokens), n - len(s.tokens)).tolist() if n > len(s.tokens) else []
+                        with s.cv:
+                            s.tokens.extend(new)
+                            if done:
+                                s.finished = True
+                            s.cv.notify_all()
+                        if done:
+                            self._retire(s)
+                self.rounds += 1
+            except BaseException as ex:  # surface engine failures to every waiting request
+                for s in live:
+                    with s.cv:
+                        s.error, s.finished = ex, True
+                        s.cv.notify_all()
+                    self._retire(s, close=False)
+            # round-robin fairness when more streams than the batch size are open
+            with self.lock:
+                if len(self.active) > self.max_batch:
+                    self.active = self.active[self.max_batch:] + self.active[: self.max_batch]
+
+    def _retire(self, s: _T3Stream, close=True):
+        with self.lock:
+            if s in self.active:
+                self.active.remove(s)
+        if close:
+            try:
+                self.native.t3_close(s.slot)
+            except Exception:
+                pass
+        with s.cv:
+            s.finished = True
+            s.cv.notify_all()
+
+    def stop(self):
+        self.running = False
+        with self.lock:
+            self.lock.notify_all()
+
+
+def drop_invalid_tokens(x: List[int], sos=6561, eos=6562) -> List[int]:
+    """chatterbox.models.s3tokenizer.drop_invalid_tokens (reference call site :667): keep what lies
+    between the first SOS (exclusive) and the first EOS (exclusive)."""
+    s = x.index(sos) + 1 if sos in x else 0
+    e = x.index(eos) if eos in x else None
+    return x[s:e]
+
+
+class TextToSpeechEngine:
+    ENC_COND_LEN = 6 * 16000
+    DEC_COND_LEN = 10 * S3GEN_SR
+
+    def __init__(self, device: str, cfg: ModelConfig = None, state_dict=None, concurrent_requests: int = None,
+                 sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0):
+        self.device = device
+        self.gpu_id = int(device.split(":")[-1]) if "cuda" in device else -1
+        if self.gpu_id < 0:
+            raise RuntimeError("TextToSpeechEngine (B200 path) needs a cuda:N device; there is no CPU fallback")
+        self.cfg = cfg or ModelConfig()
+        self._state_dict = state_dict
+        self.sampling = sampling or SamplingDefaults()
+        self.sr = S3GEN_SR
+        self.voice_manager = VoiceManager()
+        self.voice_cache = {}            # voice id -> native slot (mirrors the reference dict of Conditionals)
+        self.default_conds = None
+        n = concurrent_requests or int(os.environ.get("CONCURRENT_REQUESTS_PER_WORKER", "1"))
+        self.concurrent_requests = n
+        self.tts_semaphore = None
+        self.request_executor = concurrent.futures.ThreadPoolExecutor(max_workers=n, thread_name_prefix="cbx-req")
+        self.voice_conditioning_executor = concurrent.futures.ThreadPoolExecutor(max_workers=n, thread_name_prefix="cbx-voice")
+        self.native_kwargs = dict(max_streams=max(8, n), n_lanes=max(2, min(n, 8)))
+        self.native_kwargs.update(native_kwargs or {})
+        self.native: Optional[NativeEngine] = None
+        self.scheduler: Optional[T3Scheduler] = None
+        self.tokenizer = None
+        self.seed = seed
+        self._seq = 0
+        self._ready = False
+        self.stats = {"first_chunk_ms": []}
+
+    # ------------------------------------------------------------------ lifecycle (reference ainit :209-339)
+    async def ainit(self):
+        loop = asyncio.get_running_loop()
+        await loop.run_in_executor(self.request_executor, self._init_blocking)
+        self.tts_semaphore = asyncio.Semaphore(self.concurrent_requests)
+        return self
+
+    def _init_blocking(self):
+        from .weights import random_state_dict, synthetic_conditionals
+        torch.cuda.set_device(self.gpu_id)
+        self.native = NativeEngine(self.cfg, device=self.gpu_id, **self.native_kwargs)
+        sd = self._state_dict
+        model_path = os.environ.get("MODEL_PATH", "models")
+        if sd is None:
+            st = os.path.join(model_path, "cbx_b200.safetensors")
+            if os.path.exists(st):
+                from safetensors.torch import load_file
+                sd = load_file(st)
+            else:   # BASELINE.json configs: random-init Chatterbox weights
+                sd = random_state_dict(self.cfg, self.seed)
+        self.native.load_state_dict(sd)
+        self._state_dict = None
+        tj = os.path.join(model_path, "tokenizer.json")
+        self.tokenizer = JsonTokenizer(tj) if os.path.exists(tj) else SyntheticTokenizer(self.cfg.t3.text_vocab)
+        self.default_conds = synthetic_conditionals(self.cfg)      # stands in for conds.pt (tts.conds, :399-404)
+        self.voice_cache["default"] = self.native.voice_put("default", self.default_conds["t3"], self.default_conds["gen"])
+        self.scheduler = T3Scheduler(self.native, max_batch=min(8, self.native_kwargs["max_streams"]))
+        # warm-up, as the reference does (:274-326): 4 T3 tokens with cfg 0, one tiny S3Gen call
+        text = [self.cfg.t3.start_text_token] + self.tokenizer.text_to_tokens("compiling")[0].tolist() + [self.cfg.t3.stop_text_token]
+        s = self.scheduler.open(self.voice_cache["default"], text, 0.0, 0.8, self.sampling, 0, 4)
+        self._wait_tokens(s, 4, None)
+        self.native.s3gen_infer(self.voice_cache["default"], [0, 0, 0])
+        torch.cuda.synchronize()
+        self._ready = True
+
+    def shutdown(self):
+        if self.scheduler:
+            self.scheduler.stop()
+        self.request_executor.shutdown(wait=True)
+        self.voice_conditioning_executor.shutdown(wait=True)
+        if self.native:
+            self.native.close()
+
+    # ------------------------------------------------------------------ voices (reference :349-406)
+    def clear_voice_cache(self, voice_id: str):
+        if voice_id in self.voice_cache and voice_id != "default":
+            del self.voice_cache[voice_id]
+            self.native.voice_drop(voice_id)
+
+    def put_conditionals(self, voice_id: str, t3_cond: dict, gen: dict):
+        self.voice_cache[voice_id] = self.native.voice_put(voice_id, t3_cond, gen)
+
+    def prepare_conditionals(self, wav_fpath: str):
+        """Reference :357-384 runs the conditioning encoders (S3Tokenizer, CAMPPlus, VoiceEncoder, mel) on
+        the reference clip.  Those encoders are the next scope row; until they exist on the
+        GPU the clip only determines the *shapes*: 25 prompt tokens and 50 mel frames per second of the
+        first 10 s, contents seeded from the file name."""
+        from .weights import synthetic_conditionals
+        import zlib
+        import scipy.io.wavfile as wavfile
+        sr, data = wavfile.read(wav_fpath)
+        secs = min(data.shape[0] / float(sr), 10.0)
+        ntok = max(3, min(int(secs * 25), 250))
+        voice_id = Path(wav_fpath).name
+        c = synthetic_conditionals(self.cfg, seed=zlib.crc32(voice_id.encode()) & 0x7FFFFFFF, prompt_tokens=ntok)
+        c["t3"]["emotion_adv"] = float(os.environ.get("TTS_VOICE_EXAGGERATION_FACTOR", "0.5")) * torch.ones(1, 1, 1)
+        self.put_conditionals(voice_id, c["t3"], c["gen"])
+
+    # ------------------------------------------------------------------ helpers
+    def _wait_tokens(self, s: _T3Stream, n: int, token: Optional[CancellationToken]):
+        """Blocks until the stream holds >= n tokens or is finished."""
+        with s.cv:
+            while len(s.tokens) < n and not s.finished:
+                if token is not None and token.is_cancelled():
+                    self.scheduler.cancel(s)
+                    return False
+                s.cv.wait(0.05)
+            if s.error:
+                raise s.error
+        return True
+
+    # ------------------------------------------------------------------ the request pipeline (one thread per request)
+    def _run_request(self, text, voice_id, cfg_w, temp, chunk_size, slice_len, trim_tail_ms, trim_lead_ms, overlap, fade_ms,
+                     request_id, token: Optional[CancellationToken], emit, t_start):
+        torch.cuda.set_device(self.gpu_id)
+        st = torch.cuda.Stream()
+        nat, sched = self.native, self.scheduler
+        with torch.cuda.stream(st):
+            if voice_id:
+                vid = Path(voice_id).name
+                if vid not in self.voice_cache:
+                    path = self.voice_manager.get_voice_path(voice_id)
+                    if path is None:
+                        raise ValueError(f"voice '{voice_id}' not found")
+                    self.prepare_conditionals(path)
+                voice = self.voice_cache[vid]
+            else:
+                voice = self.voice_cache["default"]
+            chunks = split_text_into_chunks(text, chunk_size)
+            if not chunks:
+                emit(b"")
+                return
+            fade_len = int(self.sr * (fade_ms / 1000.0))
+            look_ahead = max(3, int(0.2 * slice_len))
+            lead = (trim_lead_ms * self.sr) // 1000
+            trail = (trim_tail_ms * self.sr) // 1000
+            prev_tail = None
+            first_sent = False
+            self._seq += 1
+            base_seed = (self.seed << 20) ^ (hash(request_id) & 0xFFFFF) ^ (self._seq << 8)
+
+            def send(cur, n_out, tail):
+                """crossfade (optional) + PCM on device, then D2H and hand the bytes to the event loop."""
+                if n_out <= 0:
+                    return
+                pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0)
+                host = pcm.cpu()          # stream-ordered D2H of n_out int16 samples
+                emit(host.numpy().tobytes())
+
+            streams = [None] * len(chunks)
+
+            def open_chunk(i):
+                ids = self.tokenizer.text_to_tokens(chunks[i])[0].tolist()
+                ids = [self.cfg.t3.start_text_token] + ids + [self.cfg.t3.stop_text_token]
+                max_new = self.sampling.max_new_tokens
+                if self.sampling.tokens_per_word:
+                    max_new = max(1, self.sampling.tokens_per_word * len(chunks[i].split()))
+                streams[i] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + i, max_new)
+
+            open_chunk(0)
+            for ci in range(len(chunks)):
+                if token is not None and token.is_cancelled():
+                    break
+                s = streams[ci]
+                is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
+                consumed, slice_idx, acc, cache_source, prev_len = 0, 0, [], None, 0
+                opened_next = False
+                while True:
+                    if not self._wait_tokens(s, consumed + slice_len + look_ahead, token):
+                        break
+                    # T3 of the next text chunk starts as soon as this one has finished decoding
+                    if s.finished and not opened_next and ci + 1 < len(chunks):
+                        open_chunk(ci + 1)
+                        opened_next = True
+                    avail = len(s.tokens) - consumed
+                    if avail >= slice_len + look_ahead:
+                        new, last = s.tokens[consumed: consumed + slice_len], False
+                    elif s.finished:
+                        if avail <= 0:
+                            break
+                        new, last = s.tokens[consumed:], True
+                    else:
+                        continue
+                    consumed += len(new)
+                    slice_idx += 1
+                    first_slice = slice_idx == 1
+                    acc = acc + new if overlap == "full" else new
+                    toks = list(acc)
+                    if last:
+                        toks = toks + [self.cfg.t3.stop_text_token]          # reference appends hp.stop_text_token (0)
+                    toks = [t for t in drop_invalid_tokens(toks) if t < SPEECH_VOCAB]
+                    if len(toks) == 0:
+                        if last:
+                            break
+                        continue
+                    if len(toks) < 3:
+                        toks = toks + [0] * (3 - len(toks))
+                    wav, src = nat.s3gen_infer(voice, toks, cache_source=cache_source, seed=base_seed + 7919 * ci + slice_idx)
+                    cur = wav[0]
+                    if overlap == "full":
+                        cache_source = src
+                        full_len = cur.shape[0]
+                        if not first_slice:
+                            cur = cur[prev_len:]
+                        prev_len = full_len
+                    if is_first_chunk and first_slice and lead > 0 and cur.shape[0] > lead:
+                        cur = cur[lead:]
+                    if is_last_chunk and last and trail > 0 and cur.shape[0] > trail:
+                        cur = cur[:-trail]
+                    n = cur.shape[0]
+                    # crossfade state machine (reference :710-746)
+                    if not first_sent:
+                        if fade_len > 0 and n > fade_len:
+                            send(cur, n - fade_len, None)
+                            prev_tail = cur[n - fade_len:]
+                        else:
+                            send(cur, n, None)
+                            prev_tail = None
+                        first_sent = True
+                    else:
+                        can_fade = fade_len > 0 and prev_tail is not None and prev_tail.shape[0] == fade_len and n > fade_len
+                        if can_fade:
+                            body = n - 2 * fade_len if n > 2 * fade_len else 0
+                            send(cur, fade_len + body, prev_tail)
+                            prev_tail = cur[n - fade_len:]
+                        else:
+                            if prev_tail is not None:
+                                send(prev_tail, prev_tail.shape[0], None)
+                            prev_tail = cur[n - fade_len:] if (fade_len > 0 and n > fade_len) else cur
+                    if last:
+                        break
+                if not opened_next and ci + 1 < len(chunks) and not (token is not None and token.is_cancelled()):
+                    open_chunk(ci + 1)
+            if prev_tail is not None and prev_tail.shape[0] > 0 and not (token is not None and token.is_cancelled()):
+                send(prev_tail, prev_tail.shape[0], None)     # reference `finally` flush (:756-760)
+            for s in streams:
+                if s is not None and not s.finished:
+                    sched.cancel(s)
+
+    # ------------------------------------------------------------------ public API (reference stream :815-968)
+    async def stream(self, text: str, output_format: str, voice_id: Optional[str], cfg_guidance_weight: float,
+                     synthesis_temperature: float, text_processing_chunk_size: int, audio_tokens_per_slice: int,
+                     remove_trailing_milliseconds: int, remove_leading_milliseconds: int, chunk_overlap_strategy: str,
+                     crossfade_duration_milliseconds: int, request_id: str,
+                     cancellation_token: Optional[CancellationToken] = None) -> AsyncGenerator[bytes, None]:
+        if not self._ready:
+            raise RuntimeError(f"TTS Engine on GPU {self.gpu_id} is not ready")
+        if output_format not in ("raw_pcm", "wav"):
+            raise ValueError(f"Unsupported format on the B200 path: {output_format} (containers are muxed by the caller)")
+        async with self.tts_semaphore:
+            loop = asyncio.get_running_loop()
+            q: asyncio.Queue = asyncio.Queue(maxsize=int(os.environ.get("TTS_PCM_CHUNK_QUEUE_MAX_SIZE", "3")))
+            t_start = time.time()
+            DONE = object()
+
+            def emit(b):   # called from the request thread; blocks it when the consumer is slow (bounded queue)
+                asyncio.run_coroutine_threadsafe(q.put(b), loop).result()
+
+            def work():
+                try:
+                    self._run_request(text, voice_id, cfg_guidance_weight, synthesis_temperature, text_processing_chunk_size,
+                                      audio_tokens_per_slice, remove_trailing_milliseconds, remove_leading_milliseconds,
+                                      chunk_overlap_strategy, crossfade_duration_milliseconds, request_id, cancellation_token,
+                                      emit, t_start)
+                    emit(DONE)
+                except BaseException as ex:
+                    emit(ex)
+
+            fut = loop.run_in_executor(self.request_executor, work)
+            first = True
+            try:
+                if output_format == "wav":
+                    yield _wav_header(self.sr)
+                while True:
+                    item = await q.get()
+                    if item is DONE:
+                        break
+                    if isinstance(item, BaseException):
+                        raise item
+                    if first and len(item):
+                        self.stats["first_chunk_ms"].append((time.time() - t_start) * 1e3)
+                        first = False
+                    yield item
+            finally:
+                if cancellation_token is not None and not fut.done():
+                    cancellation_token.cancel()
+                while not fut.done():        # drain so the worker thread is never blocked on a full queue
+                    try:
+                        q.get_nowait()
+                    except asyncio.QueueEmpty:
+                        await asyncio.sleep(0.005)
+
+
+def _wav_header(sr: int, channels: int = 1, bits: int = 16) -> bytes:
+    """Streaming WAV header with unknown size 0xFFFFFFFF (reference src/audio_encoding.py:97-115)."""
+    import struct
+    byte_rate = sr * channels * bits // 8
+    h = struct.pack("<4sL4s", b"RIFF", 0xFFFFFFFF, b"WAVE")
+    h += struct.pack("<4sLHHLLHH", b"fmt ", 16, 1, channels, sr, byte_rate, channels * bits // 8, bits)
+    h += struct.pack("<4sL", b"data", 0xFFFFFFFF)
+    return h

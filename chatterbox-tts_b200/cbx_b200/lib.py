@@ -37,6 +37,8 @@ SIGNATURES = {
     "cbx_s3gen_infer": (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P, _P, _U64, _P]),
     "cbx_flow_infer": (_I, [_P, _I, _P, _I, _P, _P]),
     "cbx_hift_infer": (_I, [_P, _P, _I, _P, _L, _P, _P, _P, _P, _U64, _P]),
+    "cbx_hift_f0": (_I, [_P, _P, _I, _P, _P]),
+    "cbx_hift_source": (_I, [_P, _P, _I, _P, _P, _U64, _P, _P]),
     "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "cbx_gpu_launches": (_L, [_P]),
     "cbx_op_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),

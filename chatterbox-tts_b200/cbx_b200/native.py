@@ -174,6 +174,21 @@ class NativeEngine:
                                         C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, _stream_ptr()))
         return wav, src
 
+    def hift_f0(self, mel):
+        mel = mel.contiguous().float()
+        f0 = torch.empty(mel.shape[0], device=mel.device, dtype=torch.float32)
+        L.check(self.lib.cbx_hift_f0(self.h, C.c_void_p(mel.data_ptr()), mel.shape[0], C.c_void_p(f0.data_ptr()), _stream_ptr()))
+        return f0
+
+    def hift_source(self, f0, phase=None, noise=None, seed=0):
+        f0 = f0.contiguous().float()
+        T = f0.shape[0]
+        src = torch.empty(1, 1, 480 * T, device=f0.device, dtype=torch.float32)
+        ph = _f32(phase) if phase is not None else None
+        L.check(self.lib.cbx_hift_source(self.h, C.c_void_p(f0.data_ptr()), T, ph.ctypes.data if ph is not None else None,
+                                         C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, C.c_void_p(src.data_ptr()), _stream_ptr()))
+        return src
+
     def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0):
         out = torch.empty(n_out, device=cur.device, dtype=torch.int16)
         L.check(self.lib.cbx_crossfade_pcm(self.h, C.c_void_p(cur.data_ptr()), n_out,

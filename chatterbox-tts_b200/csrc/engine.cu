@@ -283,6 +283,33 @@ int cbx_hift_infer(cbx_engine* e, const float* mel_d, int frames, const float* c
     CBX_API_END
 }
 
+int cbx_hift_f0(cbx_engine* e, const float* mel_d, int frames, float* f0_out_d, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && mel_d && f0_out_d && frames >= 1 && frames <= 2 * e->cfg.max_s3_tokens, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = pick_lane(e);
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    CBX_CHECK(cudaMemcpyAsync(L.mel, mel_d, (size_t)frames * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    hift_f0(e, L, frames, L.st);
+    CBX_CHECK(cudaMemcpyAsync(f0_out_d, L.h_f0, (size_t)frames * 4, cudaMemcpyDeviceToDevice, L.st));
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_hift_source(cbx_engine* e, const float* f0_d, int frames, const float* phase_h, const float* noise_d, uint64_t seed,
+                    float* source_out_d, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && f0_d && source_out_d && frames >= 1 && frames <= 2 * e->cfg.max_s3_tokens, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = pick_lane(e);
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    hift_source(e, L, f0_d, frames, nullptr, 0, source_out_d, phase_h, noise_d, seed, L.st);
+    br.finish();
+    CBX_API_END
+}
+
 int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, const float* cache_source_d, int64_t m, float* wav_out_d,
                     float* source_out_d, float* mel_out_d, const float* phase_h, const float* noise_d, uint64_t seed, void* stream) {
     CBX_API_BEGIN

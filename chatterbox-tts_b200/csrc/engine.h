@@ -117,6 +117,9 @@ void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int
 void hift_build(cbx_engine* e);
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st);
+void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st);
+void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* cache_src_dev, long m, float* src_out,
+                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st);
 void lane_alloc(cbx_engine* e, Lane& L);
 
 template <typename T> T* cbx_engine::reg(const std::string& name, int dtype, long numel) {

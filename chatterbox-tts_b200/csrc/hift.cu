@@ -80,20 +80,13 @@ static void resblock(cbx_engine* e, const ResBlockP& r, const float* x_in, float
     e->gpu_launches += 7;
 }
 
-void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
-                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st) {
+// mel (L.mel fp32 [Tg][80]) -> L.h_f0 [Tg]; also stages the bf16 mel for conv_pre
+void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st) {
     HiftModel& h = e->hift;
-    CBX_REQUIRE(Tg >= 1 && Tg <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
-    const long Ls = (long)Tg * H_UP, F = 120L * Tg + 1;
-    CBX_REQUIRE(m >= 0 && m <= Ls, "hift: cache_source longer than the generated source");
-    const long tlen[4] = {Tg, 8L * Tg, 40L * Tg, F};
     auto zero_tail = [&](bf16* buf, long T, int C) { CBX_CHECK(cudaMemsetAsync(buf + (H_HALO + T) * C, 0, (size_t)H_HALO * C * 2, st)); };
-    zero_tail(L.h_mel, Tg, MEL); zero_tail(L.h_f0a, Tg, H_F0CH); zero_tail(L.h_f0b, Tg, H_F0CH); zero_tail(L.h_stft, F, H_NSRC_PAD);
-    for (int i = 0; i < 4; i++) zero_tail(L.h_xb[i], tlen[i], H_BASE >> i);
-    for (int i = 0; i < 3; i++) { zero_tail(L.h_a[i], tlen[i + 1], H_BASE >> (i + 1)); zero_tail(L.h_b[i], tlen[i + 1], H_BASE >> (i + 1)); }
-
+    zero_tail(L.h_mel, Tg, MEL); zero_tail(L.h_f0a, Tg, H_F0CH); zero_tail(L.h_f0b, Tg, H_F0CH);
     launch_f32_to_bf16_rows(L.mel, MEL, L.h_mel + (long)H_HALO * MEL, MEL, Tg, MEL, ACT_NONE, 0.f, st);
-    // ---- F0 predictor: 5 x (conv k3 + ELU) -> |linear|
+    // F0 predictor: 5 x (conv k3 + ELU) -> |linear|
     const bf16* fin = L.h_mel; int cin = MEL;
     bf16* pp[2] = {L.h_f0a, L.h_f0b};
     for (int l = 0; l < 5; l++) {
@@ -103,8 +96,14 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
         fin = pp[l & 1]; cin = H_F0CH;
     }
     launch_f0_classifier(fin + (long)H_HALO * H_F0CH, H_F0CH, h.f0w, h.f0b, L.h_f0, Tg, H_F0CH, st);
-    // ---- source
-    SourceParams sp; sp.f0 = L.h_f0; sp.cum = L.h_cum; sp.s = src_out; sp.L = Ls; sp.up = H_UP; sp.sr = 24000.f; sp.n_harm = H_NHARM;
+    e->gpu_launches += 7;
+}
+
+// f0 [Tg] -> source [480*Tg] (SineGen + SourceModuleHnNSF), first m samples taken from cache_source
+void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* cache_src_dev, long m, float* src_out,
+                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st) {
+    HiftModel& h = e->hift;
+    SourceParams sp; sp.f0 = f0; sp.cum = L.h_cum; sp.s = src_out; sp.L = (long)Tg * H_UP; sp.up = H_UP; sp.sr = 24000.f; sp.n_harm = H_NHARM;
     sp.lw = h.lw; sp.lb = h.lb; sp.noise = noise_dev; sp.cache = cache_src_dev; sp.cache_len = m; sp.seed = seed;
     if (phase_h) {
         CBX_CHECK(cudaMemcpyAsync(L.h_phase, phase_h, H_NHARM * 4, cudaMemcpyHostToDevice, st));
@@ -112,6 +111,22 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
         sp.phase = L.h_phase;
     }
     launch_source(sp, Tg, st);
+    e->gpu_launches += 2;
+}
+
+void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
+                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st) {
+    HiftModel& h = e->hift;
+    CBX_REQUIRE(Tg >= 1 && Tg <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
+    const long Ls = (long)Tg * H_UP, F = 120L * Tg + 1;
+    CBX_REQUIRE(m >= 0 && m <= Ls, "hift: cache_source longer than the generated source");
+    const long tlen[4] = {Tg, 8L * Tg, 40L * Tg, F};
+    auto zero_tail = [&](bf16* buf, long T, int C) { CBX_CHECK(cudaMemsetAsync(buf + (H_HALO + T) * C, 0, (size_t)H_HALO * C * 2, st)); };
+    zero_tail(L.h_stft, F, H_NSRC_PAD);
+    for (int i = 0; i < 4; i++) zero_tail(L.h_xb[i], tlen[i], H_BASE >> i);
+    for (int i = 0; i < 3; i++) { zero_tail(L.h_a[i], tlen[i + 1], H_BASE >> (i + 1)); zero_tail(L.h_b[i], tlen[i + 1], H_BASE >> (i + 1)); }
+    hift_f0(e, L, Tg, st);
+    hift_source(e, L, L.h_f0, Tg, cache_src_dev, m, src_out, phase_h, noise_dev, seed, st);
     launch_stft16(src_out, Ls, L.h_stft + (long)H_HALO * H_NSRC_PAD, H_NSRC_PAD, (int)F, st);
     // ---- conv_pre (+ the leaky_relu that precedes ups[0])
     {
@@ -119,7 +134,7 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
         g.act = ACT_LRELU; g.act_param = 0.1f; g.outB = L.h_xb[0] + (long)H_HALO * H_BASE; g.ldc = H_BASE;
         launch_gemm(g, st);
     }
-    e->gpu_launches += 11;
+    e->gpu_launches += 2;
     for (int i = 0; i < 3; i++) {
         const int cin_i = H_BASE >> i, ch = H_BASE >> (i + 1), u = UPS_U[i], k = UPS_K[i], p = (k - u) / 2, taps = (k + u - 1) / u;
         const long Tin = tlen[i], Tout = tlen[i + 1];

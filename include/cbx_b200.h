@@ -91,6 +91,11 @@ int cbx_flow_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, flo
 int cbx_hift_infer(cbx_engine* e, const float* mel_d /*[frames][80]*/, int frames, const float* cache_source_d, int64_t m,
                    float* wav_out_d, float* source_out_d, const float* phase_h, const float* noise_d, uint64_t seed, void* stream);
 
+/* HiFT stages for parity tests: mel -> f0 (ConvRNNF0Predictor) and f0 -> source (SineGen + SourceModuleHnNSF) */
+int cbx_hift_f0(cbx_engine* e, const float* mel_d, int frames, float* f0_out_d, void* stream);
+int cbx_hift_source(cbx_engine* e, const float* f0_d, int frames, const float* phase_h, const float* noise_d, uint64_t seed,
+                    float* source_out_d, void* stream);
+
 /* equal-power crossfade + clamp + int16 conversion        -- src/tts_streaming.py:710-746 and :149-155
  * out[i] = int16(clamp(x,-1,1) * 32767) with x = prev_tail[i]*cos + cur[i]*sin for i < fade_len (when prev_tail_d),
  * x = cur[i] otherwise, for i in [0, n_out). */

@@ -19,6 +19,7 @@ import concurrent.futures
 import os
 import threading
 import time
+import zlib
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import AsyncGenerator, List, Optional
@@ -200,7 +201,7 @@ class TextToSpeechEngine:
     DEC_COND_LEN = 10 * S3GEN_SR
 
     def __init__(self, device: str, cfg: ModelConfig = None, state_dict=None, concurrent_requests: int = None,
-                 sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0):
+                 sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0, device_sink: bool = False):
         self.device = device
         self.gpu_id = int(device.split(":")[-1]) if "cuda" in device else -1
         if self.gpu_id < 0:
@@ -223,6 +224,7 @@ class TextToSpeechEngine:
         self.scheduler: Optional[T3Scheduler] = None
         self.tokenizer = None
         self.seed = seed
+        self.device_sink = device_sink   # bench `value` leg: PCM stays in HBM, emit() receives sample counts
         self._seq = 0
         self._ready = False
         self.stats = {"first_chunk_ms": []}
@@ -336,13 +338,16 @@ class TextToSpeechEngine:
             prev_tail = None
             first_sent = False
             self._seq += 1
-            base_seed = (self.seed << 20) ^ (hash(request_id) & 0xFFFFF) ^ (self._seq << 8)
+            base_seed = (self.seed << 20) ^ (zlib.crc32(str(request_id).encode()) & 0xFFFFF) ^ (self._seq << 8)
 
             def send(cur, n_out, tail):
                 """crossfade (optional) + PCM on device, then D2H and hand the bytes to the event loop."""
                 if n_out <= 0:
                     return
                 pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0)
+                if self.device_sink:
+                    emit(int(n_out))
+                    return
                 host = pcm.cpu()          # stream-ordered D2H of n_out int16 samples
                 emit(host.numpy().tobytes())
 

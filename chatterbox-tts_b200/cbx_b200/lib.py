@@ -41,6 +41,9 @@ SIGNATURES = {
     "cbx_hift_source": (_I, [_P, _P, _I, _P, _P, _U64, _P, _P]),
     "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "cbx_gpu_launches": (_L, [_P]),
+    "cbx_gemm_tc_launches": (C.c_longlong, []),
+    "cbx_profile_begin": (_I, []),
+    "cbx_profile_end": (_I, [_P, _P, _P, _I]),
     "cbx_op_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cbx_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
 }

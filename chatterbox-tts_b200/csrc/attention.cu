@@ -161,15 +161,13 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
 
 }  // namespace
 
+void attention_init() { CBX_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * TILE_BYTES)); }
+
 void launch_attention(const AttnParams& p, cudaStream_t st) {
     CBX_REQUIRE(p.T > 0 && p.H > 0 && p.batch > 0, "attention: empty problem");
     CBX_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "attention: row strides must keep 16B alignment");
-    static bool attr_set = false;
     const int smem = 5 * TILE_BYTES;
-    if (!attr_set) {
-        CBX_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    ProfScope ps(PC_ATTN, 4.0 * p.T * p.T * D * p.H * p.batch * (p.causal ? 0.5 : 1.0), st);
     dim3 grid(cdiv(p.T, BQ), p.H, p.batch);
     attn_kernel<<<grid, NT, smem, st>>>(p);
     CBX_CHECK(cudaGetLastError());

@@ -112,6 +112,17 @@ struct Philox {
 // u32 -> float in (0,1]
 __host__ __device__ static inline float u32_to_unit(uint32_t x) { return ((x >> 8) + 1) * (1.0f / 16777216.0f); }
 
+// ---------------------------------------------------------------- per-launch profiler (bench.py roofline pass)
+enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_GEMV = 2, PC_DECODE_ATTN = 3, PC_SAMPLER = 4, PC_NORM = 5, PC_ELEMWISE = 6, PC_HIFT_MISC = 7, PC_COUNT = 8 };
+bool prof_enabled();
+void prof_begin_launch(int cls, double work, cudaStream_t st);   // work: FLOPs (GEMM/ATTN) or bytes (everything else)
+void prof_end_launch(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st; bool on;
+    ProfScope(int cls, double work, cudaStream_t s) : st(s), on(prof_enabled()) { if (on) prof_begin_launch(cls, work, st); }
+    ~ProfScope() { if (on) prof_end_launch(st); }
+};
+
 // ---------------------------------------------------------------- GEMM descriptor (implemented in gemm.cu)
 // C[b][m][n] = epilogue( sum_kk A(b,m,kk) * W(b,n,kk) )
 //   A(b,m,kk) = A[b*a_bs + m*lda + (kk/kc)*tap_stride + kk%kc]   (bf16)  -> conv1d over time-major channels-last activations
@@ -132,6 +143,9 @@ struct GemmParams {
     int ct_u = 0, ct_cout = 0, ct_pad = 0, ct_len = 0;
 };
 void launch_gemm(const GemmParams& p, cudaStream_t st);
+void gemm_init();
+void gemm_tc_init();
+bool launch_gemm_tc(const GemmParams& p, cudaStream_t st);   // per-device kernel attributes (call once after cudaSetDevice)
 
 // flash attention (attention.cu): o[b][t][h*64+d] = softmax_j(scale*(q.k + bias)) v
 struct AttnParams {
@@ -141,3 +155,4 @@ struct AttnParams {
     const float* relbias = nullptr; long rb_ld = 0; long rb_hs = 0;  // bias[h*rb_hs + i*rb_ld + (T-1-i+j)]
 };
 void launch_attention(const AttnParams& p, cudaStream_t st);
+void attention_init();

@@ -75,6 +75,7 @@ int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
     CBX_REQUIRE(cfg->max_prompt_tokens >= 1 && cfg->max_s3_tokens >= 3 && 2 * (cfg->max_prompt_tokens + cfg->max_s3_tokens) <= NOISE_LEN, "bad s3gen capacity");
     cbx_engine* e = new cbx_engine();
     e->cfg = *cfg; e->device = device;
+    gemm_init(); attention_init();
     t3_build(e); flow_build(e); hift_build(e);
     t3_alloc(e);
     CBX_CHECK(cudaStreamCreateWithFlags(&e->t3_st, cudaStreamNonBlocking));
@@ -111,7 +112,7 @@ void cbx_engine_destroy(cbx_engine* e) {
     for (auto& kv : e->t3.step_graphs) cudaGraphExecDestroy(kv.second);
     for (auto& t : e->tensors) cudaFree(t.ptr);
     for (void* p : e->scratch_allocs) cudaFree(p);
-    for (Lane* L : e->lanes) { cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
+    for (Lane* L : e->lanes) { for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second); cudaFreeHost(L->g_dyn_h); cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
     cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
     delete e;
 }
@@ -174,7 +175,7 @@ int cbx_voice_put(cbx_engine* e, int voice, const float* speaker_emb_h, const in
     launch_spk_affine(xv, F_SPK, e->flow.spk_w, e->flow.spk_b, v.spks, MEL, e->t3_st);
     CBX_CHECK(cudaStreamSynchronize(e->t3_st));
     cudaFree(xv);
-    v.n_prompt = n_prompt; v.n_feat = n_feat; v.valid = true;
+    v.n_prompt = n_prompt; v.n_feat = n_feat; v.version++; v.valid = true;
     br.finish();
     CBX_API_END
 }
@@ -321,9 +322,48 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
     std::lock_guard<std::mutex> g(L.lock);
     StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
     const Voice& v = e->voices[voice];
-    flow_infer(e, L, v, tokens_h, n, L.st);
+    const long Ls = 960L * n;
+    CBX_REQUIRE(m >= 0 && m <= Ls, "s3gen: cache_source longer than the generated source");
+    flow_stage(e, L, v, tokens_h, n, L.st);
+    const bool direct = phase_h || noise_d || prof_enabled();
+    if (direct) {
+        // explicit SineGen randomness (parity tests) or per-launch profiling: plain launches
+        flow_run(e, L, v, n, L.st);
+        hift_infer(e, L, 2 * n, cache_source_d, m, wav_out_d, source_out_d, phase_h, noise_d, seed, L.st);
+    } else {
+        // steady state: the whole device-side call (~5k launches) is one CUDA graph per (voice, prompt, n) shape
+        if (m) CBX_CHECK(cudaMemcpyAsync(L.g_cache, cache_source_d, (size_t)m * 4, cudaMemcpyDeviceToDevice, L.st));
+        CBX_CHECK(cudaStreamSynchronize(L.st));          // previous call's read of the pinned params has retired
+        L.g_dyn_h->cache_len = m; L.g_dyn_h->seed = seed;
+        CBX_CHECK(cudaMemcpyAsync(L.g_dyn, L.g_dyn_h, sizeof(SourceDyn), cudaMemcpyHostToDevice, L.st));
+        const unsigned long long key = ((unsigned long long)voice << 48) | ((unsigned long long)(v.version & 0xFFFF) << 32) | ((unsigned long long)v.n_prompt << 16) | (unsigned long long)n;
+        auto it = L.graphs.find(key);
+        if (it == L.graphs.end()) {
+            const long before = e->gpu_launches;
+            cudaGraph_t graph;
+            CBX_CHECK(cudaStreamBeginCapture(L.st, cudaStreamCaptureModeThreadLocal));
+            try {
+                flow_run(e, L, v, n, L.st);
+                hift_infer(e, L, 2 * n, L.g_cache, 0, L.g_wav, L.g_src, nullptr, nullptr, 0, L.st, L.g_dyn);
+            } catch (...) {
+                cudaGraph_t junk; cudaStreamEndCapture(L.st, &junk);
+                throw;
+            }
+            CBX_CHECK(cudaStreamEndCapture(L.st, &graph));
+            cudaGraphExec_t exec;
+            CBX_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+            CBX_CHECK(cudaGraphDestroy(graph));
+            if (L.graphs.size() >= 64) { for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second); L.graphs.clear(); }
+            it = L.graphs.emplace(key, exec).first;
+            L.launches_per_graph[key] = e->gpu_launches - before;
+            e->gpu_launches = before;
+        }
+        CBX_CHECK(cudaGraphLaunch(it->second, L.st));
+        e->gpu_launches += L.launches_per_graph[key];
+        CBX_CHECK(cudaMemcpyAsync(wav_out_d, L.g_wav, (size_t)Ls * 4, cudaMemcpyDeviceToDevice, L.st));
+        CBX_CHECK(cudaMemcpyAsync(source_out_d, L.g_src, (size_t)Ls * 4, cudaMemcpyDeviceToDevice, L.st));
+    }
     if (mel_out_d) CBX_CHECK(cudaMemcpyAsync(mel_out_d, L.mel, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
-    hift_infer(e, L, 2 * n, cache_source_d, m, wav_out_d, source_out_d, phase_h, noise_d, seed, L.st);
     br.finish();
     CBX_API_END
 }

@@ -69,7 +69,7 @@ struct HiftModel {
 };
 
 struct Voice {
-    bool valid = false; float* prefix = nullptr;   // [34][1024]
+    bool valid = false; int version = 0; float* prefix = nullptr;   // [34][1024]
     int n_prompt = 0, n_feat = 0; int* prompt_token = nullptr; float* prompt_feat = nullptr; float* spks = nullptr;
 };
 
@@ -83,6 +83,10 @@ struct Lane {   // S3Gen workspace (one call at a time)
     float* mel; bf16 *h_mel, *h_f0a, *h_f0b, *h_stft; float *h_f0, *h_s; double* h_cum;
     bf16* h_xb[4];          // halo'd bf16 inputs of conv_pre output / ups outputs (lrelu'd)
     float *h_x[3], *h_r[3], *h_acc[3], *h_si[3]; bf16 *h_a[3], *h_b[3]; float* h_post; float* h_phase;
+    // graph-replayed s3gen calls: lane-owned I/O buffers + per-call dynamic params, graphs keyed by (voice, n_prompt, n)
+    float *g_wav, *g_src, *g_cache; SourceDyn* g_dyn; SourceDyn* g_dyn_h;
+    std::unordered_map<unsigned long long, cudaGraphExec_t> graphs;
+    std::unordered_map<unsigned long long, long> launches_per_graph;
 };
 
 struct cbx_engine {
@@ -116,10 +120,12 @@ void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int
 
 void hift_build(cbx_engine* e);
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
-                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st);
+                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr);
+void flow_stage(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st);
+void flow_run(cbx_engine* e, Lane& L, const Voice& v, int n, cudaStream_t st);
 void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st);
 void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* cache_src_dev, long m, float* src_out,
-                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st);
+                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr);
 void lane_alloc(cbx_engine* e, Lane& L);
 
 template <typename T> T* cbx_engine::reg(const std::string& name, int dtype, long numel) {

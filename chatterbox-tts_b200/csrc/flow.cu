@@ -138,6 +138,9 @@ void lane_alloc(cbx_engine* e, Lane& L) {
     }
     L.h_post = e->scratch<float>(F * H_NSRC);
     L.h_phase = e->scratch<float>(16);
+    L.g_wav = e->scratch<float>(Tg * H_UP); L.g_src = e->scratch<float>(Tg * H_UP); L.g_cache = e->scratch<float>(Tg * H_UP);
+    L.g_dyn = e->scratch<SourceDyn>(1);
+    CBX_CHECK(cudaMallocHost(&L.g_dyn_h, sizeof(SourceDyn)));
 }
 
 // ---------------------------------------------------------------------------------------------- encoder
@@ -264,17 +267,24 @@ static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) 
     e->gpu_launches += 5;
 }
 
-void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st) {
-    FlowModel& f = e->flow;
+// host -> device staging of one call's tokens (not graph-captured)
+void flow_stage(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st) {
     const cbx_config& c = e->cfg;
     CBX_REQUIRE(n >= 1 && n <= c.max_s3_tokens, "s3gen: token count out of range");
-    const int Tt = v.n_prompt + n, T = 2 * Tt, L1 = v.n_feat;
-    CBX_REQUIRE(L1 <= T, "s3gen: prompt_feat longer than the encoded sequence");
+    const int T = 2 * (v.n_prompt + n);
+    CBX_REQUIRE(v.n_feat <= T, "s3gen: prompt_feat longer than the encoded sequence");
     CBX_REQUIRE(T <= NOISE_LEN, "s3gen: sequence exceeds the CFM noise buffer");
     for (int i = 0; i < n; i++) CBX_REQUIRE(tokens_h[i] >= 0 && tokens_h[i] < F_V, "s3gen: token id out of range");
     CBX_CHECK(cudaMemcpyAsync(L.tok, v.prompt_token, (size_t)v.n_prompt * 4, cudaMemcpyDeviceToDevice, st));
     CBX_CHECK(cudaMemcpyAsync(L.tok + v.n_prompt, tokens_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CBX_CHECK(cudaStreamSynchronize(st));   // tokens_h may be a transient host buffer
+}
+
+// device-only part (CUDA-graph capturable): L.tok -> L.mel
+void flow_run(cbx_engine* e, Lane& L, const Voice& v, int n, cudaStream_t st) {
+    FlowModel& f = e->flow;
+    const cbx_config& c = e->cfg;
+    const int Tt = v.n_prompt + n, T = 2 * Tt, L1 = v.n_feat;
     encoder(e, L, Tt, st);
     CBX_CHECK(cudaMemsetAsync(L.cond, 0, (size_t)T * MEL * 4, st));
     CBX_CHECK(cudaMemcpyAsync(L.cond, v.prompt_feat, (size_t)L1 * MEL * 4, cudaMemcpyDeviceToDevice, st));
@@ -295,4 +305,9 @@ void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int
         e->gpu_launches += 2;
     }
     CBX_CHECK(cudaMemcpyAsync(L.mel, L.x + (long)L1 * MEL, (size_t)(T - L1) * MEL * 4, cudaMemcpyDeviceToDevice, st));
+}
+
+void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st) {
+    flow_stage(e, L, v, tokens_h, n, st);
+    flow_run(e, L, v, n, st);
 }

@@ -2,6 +2,7 @@
 // Baseline tensor path: mma.sync m16n8k16 fed by a 4-stage cp.async ring.  The tcgen05/TMA
 // variant (gemm_tc.cu) replaces it for the large CFM / HiFT shapes once validated against this one.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace {
 
@@ -20,57 +21,6 @@ struct Cfg {
 
 // 64-byte rows (BK=32 bf16), 16B chunk index XOR-swizzled by (row>>1)&3 -> conflict-free ldmatrix
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
-
-__device__ __forceinline__ void epilogue_pair(const GemmParams& p, int b, int m, int n, float v0, float v1) {
-    // n is even; handles columns n, n+1 of row m
-    if (m >= p.M || n >= p.N) return;
-    const bool has1 = (n + 1) < p.N;
-    if (p.ct_u) {
-        int ph = n / p.ct_cout;
-        int t = m * p.ct_u + ph - p.ct_pad;
-        if (t < 0 || t >= p.ct_len) return;
-    }
-    if (p.bias) { v0 += p.bias[n]; if (has1) v1 += p.bias[n + 1]; }
-    if (p.bias2) { const float* b2 = p.bias2 + (long)b * p.bias2_bs; v0 += b2[n]; if (has1) v1 += b2[n + 1]; }
-    if (p.glu) {
-        float g = v0 / (1.f + expf(-v0)) * v1;
-        long o = (long)b * p.c_bs + (long)m * p.ldc + (n >> 1);
-        if (p.outB) p.outB[o] = __float2bfloat16(g);
-        if (p.outF) p.outF[o] = g;
-        return;
-    }
-    if (p.act) {
-        float a0 = p.act_alpha ? p.act_alpha[n] : p.act_param;
-        float a1 = (p.act_alpha && has1) ? p.act_alpha[n + 1] : p.act_param;
-        v0 = act_apply(p.act, v0, a0);
-        v1 = act_apply(p.act, v1, a1);
-    }
-    if (p.res) {
-        const float* r = p.res + (long)b * p.r_bs + (long)m * p.ldr + n;
-        v0 += r[0]; if (has1) v1 += r[1];
-    }
-    long o = (long)b * p.c_bs + (long)m * p.ldc + n;
-    if (p.outF) {
-        float w0 = p.out_scale * v0, w1 = p.out_scale * v1;
-        if (p.accumulate) { w0 += p.outF[o]; if (has1) w1 += p.outF[o + 1]; }
-        p.outF[o] = w0; if (has1) p.outF[o + 1] = w1;
-        v0 = w0; v1 = w1;
-    } else {
-        v0 *= p.out_scale; v1 *= p.out_scale;
-    }
-    if (p.outB) {
-        if (has1 && ((o & 1) == 0)) *reinterpret_cast<uint32_t*>(p.outB + o) = pack_bf16(v0, v1);
-        else { p.outB[o] = __float2bfloat16(v0); if (has1) p.outB[o + 1] = __float2bfloat16(v1); }
-    }
-    if (p.outB2) {
-        float a0 = p.act2_alpha ? p.act2_alpha[n] : p.act2_param;
-        float a1 = (p.act2_alpha && has1) ? p.act2_alpha[n + 1] : p.act2_param;
-        long o2 = (long)b * p.c2_bs + (long)m * p.ldc2 + n;
-        float u0 = act_apply(p.act2, v0, a0), u1 = act_apply(p.act2, v1, a1);
-        if (has1 && ((o2 & 1) == 0)) *reinterpret_cast<uint32_t*>(p.outB2 + o2) = pack_bf16(u0, u1);
-        else { p.outB2[o2] = __float2bfloat16(u0); if (has1) p.outB2[o2 + 1] = __float2bfloat16(u1); }
-    }
-}
 
 template <int BM, int BN, int WM, int WN>
 __global__ void __launch_bounds__(Cfg<BM, BN, WM, WN>::THREADS) gemm_mma_kernel(const GemmParams p) {
@@ -190,17 +140,18 @@ __global__ void __launch_bounds__(Cfg<BM, BN, WM, WN>::THREADS) gemm_mma_kernel(
 template <int BM, int BN, int WM, int WN>
 void launch_cfg(const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BM, BN, WM, WN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<BM, BN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
     dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN), p.batch);
     gemm_mma_kernel<BM, BN, WM, WN><<<grid, C::THREADS, C::SMEM, st>>>(p);
     CBX_CHECK(cudaGetLastError());
 }
 
 }  // namespace
+
+void gemm_init() {
+    gemm_tc_init();
+    CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<128, 128, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128, 128, 4, 4>::SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<64, 64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, 64, 2, 4>::SMEM));
+}
 
 void launch_gemm(const GemmParams& p, cudaStream_t st) {
     CBX_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.batch > 0, "gemm: empty problem");
@@ -209,6 +160,8 @@ void launch_gemm(const GemmParams& p, cudaStream_t st) {
     CBX_REQUIRE(((uintptr_t)p.A & 15) == 0 && ((uintptr_t)p.W & 15) == 0, "gemm: base pointers must be 16-byte aligned");
     CBX_REQUIRE(!p.glu || (p.N % 2 == 0), "gemm: glu needs even N");
     // pick the tile so the grid covers the 148 SMs: big tiles only when they still give >= ~2 waves
+    ProfScope ps(PC_GEMM, 2.0 * p.M * p.N * p.K * p.batch, st);
+    if (launch_gemm_tc(p, st)) return;
     long big = (long)cdiv(p.M, 128) * cdiv(p.N, 128) * p.batch;
     if (big >= 296) launch_cfg<128, 128, 4, 4>(p, st);
     else launch_cfg<64, 64, 2, 4>(p, st);

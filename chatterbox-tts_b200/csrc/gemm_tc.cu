@@ -1,0 +1,193 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: C[128 x BN] tile per CTA, operands staged by TMA into a
+// SWIZZLE_128B smem ring, one elected thread issues tcgen05.mma (M=128, N=BN, K=16 per instruction) into a
+// TMEM accumulator, four epilogue warps read it back with tcgen05.ld and apply the fused epilogue.
+// The A operand is described by a 4-D tensor map (channel, row, tap, batch): row stride lda, tap stride
+// tap_stride -- conv1d over time-major channels-last activations becomes plain TMA boxes (implicit GEMM).
+#include <cuda.h>
+#include <cstdlib>
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace {
+
+constexpr int TM = 128, TK = 64, A_BYTES = TM * TK * 2;
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = BN <= 64 ? 8 : (BN <= 128 ? 6 : 4);
+    static constexpr int B_BYTES = BN * TK * 2;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();   // a lost arrival must fail loudly, never hang the device
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t lo = ((smem_addr >> 4) & 0x3FFF) | (1u << 16);                     // start address, LBO = 1 (ignored for swizzled K-major)
+    uint64_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);                       // SBO = 1024 B, descriptor version 1 (sm_100), SWIZZLE_128B
+    return lo | (hi << 32);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                         const GemmParams p, int kc_blocks, int w_batched) {
+    using C = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + C::STAGES * A_BYTES;
+    const uint32_t bars = sB + C::STAGES * C::B_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * C::STAGES, tmem_full = bars + 16 * C::STAGES, tmem_slot = tmem_full + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN, b = blockIdx.z;
+    const int KB = p.K / TK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {   // TMA producer
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % C::STAGES, ph = (kb / C::STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, A_BYTES + C::B_BYTES);
+                const int tap = kb / kc_blocks, ci = (kb % kc_blocks) * TK;
+                tma_load_4d(sA + s * A_BYTES, &tmA, full0 + 8 * s, ci, m0, tap, b);
+                tma_load_3d(sB + s * C::B_BYTES, &tmW, full0 + 8 * s, kb * TK, n0, w_batched ? b : 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // MMA issuer
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % C::STAGES, ph = (kb / C::STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t ad = umma_desc(sA + s * A_BYTES), bd = umma_desc(sB + s * C::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TK / 16; k++) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);   // +32 B per K=16 step
+                umma_commit(empty0 + 8 * s);     // smem slot is free once these MMAs retire
+            }
+            umma_commit(tmem_full);
+        }
+    } else {               // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (n0 + c0 < p.N) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) epilogue_pair(p, b, row, n0 + c0 + 2 * j, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+bool g_tc_ok = false;
+long g_tc_launches = 0;
+
+template <int BN>
+bool launch_tc(const GemmParams& p, cudaStream_t st) {
+    using C = TcCfg<BN>;
+    const int ntaps = p.K / p.kc;
+    alignas(64) CUtensorMap tmA, tmW;
+    {
+        cuuint64_t dim[4] = {(cuuint64_t)p.kc, (cuuint64_t)p.M, (cuuint64_t)ntaps, (cuuint64_t)p.batch};
+        cuuint64_t str[3] = {(cuuint64_t)p.lda * 2, (cuuint64_t)(ntaps > 1 ? p.tap_stride : p.lda) * 2, (cuuint64_t)(p.batch > 1 ? p.a_bs : p.lda) * 2};
+        cuuint32_t box[4] = {TK, TM, 1, 1}, es[4] = {1, 1, 1, 1};
+        if (g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p.A, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+    const int w_batched = (p.batch > 1 && p.w_bs != 0) ? 1 : 0;
+    {
+        cuuint64_t dim[3] = {(cuuint64_t)p.K, (cuuint64_t)p.N, (cuuint64_t)(w_batched ? p.batch : 1)};
+        cuuint64_t str[2] = {(cuuint64_t)p.ldw * 2, (cuuint64_t)(w_batched ? p.w_bs : p.ldw) * 2};
+        cuuint32_t box[3] = {TK, BN, 1}, es[3] = {1, 1, 1};
+        if (g_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)p.W, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+    dim3 grid(cdiv(p.M, TM), cdiv(p.N, BN), p.batch);
+    gemm_tc_kernel<BN><<<grid, 192, C::SMEM, st>>>(tmA, tmW, p, p.kc / TK, w_batched);
+    CBX_CHECK(cudaGetLastError());
+    g_tc_launches++;
+    return true;
+}
+
+}  // namespace
+
+void gemm_tc_init() {
+    g_tc_ok = false;
+    if (const char* d = getenv("CBX_DISABLE_TC")) { if (d[0] == '1') return; }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return;
+    g_encode = (EncodeFn)fn;
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
+    g_tc_ok = true;
+}
+
+// returns false when the problem does not fit the TMA/tcgen05 path (caller falls back to the mma.sync kernel)
+bool launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
+    if (!g_tc_ok) return false;
+    if (p.kc % TK != 0 || p.K % p.kc != 0 || p.K % TK != 0) return false;
+    if (p.lda % 8 || p.ldw % 8 || p.tap_stride % 8 || p.a_bs % 8 || p.w_bs % 8) return false;
+    if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15)) return false;
+    // wide tiles only when they still leave enough CTAs in flight
+    const long ctas128 = (long)cdiv(p.M, TM) * cdiv(p.N, 128) * p.batch;
+    if (p.N >= 128 && ctas128 >= 96) return launch_tc<128>(p, st);
+    return launch_tc<64>(p, st);
+}
+
+extern "C" long long cbx_gemm_tc_launches(void) { return g_tc_launches; }

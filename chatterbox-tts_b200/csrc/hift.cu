@@ -101,10 +101,10 @@ void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st) {
 
 // f0 [Tg] -> source [480*Tg] (SineGen + SourceModuleHnNSF), first m samples taken from cache_source
 void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* cache_src_dev, long m, float* src_out,
-                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st) {
+                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn) {
     HiftModel& h = e->hift;
     SourceParams sp; sp.f0 = f0; sp.cum = L.h_cum; sp.s = src_out; sp.L = (long)Tg * H_UP; sp.up = H_UP; sp.sr = 24000.f; sp.n_harm = H_NHARM;
-    sp.lw = h.lw; sp.lb = h.lb; sp.noise = noise_dev; sp.cache = cache_src_dev; sp.cache_len = m; sp.seed = seed;
+    sp.lw = h.lw; sp.lb = h.lb; sp.noise = noise_dev; sp.cache = cache_src_dev; sp.cache_len = m; sp.seed = seed; sp.dyn = dyn;
     if (phase_h) {
         CBX_CHECK(cudaMemcpyAsync(L.h_phase, phase_h, H_NHARM * 4, cudaMemcpyHostToDevice, st));
         CBX_CHECK(cudaStreamSynchronize(st));
@@ -115,7 +115,7 @@ void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* c
 }
 
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
-                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st) {
+                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn) {
     HiftModel& h = e->hift;
     CBX_REQUIRE(Tg >= 1 && Tg <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
     const long Ls = (long)Tg * H_UP, F = 120L * Tg + 1;
@@ -126,7 +126,7 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
     for (int i = 0; i < 4; i++) zero_tail(L.h_xb[i], tlen[i], H_BASE >> i);
     for (int i = 0; i < 3; i++) { zero_tail(L.h_a[i], tlen[i + 1], H_BASE >> (i + 1)); zero_tail(L.h_b[i], tlen[i + 1], H_BASE >> (i + 1)); }
     hift_f0(e, L, Tg, st);
-    hift_source(e, L, L.h_f0, Tg, cache_src_dev, m, src_out, phase_h, noise_dev, seed, st);
+    hift_source(e, L, L.h_f0, Tg, cache_src_dev, m, src_out, phase_h, noise_dev, seed, st, dyn);
     launch_stft16(src_out, Ls, L.h_stft + (long)H_HALO * H_NSRC_PAD, H_NSRC_PAD, (int)F, st);
     // ---- conv_pre (+ the leaky_relu that precedes ups[0])
     {

@@ -38,7 +38,9 @@ __global__ void f0_prefix_kernel(const float* __restrict__ f0, double* cum, int 
 __global__ void source_kernel(const SourceParams p) {
     long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.L) return;
-    if (n < p.cache_len) { p.s[n] = p.cache[n]; return; }
+    const long cache_len = p.dyn ? (long)p.dyn->cache_len : p.cache_len;
+    const unsigned long long seed = p.dyn ? p.dyn->seed : p.seed;
+    if (n < cache_len) { p.s[n] = p.cache[n]; return; }
     int t = n / p.up, j = n % p.up;
     float f = p.f0[t];
     float uv = f > p.voiced_thr ? 1.f : 0.f;
@@ -52,7 +54,7 @@ __global__ void source_kernel(const SourceParams p) {
         float phase0 = (h == 0) ? 0.f : (p.phase ? p.phase[h] : 0.f);
         if (!p.phase && h > 0) {
             uint32_t r4[4];
-            Philox::gen(p.seed, (uint32_t)h, 0u, 0x5048u, 0u, r4);
+            Philox::gen(seed, (uint32_t)h, 0u, 0x5048u, 0u, r4);
             phase0 = (u32_to_unit(r4[0]) * 2.f - 1.f) * 3.14159265358979f;
         }
         float sine = p.sine_amp * sinf(theta + phase0);
@@ -60,7 +62,7 @@ __global__ void source_kernel(const SourceParams p) {
         if (p.noise) nz = p.noise[(long)h * p.L + n];
         else {
             uint32_t r4[4];
-            Philox::gen(p.seed, (uint32_t)n, (uint32_t)(n >> 32), 0x4E5Au + h, 0u, r4);
+            Philox::gen(seed, (uint32_t)n, (uint32_t)(n >> 32), 0x4E5Au + h, 0u, r4);
             float u1 = u32_to_unit(r4[0]), u2 = u32_to_unit(r4[1]);
             nz = sqrtf(-2.f * logf(u1)) * cosf(6.283185307179586f * u2);
         }
@@ -188,19 +190,23 @@ void launch_f0_classifier(const bf16* x, long ld, const float* w, const float* b
     CBX_CHECK(cudaGetLastError());
 }
 void launch_source(const SourceParams& p, int T, cudaStream_t st) {
+    ProfScope ps(PC_HIFT_MISC, (double)p.L * 4, st);
     f0_prefix_kernel<<<1, 32, 0, st>>>(p.f0, p.cum, T, p.up, p.sr, p.n_harm);
     source_kernel<<<g1(p.L), 256, 0, st>>>(p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_stft16(const float* s, long L, bf16* out, long ld, int F, cudaStream_t st) {
+    ProfScope ps(PC_HIFT_MISC, (double)L * 4 + (double)F * ld * 2, st);
     stft16_kernel<<<g1(F, 128), 128, 0, st>>>(s, L, out, ld, F);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_istft16(const float* y, long ldy, int F, float* wav, long L, float limit, const float* fade, int fade_len, cudaStream_t st) {
+    ProfScope ps(PC_HIFT_MISC, (double)F * ldy * 4 + (double)L * 4, st);
     istft16_kernel<<<g1(L), 256, 0, st>>>(y, ldy, F, wav, L, limit, fade, fade_len);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_snake_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, const float* alpha, cudaStream_t st) {
+    ProfScope ps(PC_HIFT_MISC, (double)rows * C * 6, st);
     snake_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(in, ld_in, out, ld_out, rows, C, alpha);
     CBX_CHECK(cudaGetLastError());
 }

@@ -1,6 +1,8 @@
 #pragma once
 #include "common.cuh"
 
+struct SourceDyn { long long cache_len; unsigned long long seed; };   // per-call values read from device memory (CUDA-graph replay)
+
 struct SourceParams {
     const float* f0 = nullptr; double* cum = nullptr;
     float* s = nullptr; long L = 0; int up = 480; float sr = 24000.f;
@@ -10,6 +12,7 @@ struct SourceParams {
     const float* noise = nullptr;    // optional explicit N(0,1) noise [n_harm][L]
     const float* cache = nullptr; long cache_len = 0;   // cache_source overwrite of the first samples
     unsigned long long seed = 0;
+    const SourceDyn* dyn = nullptr;   // non-null: cache_len / seed come from here instead of the fields above
 };
 void hift_init_constants();
 void launch_f0_classifier(const bf16* x, long ld, const float* w, const float* b, float* f0, int T, int C, cudaStream_t st);

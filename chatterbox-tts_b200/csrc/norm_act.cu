@@ -121,6 +121,7 @@ static inline dim3 g1(long n, int t = 256) { return dim3((unsigned)((n + t - 1) 
 void launch_norm(const NormParams& p, cudaStream_t st) {
     long warps = (long)p.rows * p.batch;
     if (warps == 0) return;
+    ProfScope ps(PC_NORM, (double)warps * p.C * 6, st);
     norm_kernel<<<g1(warps * 32, 256), 256, 0, st>>>(p);
     CBX_CHECK(cudaGetLastError());
 }
@@ -129,6 +130,7 @@ void launch_gather_rows_bf16(const float* table, const int* idx, int n, int C, b
     CBX_CHECK(cudaGetLastError());
 }
 void launch_f32_to_bf16_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, int act, float act_param, cudaStream_t st) {
+    ProfScope ps(PC_ELEMWISE, (double)rows * C * 6, st);
     if (rows == 0) return;
     f32_to_bf16_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(in, ld_in, out, ld_out, rows, C, act, act_param);
     CBX_CHECK(cudaGetLastError());
@@ -142,10 +144,12 @@ void launch_upsample2(const float* in, bf16* out, long ld_out, int T, int C, cud
     CBX_CHECK(cudaGetLastError());
 }
 void launch_pack_cfm_input(const float* x, const float* mu, const float* spks, const float* cond, bf16* out, long out_bs, int T, int mel, cudaStream_t st) {
+    ProfScope ps(PC_ELEMWISE, (double)T * mel * 4 * 2 * 6, st);
     pack_cfm_input_kernel<<<g1((long)2 * T * 4 * mel), 256, 0, st>>>(x, mu, spks, cond, out, out_bs, T, mel);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_euler_update(float* x, const float* v, long v_bs, long n, float dt, float r, cudaStream_t st) {
+    ProfScope ps(PC_ELEMWISE, (double)n * 16, st);
     euler_update_kernel<<<g1(n), 256, 0, st>>>(x, v, v_bs, n, dt, r);
     CBX_CHECK(cudaGetLastError());
 }

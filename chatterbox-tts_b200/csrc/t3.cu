@@ -243,8 +243,8 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
         m.h_active = act;
     }
     const long per_step = 5L * e->cfg.t3_layers + 2;
-    if (noise_dev) {
-        for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev + (long)i * n * T3_V, st);
+    if (noise_dev || prof_enabled()) {
+        for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev ? noise_dev + (long)i * n * T3_V : nullptr, st);
     } else {
         auto it = m.step_graphs.find(n);
         if (it == m.step_graphs.end()) {

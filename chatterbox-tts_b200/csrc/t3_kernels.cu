@@ -479,17 +479,20 @@ void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
     const int S = p.strips_per_cta;
     size_t smem = (size_t)8 * NT * (p.K + 8) * 2 + (size_t)nwarps * S * 16 * 8 * NT * 4;
     int grid = cdiv(p.n_strips, S);
+    ProfScope ps(PC_GEMV, (double)p.n_strips * 16 * p.K * 2 + (double)p.rows * (p.K + p.N) * 4, st);
     CBX_REQUIRE(smem <= 200 * 1024, "gemv: staging exceeds shared memory");
     if (NT == 1) gemv_kernel<1><<<grid, nwarps * 32, smem, st>>>(p);
     else gemv_kernel<2><<<grid, nwarps * 32, smem, st>>>(p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st) {
+    ProfScope ps(PC_DECODE_ATTN, 0.0, st);
     decode_attn_kernel<<<dim3(p.H, rows), 128, (size_t)(max_pos + PAGE) * sizeof(float), st>>>(p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st) {
     CBX_REQUIRE(p.V <= SAMP_T * SAMP_E, "sampler: vocabulary too large for the register tile");
+    ProfScope ps(PC_SAMPLER, (double)n_streams * 2 * p.V * 4, st);
     sampler_kernel<<<n_streams, SAMP_T, 0, st>>>(p);
     CBX_CHECK(cudaGetLastError());
 }

@@ -104,6 +104,15 @@ int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const fl
 
 /* counters for bench.py: kernels launched by this library since engine creation */
 int64_t cbx_gpu_launches(cbx_engine* e);
+/* GEMM launches that took the tcgen05/TMA path (process-wide; 0 means the mma.sync fallback served everything) */
+long long cbx_gemm_tc_launches(void);
+
+/* per-launch profiler for bench.py's roofline pass: between begin and end every kernel launch is bracketed by
+ * CUDA events on its stream (T3 steps run un-graphed); end() returns, per kernel class (0 gemm, 1 attention,
+ * 2 t3 gemv, 3 t3 decode attention, 4 sampler, 5 norm, 6 elementwise, 7 hift misc), the launch count, summed
+ * device milliseconds and summed algorithmic work (FLOPs for classes 0-1, bytes otherwise). */
+int cbx_profile_begin(void);
+int cbx_profile_end(int64_t* counts, double* ms, double* work, int n_classes);
 
 /* single-op hooks (kernel unit tests): C[M][N] = A[M][K] * W[N][K]^T (+bias), bf16 in, fp32 out; attention over
  * fused q|k|v rows; all pointers device. */

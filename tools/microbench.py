@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Stage-level timings on one B200 (CUDA events): T3 decode steps at 1..8 streams, S3Gen call latency by token count."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "chatterbox-tts_b200")):
+    sys.path.insert(0, p)
+import torch
+from cbx_b200.config import ModelConfig
+from cbx_b200.native import NativeEngine
+from cbx_b200.weights import random_state_dict, synthetic_conditionals
+
+
+def main():
+    cfg = ModelConfig()
+    eng = NativeEngine(cfg, max_streams=8, n_lanes=1)
+    eng.load_state_dict(random_state_dict(cfg, 0))
+    conds = synthetic_conditionals(cfg)
+    v = eng.voice_put("default", conds["t3"], conds["gen"])
+    out = {}
+    text = [255] + [(7 * i) % 700 + 1 for i in range(145)] + [0]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for ns in (1, 2, 4, 8):
+        t0 = time.time()
+        slots = [eng.t3_open(v, text, seed=i, max_new=1000) for i in range(ns)]
+        torch.cuda.synchronize()
+        prefill_ms = (time.time() - t0) * 1e3 / ns
+        eng.t3_step(slots, 20)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        eng.t3_step(slots, 200)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 200
+        pos = 34 + len(text) + 1 + 120
+        wbytes = 30 * 16779264 * 2 + 8208 * 1024 * 2
+        kvbytes = 122880 * pos * 2 * ns
+        out[f"t3_streams{ns}"] = {"ms_per_step": ms, "tok_s": ns * 1e3 / ms, "audio_s_per_s": ns * 1e3 / ms / 25, "prefill_ms": prefill_ms,
+                                  "hbm_gbs": (wbytes + kvbytes) / (ms * 1e-3) / 1e9}
+        for s in slots:
+            eng.t3_close(s)
+    for n in (35, 70, 140, 245):
+        toks = [(i * 37) % 6561 for i in range(n)]
+        for _ in range(2):
+            eng.s3gen_infer(v, toks, seed=1)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(3):
+            eng.s3gen_infer(v, toks, seed=1)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        a.record()
+        for _ in range(3):
+            eng.flow_infer(v, toks)
+        b.record()
+        torch.cuda.synchronize()
+        fms = a.elapsed_time(b) / 3
+        T = 2 * (194 + n)
+        flops = 2 * (66.08e6 + 57344 * T) * T * 20
+        out[f"s3gen_n{n}"] = {"ms": ms, "flow_eager_ms": fms, "T": T, "cfm_tflops_vs_graph_total": flops / (ms * 1e-3) / 1e12, "audio_s": n * 0.04}
+    print(json.dumps(out, indent=1))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

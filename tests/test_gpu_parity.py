@@ -54,6 +54,12 @@ def test_gemm_op(dev, M, N, K):
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t() + b
     assert _rel(out, ref) < 1e-5
+    if K % 64 == 0:   # these shapes must be served by the tcgen05/TMA kernel, not the mma.sync fallback
+        before = lib.cbx_gemm_tc_launches()
+        L.check(lib.cbx_op_gemm(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, None))
+        torch.cuda.synchronize()
+        assert lib.cbx_gemm_tc_launches() == before + 1
+        assert _rel(out, ref) < 1e-5
 
 
 @pytest.mark.parametrize("T,H,B,causal", [(64, 8, 2, 0), (100, 8, 1, 0), (333, 16, 2, 1), (1000, 8, 2, 0)])

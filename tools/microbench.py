@@ -64,6 +64,7 @@ def main():
         T = 2 * (194 + n)
         flops = 2 * (66.08e6 + 57344 * T) * T * 20
         out[f"s3gen_n{n}"] = {"ms": ms, "flow_eager_ms": fms, "T": T, "cfm_tflops_vs_graph_total": flops / (ms * 1e-3) / 1e12, "audio_s": n * 0.04}
+    out["gemm_tc_launches"] = int(eng.lib.cbx_gemm_tc_launches())
     print(json.dumps(out, indent=1))
     eng.close()
 

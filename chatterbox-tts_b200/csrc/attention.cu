@@ -6,7 +6,7 @@
 
 namespace {
 
-constexpr int D = 64, BQ = 64, BKV = 64, NT = 128;
+constexpr int D = 64, BQ = 64, BKV = 64, NT = 128, KVS = 4;   // KVS-deep K/V ring: small grids (1 CTA/SM) are bound by load latency
 constexpr int TILE_BYTES = 64 * 128;  // 64 rows x 128 B
 
 __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
     const bf16* Q = p.q + (long)b * p.q_bs + h * D;
     const bf16* K = p.k + (long)b * p.k_bs + h * D;
     const bf16* V = p.v + (long)b * p.v_bs + h * D;
-    const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + 2 * TILE_BYTES;
+    const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + KVS * TILE_BYTES;
 
     int n_kv_tiles = (p.T + BKV - 1) / BKV;
     if (p.causal) {
@@ -39,9 +39,14 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
         n_kv_tiles = (last + BKV - 1) / BKV;
     }
     load_tile(sQ, Q, p.ldq, q0, p.T, tid);
-    load_tile(sK, K, p.ldk, 0, p.T, tid);
-    load_tile(sV, V, p.ldv, 0, p.T, tid);
-    cp_async_commit();
+#pragma unroll
+    for (int s = 0; s < KVS - 1; s++) {
+        if (s < n_kv_tiles) {
+            load_tile(sK + s * TILE_BYTES, K, p.ldk, s * BKV, p.T, tid);
+            load_tile(sV + s * TILE_BYTES, V, p.ldv, s * BKV, p.T, tid);
+        }
+        cp_async_commit();
+    }
 
     float o[8][4];
 #pragma unroll
@@ -54,13 +59,16 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
     const int qi0 = q0 + warp * 16 + g, qi1 = qi0 + 8;
 
     for (int kt = 0; kt < n_kv_tiles; kt++) {
-        const int buf = kt & 1;
-        if (kt + 1 < n_kv_tiles) {
-            load_tile(sK + (buf ^ 1) * TILE_BYTES, K, p.ldk, (kt + 1) * BKV, p.T, tid);
-            load_tile(sV + (buf ^ 1) * TILE_BYTES, V, p.ldv, (kt + 1) * BKV, p.T, tid);
+        const int buf = kt % KVS;
+        {
+            const int nk = kt + KVS - 1;
+            if (nk < n_kv_tiles) {
+                load_tile(sK + (nk % KVS) * TILE_BYTES, K, p.ldk, nk * BKV, p.T, tid);
+                load_tile(sV + (nk % KVS) * TILE_BYTES, V, p.ldv, nk * BKV, p.T, tid);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<KVS - 1>();
         __syncthreads();
         if (kt == 0) {
 #pragma unroll
@@ -161,12 +169,12 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
 
 }  // namespace
 
-void attention_init() { CBX_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * TILE_BYTES)); }
+void attention_init() { CBX_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 + 2 * KVS) * TILE_BYTES)); }
 
 void launch_attention(const AttnParams& p, cudaStream_t st) {
     CBX_REQUIRE(p.T > 0 && p.H > 0 && p.batch > 0, "attention: empty problem");
     CBX_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "attention: row strides must keep 16B alignment");
-    const int smem = 5 * TILE_BYTES;
+    const int smem = (1 + 2 * KVS) * TILE_BYTES;
     ProfScope ps(PC_ATTN, 4.0 * p.T * p.T * D * p.H * p.batch * (p.causal ? 0.5 : 1.0), st);
     dim3 grid(cdiv(p.T, BQ), p.H, p.batch);
     attn_kernel<<<grid, NT, smem, st>>>(p);

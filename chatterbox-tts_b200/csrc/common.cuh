@@ -45,6 +45,25 @@ __device__ __forceinline__ float act_apply(int act, float v, float param) {
     }
 }
 
+template <int ACT>
+__device__ __forceinline__ void act_apply8(float (&v)[8], const float (&alpha)[8] /*per-column parameter (snake alpha / lrelu slope)*/) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if constexpr (ACT == ACT_GELU) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+        else if constexpr (ACT == ACT_SILU) v[i] = v[i] / (1.f + expf(-v[i]));
+        else if constexpr (ACT == ACT_MISH) { float sp = v[i] > 20.f ? v[i] : log1pf(expf(v[i])); v[i] = v[i] * tanhf(sp); }
+        else if constexpr (ACT == ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : v[i] * alpha[i];
+        else if constexpr (ACT == ACT_ELU) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+        else if constexpr (ACT == ACT_SNAKE) { float a = alpha[i]; float s = sinf(v[i] * a); v[i] = v[i] + s * s / (a + 1e-9f); }
+    }
+}
+
+// activation pairs (main, second output) that the model actually uses; every GEMM kernel is instantiated per pair so that
+// only one activation's code is resident (a runtime switch over all of them overflowed the instruction cache)
+#define CBX_FOR_ACT_PAIRS(X) \
+    X(ACT_NONE, ACT_NONE) X(ACT_GELU, ACT_NONE) X(ACT_SILU, ACT_NONE) X(ACT_MISH, ACT_NONE) X(ACT_LRELU, ACT_NONE) \
+    X(ACT_ELU, ACT_NONE) X(ACT_SNAKE, ACT_NONE) X(ACT_NONE, ACT_SNAKE) X(ACT_NONE, ACT_LRELU)
+
 // ---------------------------------------------------------------- warp / block reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

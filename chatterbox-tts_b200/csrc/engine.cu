@@ -382,8 +382,14 @@ int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const fl
 
 int64_t cbx_gpu_launches(cbx_engine* e) { return e ? e->gpu_launches : -1; }
 
+static void ops_init_once() {
+    static std::once_flag once;
+    std::call_once(once, [] { gemm_init(); attention_init(); });
+}
+
 int cbx_op_gemm(const void* a, const void* w, const float* bias, float* out, int M, int N, int K, void* stream) {
     CBX_API_BEGIN
+    ops_init_once();
     GemmParams g; g.A = (const bf16*)a; g.lda = K; g.kc = K; g.W = (const bf16*)w; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias; g.outF = out; g.ldc = N;
     launch_gemm(g, (cudaStream_t)stream);
     CBX_API_END
@@ -391,6 +397,7 @@ int cbx_op_gemm(const void* a, const void* w, const float* bias, float* out, int
 
 int cbx_op_attention(const void* qkv, void* out, int T, int H, int batch, int causal, void* stream) {
     CBX_API_BEGIN
+    ops_init_once();
     const long ld = 3L * H * 64;
     AttnParams a; a.q = (const bf16*)qkv; a.k = a.q + H * 64; a.v = a.q + 2 * H * 64; a.ldq = a.ldk = a.ldv = ld; a.q_bs = a.k_bs = a.v_bs = (long)T * ld;
     a.o = (bf16*)out; a.ldo = H * 64; a.o_bs = (long)T * H * 64; a.T = T; a.H = H; a.batch = batch; a.causal = causal; a.scale = 0.125f;

@@ -16,13 +16,15 @@ struct Cfg {
     static constexpr int THREADS = WARPS_M * WARPS_N * 32;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES);
+    static constexpr int PIPE = STAGES * (A_BYTES + B_BYTES);
+    static constexpr int EPI = BM * (BN + 4) * 4;
+    static constexpr int SMEM = PIPE > EPI ? PIPE : EPI;
 };
 
 // 64-byte rows (BK=32 bf16), 16B chunk index XOR-swizzled by (row>>1)&3 -> conflict-free ldmatrix
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int ACT, int ACT2>
 __global__ void __launch_bounds__(Cfg<BM, BN, WM, WN>::THREADS) gemm_mma_kernel(const GemmParams p) {
     using C = Cfg<BM, BN, WM, WN>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -125,32 +127,56 @@ __global__ void __launch_bounds__(Cfg<BM, BN, WM, WN>::THREADS) gemm_mma_kernel(
     }
     cp_async_wait<0>();
 
+    // ---- epilogue: re-layout the accumulators through shared memory so that every thread owns 8 consecutive
+    // columns of one row (vector loads/stores, coalesced across the warp), then the fused epilogue
+    __syncthreads();
+    float* ct = reinterpret_cast<float*>(smem);
+    constexpr int LDT = BN + 4;
     const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
     for (int i = 0; i < WM; i++)
 #pragma unroll
         for (int j = 0; j < WN; j++) {
-            int m = m0 + wm * (16 * WM) + i * 16 + g;
-            int n = n0 + wn * (8 * WN) + j * 8 + tg * 2;
-            epilogue_pair(p, b, m, n, acc[i][j][0], acc[i][j][1]);
-            epilogue_pair(p, b, m + 8, n, acc[i][j][2], acc[i][j][3]);
+            int r = wm * (16 * WM) + i * 16 + g, c = wn * (8 * WN) + j * 8 + tg * 2;
+            *reinterpret_cast<float2*>(ct + r * LDT + c) = make_float2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<float2*>(ct + (r + 8) * LDT + c) = make_float2(acc[i][j][2], acc[i][j][3]);
         }
+    __syncthreads();
+    {
+        constexpr int CPR = BN / 8, RSTEP = C::THREADS / CPR;
+        const int cc = (tid % CPR) * 8;
+        ColOps co;
+        load_colops(p, b, n0 + cc, co);
+        epilogue_rows<ACT, ACT2>(p, b, m0, tid / CPR, RSTEP, BM, ct, LDT, cc, co);
+    }
 }
 
 template <int BM, int BN, int WM, int WN>
 void launch_cfg(const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BM, BN, WM, WN>;
     dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN), p.batch);
-    gemm_mma_kernel<BM, BN, WM, WN><<<grid, C::THREADS, C::SMEM, st>>>(p);
+    bool done = false;
+#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { gemm_mma_kernel<BM, BN, WM, WN, A1, A2><<<grid, C::THREADS, C::SMEM, st>>>(p); done = true; }
+    CBX_FOR_ACT_PAIRS(CBX_LAUNCH)
+#undef CBX_LAUNCH
+    CBX_REQUIRE(done, "gemm: activation pair not instantiated");
     CBX_CHECK(cudaGetLastError());
+}
+
+template <int BM, int BN, int WM, int WN>
+void init_cfg() {
+    using C = Cfg<BM, BN, WM, WN>;
+#define CBX_ATTR(A1, A2) CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<BM, BN, WM, WN, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    CBX_FOR_ACT_PAIRS(CBX_ATTR)
+#undef CBX_ATTR
 }
 
 }  // namespace
 
 void gemm_init() {
     gemm_tc_init();
-    CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<128, 128, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128, 128, 4, 4>::SMEM));
-    CBX_CHECK(cudaFuncSetAttribute(gemm_mma_kernel<64, 64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64, 64, 2, 4>::SMEM));
+    init_cfg<128, 128, 4, 4>();
+    init_cfg<64, 64, 2, 4>();
 }
 
 void launch_gemm(const GemmParams& p, cudaStream_t st) {

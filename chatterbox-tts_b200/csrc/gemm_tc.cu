@@ -11,12 +11,16 @@
 namespace {
 
 constexpr int TM = 128, TK = 64, A_BYTES = TM * TK * 2;
+__device__ unsigned long long g_tc_trace[16];
 template <int BN> struct TcCfg {
     static constexpr int STAGES = BN <= 64 ? 8 : (BN <= 128 ? 6 : 4);
     static constexpr int B_BYTES = BN * TK * 2;
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TC_TRACE(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_trace[i] = gtime(); } while (0)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -52,8 +56,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+template <int BN, int ACT, int ACT2>
+__global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                          const GemmParams p, int kc_blocks, int w_batched) {
     using C = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN, b = blockIdx.z;
     const int KB = p.K / TK;
 
+    if (threadIdx.x == 0) TC_TRACE(0);
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < C::STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(tmem_full, 1);
@@ -80,6 +85,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    if (threadIdx.x == 0) TC_TRACE(1);
     if (warp == 0) {
         if (lane == 0) {   // TMA producer
             for (int kb = 0; kb < KB; kb++) {
@@ -98,6 +104,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             for (int kb = 0; kb < KB; kb++) {
                 const int s = kb % C::STAGES, ph = (kb / C::STAGES) & 1;
                 mbar_wait(full0 + 8 * s, ph);
+                if (kb == 0) TC_TRACE(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t ad = umma_desc(sA + s * A_BYTES), bd = umma_desc(sB + s * C::B_BYTES);
 #pragma unroll
@@ -105,29 +112,46 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                 umma_commit(empty0 + 8 * s);     // smem slot is free once these MMAs retire
             }
             umma_commit(tmem_full);
+            TC_TRACE(3);
         }
-    } else {               // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+    } else {               // epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+        const int q = warp & 3, half = (warp - 2) >> 2, et = threadIdx.x - 64;
+        constexpr int LDT = BN + 4, CPR = BN / 8, RSTEP = 256 / CPR;
+        const int cc = (et % CPR) * 8;
+        ColOps co;
+        load_colops(p, b, n0 + cc, co);      // overlaps the main loop
         mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 64) TC_TRACE(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (n0 + c0 < p.N) {
+        // TMEM -> registers (thread = row) -> shared staging tile; the operand ring is idle by now and is reused for it
+        float* tile = reinterpret_cast<float*>(smem_raw + (sA - smem_u32(smem_raw)));
+        {
+            float* trow = tile + (q * 32 + lane) * LDT + half * (BN / 2);
 #pragma unroll
-                for (int j = 0; j < 8; j++) epilogue_pair(p, b, row, n0 + c0 + 2 * j, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            for (int g = 0; g < BN / 64; g++) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2) + g * 32;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    *reinterpret_cast<uint4*>(trow + g * 32 + 4 * c) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
             }
         }
+        if (threadIdx.x == 64) TC_TRACE(7);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) TC_TRACE(8);
+        epilogue_rows<ACT, ACT2>(p, b, m0, et / CPR, RSTEP, TM, tile, LDT, cc, co);
     }
+    if (threadIdx.x == 64) TC_TRACE(5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(6);
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
 }
 
@@ -158,7 +182,11 @@ bool launch_tc(const GemmParams& p, cudaStream_t st) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
     }
     dim3 grid(cdiv(p.M, TM), cdiv(p.N, BN), p.batch);
-    gemm_tc_kernel<BN><<<grid, 192, C::SMEM, st>>>(tmA, tmW, p, p.kc / TK, w_batched);
+    bool done = false;
+#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { gemm_tc_kernel<BN, A1, A2><<<grid, 320, C::SMEM, st>>>(tmA, tmW, p, p.kc / TK, w_batched); done = true; }
+    CBX_FOR_ACT_PAIRS(CBX_LAUNCH)
+#undef CBX_LAUNCH
+    if (!done) return false;
     CBX_CHECK(cudaGetLastError());
     g_tc_launches++;
     return true;
@@ -173,8 +201,11 @@ void gemm_tc_init() {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return;
     g_encode = (EncodeFn)fn;
-    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM));
-    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
+#define CBX_ATTR(A1, A2) \
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<64, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM)); \
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
+    CBX_FOR_ACT_PAIRS(CBX_ATTR)
+#undef CBX_ATTR
     g_tc_ok = true;
 }
 
@@ -191,3 +222,5 @@ bool launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
 }
 
 extern "C" long long cbx_gemm_tc_launches(void) { return g_tc_launches; }
+
+extern "C" int cbx_gemm_tc_trace(unsigned long long* out_h) { return cudaMemcpyFromSymbol(out_h, g_tc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1; }

@@ -5,31 +5,44 @@
 
 namespace {
 
-// one warp per row; C <= 2048
+// one warp per row, the row cached in registers (C <= 32 * NORM_MAX_PER_LANE): one global read, two-pass statistics
+constexpr int NORM_MAX_PER_LANE = 32;
 __global__ void norm_kernel(NormParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const long total = (long)p.rows * p.batch;
     if (warp >= total) return;
     const int b = warp / p.rows, r = warp % p.rows;
     const float* x = p.in + (long)b * p.in_bs + (long)r * p.ld_in;
-    float mean = 0.f;
-    if (!p.rms) {
-        float s = 0.f;
-        for (int c = lane; c < p.C; c += 32) s += x[c];
-        mean = warp_sum(s) / p.C;
+    float xv[NORM_MAX_PER_LANE];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER_LANE; i++) {
+        int c = lane + 32 * i;
+        xv[i] = c < p.C ? x[c] : 0.f;
+        s += xv[i];
     }
+    const float mean = p.rms ? 0.f : warp_sum(s) / p.C;
     float v = 0.f;
-    for (int c = lane; c < p.C; c += 32) { float d = x[c] - mean; v += d * d; }
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER_LANE; i++) {
+        int c = lane + 32 * i;
+        float d = c < p.C ? xv[i] - mean : 0.f;
+        v += d * d;
+    }
     const float rstd = rsqrtf(warp_sum(v) / p.C + p.eps);
     const float* add = p.add ? p.add + (long)b * p.add_bs : nullptr;
-    for (int c = lane; c < p.C; c += 32) {
-        float y = (x[c] - mean) * rstd * p.gain[c];
-        if (p.bias) y += p.bias[c];
-        y = act_apply(p.act, y, 0.f);
-        if (add) y += add[c];
-        y *= p.out_scale;
-        if (p.outF) p.outF[(long)b * p.outF_bs + (long)r * p.ld_outF + c] = y;
-        if (p.outB) p.outB[(long)b * p.outB_bs + (long)r * p.ld_outB + c] = __float2bfloat16(y);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER_LANE; i++) {
+        int c = lane + 32 * i;
+        if (c < p.C) {
+            float y = (xv[i] - mean) * rstd * p.gain[c];
+            if (p.bias) y += p.bias[c];
+            y = act_apply(p.act, y, 0.f);
+            if (add) y += add[c];
+            y *= p.out_scale;
+            if (p.outF) p.outF[(long)b * p.outF_bs + (long)r * p.ld_outF + c] = y;
+            if (p.outB) p.outB[(long)b * p.outB_bs + (long)r * p.ld_outB + c] = __float2bfloat16(y);
+        }
     }
 }
 
@@ -121,6 +134,7 @@ static inline dim3 g1(long n, int t = 256) { return dim3((unsigned)((n + t - 1) 
 void launch_norm(const NormParams& p, cudaStream_t st) {
     long warps = (long)p.rows * p.batch;
     if (warps == 0) return;
+    CBX_REQUIRE(p.C <= 32 * NORM_MAX_PER_LANE, "norm: row too wide for the register tile");
     ProfScope ps(PC_NORM, (double)warps * p.C * 6, st);
     norm_kernel<<<g1(warps * 32, 256), 256, 0, st>>>(p);
     CBX_CHECK(cudaGetLastError());

@@ -106,6 +106,9 @@ int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const fl
 int64_t cbx_gpu_launches(cbx_engine* e);
 /* GEMM launches that took the tcgen05/TMA path (process-wide; 0 means the mma.sync fallback served everything) */
 long long cbx_gemm_tc_launches(void);
+/* debug: %globaltimer stamps (ns) of the last tcgen05 GEMM's CTA 0: start, setup done, first TMA landed, MMAs issued,
+ * accumulator ready, epilogue done, teardown */
+int cbx_gemm_tc_trace(unsigned long long* out_h);
 
 /* per-launch profiler for bench.py's roofline pass: between begin and end every kernel launch is bracketed by
  * CUDA events on its stream (T3 steps run un-graphed); end() returns, per kernel class (0 gemm, 1 attention,

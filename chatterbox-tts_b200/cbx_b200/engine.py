@@ -16,6 +16,7 @@ three asyncio tasks racing a cancel event per token.
 """
 import asyncio
 import concurrent.futures
+import contextlib
 import os
 import threading
 import time
@@ -32,6 +33,10 @@ from .native import NativeEngine
 from .text_processing import split_text_into_chunks, SyntheticTokenizer, JsonTokenizer
 
 SPEECH_VOCAB = 6561
+
+
+class _Cancelled(Exception):
+    pass
 
 
 class CancellationToken:
@@ -102,6 +107,7 @@ class T3Scheduler(threading.Thread):
     def __init__(self, native: NativeEngine, steps_per_round: int = 7, max_batch: int = 8):
         super().__init__(daemon=True, name="cbx-t3-scheduler")
         self.native, self.k, self.max_batch = native, steps_per_round, max_batch
+        self.on_gpu = not getattr(native, "is_fake", False)
         self.active: List[_T3Stream] = []
         self.lock = threading.Condition()
         self.running = True
@@ -109,7 +115,7 @@ class T3Scheduler(threading.Thread):
         self.start()
 
     def open(self, voice, text_ids, cfg_w, temp, sd: SamplingDefaults, seed, max_new) -> _T3Stream:
-        with torch.cuda.stream(self._stream()):
+        with self._ctx():
             slot = self.native.t3_open(voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new)
         s = _T3Stream(slot, max_new)
         with self.lock:
@@ -122,13 +128,17 @@ class T3Scheduler(threading.Thread):
 
     _tls = threading.local()
 
-    def _stream(self):
+    def _ctx(self):
+        """Per-thread CUDA stream context (a no-op for the host-logic tests' fake backend)."""
+        if not self.on_gpu:
+            return contextlib.nullcontext()
         if not hasattr(self._tls, "st"):
             self._tls.st = torch.cuda.Stream()
-        return self._tls.st
+        return torch.cuda.stream(self._tls.st)
 
     def run(self):
-        torch.cuda.set_device(self.native.device)
+        if self.on_gpu:
+            torch.cuda.set_device(self.native.device)
         while self.running:
             with self.lock:
                 while self.running and not self.active:
@@ -145,7 +155,7 @@ class T3Scheduler(threading.Thread):
             if not live:
                 continue
             try:
-                with torch.cuda.stream(self._stream()):
+                with self._ctx():
                     self.native.t3_step([s.slot for s in live], self.k)
                     for s in live:
                         n, done = self.native.t3_poll(s.slot)
@@ -201,10 +211,14 @@ class TextToSpeechEngine:
     DEC_COND_LEN = 10 * S3GEN_SR
 
     def __init__(self, device: str, cfg: ModelConfig = None, state_dict=None, concurrent_requests: int = None,
-                 sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0, device_sink: bool = False):
+                 sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0, device_sink: bool = False,
+                 backend=None):
+        """`backend` injects an object with NativeEngine's interface (host-logic tests only); the product path
+        always builds a NativeEngine on `device` and refuses anything that is not cuda:N."""
         self.device = device
         self.gpu_id = int(device.split(":")[-1]) if "cuda" in device else -1
-        if self.gpu_id < 0:
+        self._backend = backend
+        if self.gpu_id < 0 and backend is None:
             raise RuntimeError("TextToSpeechEngine (B200 path) needs a cuda:N device; there is no CPU fallback")
         self.cfg = cfg or ModelConfig()
         self._state_dict = state_dict
@@ -238,6 +252,13 @@ class TextToSpeechEngine:
 
     def _init_blocking(self):
         from .weights import random_state_dict, synthetic_conditionals
+        if self._backend is not None:
+            self.native = self._backend
+            self.tokenizer = SyntheticTokenizer(self.cfg.t3.text_vocab)
+            self.voice_cache["default"] = 0
+            self.scheduler = T3Scheduler(self.native, max_batch=8)
+            self._ready = True
+            return
         torch.cuda.set_device(self.gpu_id)
         self.native = NativeEngine(self.cfg, device=self.gpu_id, **self.native_kwargs)
         sd = self._state_dict
@@ -313,10 +334,10 @@ class TextToSpeechEngine:
     # ------------------------------------------------------------------ the request pipeline (one thread per request)
     def _run_request(self, text, voice_id, cfg_w, temp, chunk_size, slice_len, trim_tail_ms, trim_lead_ms, overlap, fade_ms,
                      request_id, token: Optional[CancellationToken], emit, t_start):
-        torch.cuda.set_device(self.gpu_id)
-        st = torch.cuda.Stream()
         nat, sched = self.native, self.scheduler
-        with torch.cuda.stream(st):
+        if self._backend is None:
+            torch.cuda.set_device(self.gpu_id)
+        with (torch.cuda.stream(torch.cuda.Stream()) if self._backend is None else contextlib.nullcontext()):
             if voice_id:
                 vid = Path(voice_id).name
                 if vid not in self.voice_cache:
@@ -458,7 +479,14 @@ class TextToSpeechEngine:
             DONE = object()
 
             def emit(b):   # called from the request thread; blocks it when the consumer is slow (bounded queue)
-                asyncio.run_coroutine_threadsafe(q.put(b), loop).result()
+                f = asyncio.run_coroutine_threadsafe(q.put(b), loop)
+                while True:
+                    try:
+                        return f.result(timeout=0.1)
+                    except concurrent.futures.TimeoutError:
+                        if cancellation_token is not None and cancellation_token.is_cancelled():
+                            f.cancel()
+                            raise _Cancelled()
 
             def work():
                 try:
@@ -467,8 +495,13 @@ class TextToSpeechEngine:
                                       chunk_overlap_strategy, crossfade_duration_milliseconds, request_id, cancellation_token,
                                       emit, t_start)
                     emit(DONE)
+                except _Cancelled:
+                    pass
                 except BaseException as ex:
-                    emit(ex)
+                    try:
+                        emit(ex)
+                    except _Cancelled:
+                        pass
 
             fut = loop.run_in_executor(self.request_executor, work)
             first = True

@@ -11,7 +11,6 @@ from typing import List
 
 import torch
 
-_PUNCT = {"‘": "'", "’": "'", "“": '"', "”": '"', "…": "...", "—": "-", "–": "-"}
 _SENT_END = re.compile(r"(?<=[.!?])[\"')\]]*\s+")
 
 
@@ -76,29 +75,45 @@ def _split_oversized(text: str, max_len: int) -> List[str]:
     return [c.strip() for c in _merge_small(mid, 2, max_len) if c.strip()]
 
 
+_NORMALISE = (("...", ". "), ("\u2026", ". "), (" - ", ", "), ("\u2014", "-"), ("\u2013", "-"), (" ,", ","),
+              ("\u201c", '"'), ("\u201d", '"'), ("\u2018", "'"), ("\u2019", "'"))
+_ENDERS = (".", "!", "?", "-")
+
+
 def split_text_into_chunks(text: str, max_length: int = None) -> List[str]:
+    """Same observable behaviour as the reference (src/text_processing.py:114-196): collapse whitespace, normalise
+    punctuation, capitalise the first letter, segment into sentences, make every sentence end with punctuation, pack
+    sentences while `len(chunk) + len(sentence) + 1 <= max_length`, split oversized sentences, merge one-word chunks."""
     if not text or not text.strip():
         return []
-    for k, v in _PUNCT.items():
-        text = text.replace(k, v)
-    text = re.sub(r"\s+", " ", text).strip()
-    if not max_length or max_length <= 0:
-        return [text]
-    chunks, cur = [], ""
+    text = " ".join(text.split())
+    for old, new in _NORMALISE:
+        text = text.replace(old, new)
+    if text and text[0].islower():
+        text = text[0].upper() + text[1:]
+    sentences = []
     for s in _sentences(text):
+        s = s.strip()
+        if s:
+            sentences.append(s if s.endswith(_ENDERS) else s + ".")
+    if max_length is None:
+        return sentences
+    chunks, cur = [], ""
+    for s in sentences:
         if len(s) > max_length:
             if cur:
                 chunks.append(cur)
                 cur = ""
             chunks.extend(_split_oversized(s, max_length))
-        elif cur and len(cur) + len(s) + 1 > max_length:
-            chunks.append(cur)
-            cur = s
-        else:
+        elif len(cur) + len(s) + 1 <= max_length:
             cur = (cur + " " + s) if cur else s
+        else:
+            if cur:
+                chunks.append(cur)
+            cur = s
     if cur:
         chunks.append(cur)
-    return [c for c in _merge_small(chunks, 2, max_length) if c.strip()]
+    return [c.strip() for c in _merge_small(chunks, 2, max_length) if c.strip()]
 
 
 class SyntheticTokenizer:

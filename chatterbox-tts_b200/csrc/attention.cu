@@ -23,6 +23,7 @@ __device__ __forceinline__ void load_tile(uint32_t sdst, const bf16* base, long 
 }
 
 __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
+    pdl_prologue();
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
@@ -177,6 +178,6 @@ void launch_attention(const AttnParams& p, cudaStream_t st) {
     const int smem = (1 + 2 * KVS) * TILE_BYTES;
     ProfScope ps(PC_ATTN, 4.0 * p.T * p.T * D * p.H * p.batch * (p.causal ? 0.5 : 1.0), st);
     dim3 grid(cdiv(p.T, BQ), p.H, p.batch);
-    attn_kernel<<<grid, NT, smem, st>>>(p);
+    launch_pdl(attn_kernel, dim3(grid), dim3(NT), smem, st, p);
     CBX_CHECK(cudaGetLastError());
 }

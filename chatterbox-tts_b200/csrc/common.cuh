@@ -131,6 +131,25 @@ struct Philox {
 // u32 -> float in (0,1]
 __host__ __device__ static inline float u32_to_unit(uint32_t x) { return ((x >> 8) + 1) * (1.0f / 16777216.0f); }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel calls pdl_prologue() (or its two halves) and is launched through launch_pdl(): the next kernel's CTAs are
+// scheduled as soon as all CTAs of the current one have started, run their prologue (barrier init, TMEM allocation,
+// weight prefetch) and then block in griddepcontrol.wait until the current kernel has completed and flushed its writes.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CBX_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // ---------------------------------------------------------------- per-launch profiler (bench.py roofline pass)
 enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_GEMV = 2, PC_DECODE_ATTN = 3, PC_SAMPLER = 4, PC_NORM = 5, PC_ELEMWISE = 6, PC_HIFT_MISC = 7, PC_COUNT = 8 };
 bool prof_enabled();

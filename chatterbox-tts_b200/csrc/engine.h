@@ -38,6 +38,8 @@ struct T3Model {
     int* page_table = nullptr; T3SlotState* slot_state = nullptr; int* slot_pos = nullptr; uint8_t* seen = nullptr;
     int* out_tokens = nullptr; int out_stride = 0; float *x, *qkv, *attn, *act, *logits;
     int *d_slots = nullptr, *d_rowmap = nullptr;   // active set staging [max_streams], [2*max_streams]
+    // megakernel state
+    bool mega = false; MegaLayer* d_layers = nullptr; float *xa = nullptr, *xb = nullptr, *opart = nullptr, *dpart = nullptr, *apart = nullptr; unsigned int* bar = nullptr;
     // prefill workspace
     float* pf_x; bf16 *pf_xn, *pf_qkv, *pf_att, *pf_act; int* pf_text; int pf_max = 0;
     // host side

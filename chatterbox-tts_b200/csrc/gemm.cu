@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(Cfg<BM, BN, WM, WN>::THREADS) gemm_mma_kernel(
     const bf16* Ab = p.A + (long)b * p.a_bs;
     const bf16* Wb = p.W + (long)b * p.w_bs;
     const uint32_t sbase = smem_u32(smem);
+    pdl_prologue();
 
     constexpr int A_CH = BM * 4 / C::THREADS;  // 16B chunks per thread per stage
     constexpr int B_CH = BN * 4 / C::THREADS;
@@ -156,7 +157,7 @@ void launch_cfg(const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BM, BN, WM, WN>;
     dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN), p.batch);
     bool done = false;
-#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { gemm_mma_kernel<BM, BN, WM, WN, A1, A2><<<grid, C::THREADS, C::SMEM, st>>>(p); done = true; }
+#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { launch_pdl(gemm_mma_kernel<BM, BN, WM, WN, A1, A2>, grid, dim3(C::THREADS), C::SMEM, st, p); done = true; }
     CBX_FOR_ACT_PAIRS(CBX_LAUNCH)
 #undef CBX_LAUNCH
     CBX_REQUIRE(done, "gemm: activation pair not instantiated");

@@ -79,9 +79,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_launch_dependents();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pdl_wait();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -183,7 +185,7 @@ bool launch_tc(const GemmParams& p, cudaStream_t st) {
     }
     dim3 grid(cdiv(p.M, TM), cdiv(p.N, BN), p.batch);
     bool done = false;
-#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { gemm_tc_kernel<BN, A1, A2><<<grid, 320, C::SMEM, st>>>(tmA, tmW, p, p.kc / TK, w_batched); done = true; }
+#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { launch_pdl(gemm_tc_kernel<BN, A1, A2>, grid, dim3(320), C::SMEM, st, tmA, tmW, p, p.kc / TK, w_batched); done = true; }
     CBX_FOR_ACT_PAIRS(CBX_LAUNCH)
 #undef CBX_LAUNCH
     if (!done) return false;

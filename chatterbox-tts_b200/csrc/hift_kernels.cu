@@ -11,6 +11,7 @@ __constant__ float c_sin16[16];
 
 // f0[t] = | w . x[t] + b |  (x bf16 [T][C], one warp per frame)
 __global__ void f0_classifier_kernel(const bf16* __restrict__ x, long ld, const float* __restrict__ w, const float* __restrict__ b, float* f0, int T, int C) {
+    pdl_prologue();
     int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= T) return;
     float s = 0.f;
@@ -21,6 +22,7 @@ __global__ void f0_classifier_kernel(const bf16* __restrict__ x, long ld, const 
 
 // per-frame, per-harmonic phase prefix (cycles, double): cum[t][h] = sum_{u<t} up * fp32(f0[u]*(h+1)/sr)
 __global__ void f0_prefix_kernel(const float* __restrict__ f0, double* cum, int T, int up, float sr, int H) {
+    pdl_prologue();
     int h = threadIdx.x;
     if (h < H && blockIdx.x == 0) {
         double c = 0.0;
@@ -36,6 +38,7 @@ __global__ void f0_prefix_kernel(const float* __restrict__ f0, double* cum, int 
 //   theta_h = 2*pi*frac(cum[t][h] + (j+1) * fp32(f0[t]*h/sr)),  sine = amp*sin(theta_h + phase_h)
 //   s = tanh( sum_h lw[h] * (sine*uv + namp*noise_h) + lb )
 __global__ void source_kernel(const SourceParams p) {
+    pdl_prologue();
     long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.L) return;
     const long cache_len = p.dyn ? (long)p.dyn->cache_len : p.cache_len;
@@ -73,6 +76,7 @@ __global__ void source_kernel(const SourceParams p) {
 
 // STFT (n_fft 16, hop 4, hann, center/reflect): out[f][c] c<9 real, 9..17 imag, bf16, row stride ld (>=18; extra channels zero)
 __global__ void stft16_kernel(const float* __restrict__ s, long L, bf16* out, long ld, int F) {
+    pdl_prologue();
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     float x[16];
@@ -97,6 +101,7 @@ __global__ void stft16_kernel(const float* __restrict__ s, long L, bf16* out, lo
 
 // y[F][18] (fp32: 9 log-magnitudes, 9 phase pre-activations) -> wav[4*(F-1)], with clamp and leading trim-fade
 __global__ void istft16_kernel(const float* __restrict__ y, long ldy, int F, float* wav, long L, float limit, const float* __restrict__ fade, int fade_len) {
+    pdl_prologue();
     long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= L) return;
     // frames f with 0 <= n + 8 - 4f < 16
@@ -130,6 +135,7 @@ __global__ void istft16_kernel(const float* __restrict__ y, long ldy, int F, flo
 }
 
 __global__ void snake_rows_kernel(const float* __restrict__ in, long ld_in, bf16* out, long ld_out, int rows, int C, const float* __restrict__ alpha) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)rows * C) return;
     int r = i / C, c = i % C;
@@ -138,6 +144,7 @@ __global__ void snake_rows_kernel(const float* __restrict__ in, long ld_in, bf16
 
 // ESPnet relative positional table: row j <-> relative position T-1-j; bf16 [2T-1][D]
 __global__ void relpos_table_kernel(bf16* out, int T, int D) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)(2 * T - 1) * D) return;
     int j = i / D, c = i % D;
@@ -148,11 +155,13 @@ __global__ void relpos_table_kernel(bf16* out, int T, int D) {
 }
 
 __global__ void copy_row_kernel(float* dst, const float* src, int C) {
+    pdl_prologue();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) dst[c] = src[c];
 }
 
 __global__ void spk_affine_kernel(const float* __restrict__ emb, int D, const float* __restrict__ w, const float* __restrict__ b, float* out, int N) {
+    pdl_prologue();
     // out = W * (emb / max(||emb||, 1e-12)) + b ; one CTA
     __shared__ float red[32];
     __shared__ float nrm;
@@ -186,39 +195,39 @@ void hift_init_constants() {
     CBX_CHECK(cudaMemcpyToSymbol(c_sin16, sn, sizeof(sn)));
 }
 void launch_f0_classifier(const bf16* x, long ld, const float* w, const float* b, float* f0, int T, int C, cudaStream_t st) {
-    f0_classifier_kernel<<<g1((long)T * 32), 256, 0, st>>>(x, ld, w, b, f0, T, C);
+    launch_pdl(f0_classifier_kernel, dim3(g1((long)T * 32)), dim3(256), 0, st, x, ld, w, b, f0, T, C);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_source(const SourceParams& p, int T, cudaStream_t st) {
     ProfScope ps(PC_HIFT_MISC, (double)p.L * 4, st);
-    f0_prefix_kernel<<<1, 32, 0, st>>>(p.f0, p.cum, T, p.up, p.sr, p.n_harm);
-    source_kernel<<<g1(p.L), 256, 0, st>>>(p);
+    launch_pdl(f0_prefix_kernel, dim3(1), dim3(32), 0, st, p.f0, p.cum, T, p.up, p.sr, p.n_harm);
+    launch_pdl(source_kernel, dim3(g1(p.L)), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_stft16(const float* s, long L, bf16* out, long ld, int F, cudaStream_t st) {
     ProfScope ps(PC_HIFT_MISC, (double)L * 4 + (double)F * ld * 2, st);
-    stft16_kernel<<<g1(F, 128), 128, 0, st>>>(s, L, out, ld, F);
+    launch_pdl(stft16_kernel, g1(F, 128), dim3(128), 0, st, s, L, out, ld, F);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_istft16(const float* y, long ldy, int F, float* wav, long L, float limit, const float* fade, int fade_len, cudaStream_t st) {
     ProfScope ps(PC_HIFT_MISC, (double)F * ldy * 4 + (double)L * 4, st);
-    istft16_kernel<<<g1(L), 256, 0, st>>>(y, ldy, F, wav, L, limit, fade, fade_len);
+    launch_pdl(istft16_kernel, dim3(g1(L)), dim3(256), 0, st, y, ldy, F, wav, L, limit, fade, fade_len);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_snake_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, const float* alpha, cudaStream_t st) {
     ProfScope ps(PC_HIFT_MISC, (double)rows * C * 6, st);
-    snake_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(in, ld_in, out, ld_out, rows, C, alpha);
+    launch_pdl(snake_rows_kernel, dim3(g1((long)rows * C)), dim3(256), 0, st, in, ld_in, out, ld_out, rows, C, alpha);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_relpos_table(bf16* out, int T, int D, cudaStream_t st) {
-    relpos_table_kernel<<<g1((long)(2 * T - 1) * D), 256, 0, st>>>(out, T, D);
+    launch_pdl(relpos_table_kernel, dim3(g1((long)(2 * T - 1) * D)), dim3(256), 0, st, out, T, D);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_copy_row(float* dst, const float* src, int C, cudaStream_t st) {
-    copy_row_kernel<<<g1(C), 256, 0, st>>>(dst, src, C);
+    launch_pdl(copy_row_kernel, dim3(g1(C)), dim3(256), 0, st, dst, src, C);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_spk_affine(const float* emb, int D, const float* w, const float* b, float* out, int N, cudaStream_t st) {
-    spk_affine_kernel<<<1, 128, 0, st>>>(emb, D, w, b, out, N);
+    launch_pdl(spk_affine_kernel, dim3(1), dim3(128), 0, st, emb, D, w, b, out, N);
     CBX_CHECK(cudaGetLastError());
 }

@@ -8,6 +8,7 @@ namespace {
 // one warp per row, the row cached in registers (C <= 32 * NORM_MAX_PER_LANE): one global read, two-pass statistics
 constexpr int NORM_MAX_PER_LANE = 32;
 __global__ void norm_kernel(NormParams p) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const long total = (long)p.rows * p.batch;
     if (warp >= total) return;
@@ -47,6 +48,7 @@ __global__ void norm_kernel(NormParams p) {
 }
 
 __global__ void gather_rows_bf16_kernel(const float* __restrict__ table, const int* __restrict__ idx, int n, int C, bf16* out, long ld) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)n * C) return;
     int r = i / C, c = i % C;
@@ -55,6 +57,7 @@ __global__ void gather_rows_bf16_kernel(const float* __restrict__ table, const i
 }
 
 __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ in, long ld_in, bf16* out, long ld_out, int rows, int C, int act, float act_param) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)rows * C) return;
     int r = i / C, c = i % C;
@@ -62,6 +65,7 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ in, long ld_in
 }
 
 __global__ void add_rows_kernel(float* a, long lda, const float* b, long ldb, int rows, int C) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)rows * C) return;
     int r = i / C, c = i % C;
@@ -70,6 +74,7 @@ __global__ void add_rows_kernel(float* a, long lda, const float* b, long ldb, in
 
 // nearest x2 upsample along time, fp32 [T][C] -> bf16 [2T][C]
 __global__ void upsample2_kernel(const float* __restrict__ in, bf16* out, long ld_out, int T, int C) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)2 * T * C) return;
     int r = i / C, c = i % C;
@@ -79,6 +84,7 @@ __global__ void upsample2_kernel(const float* __restrict__ in, bf16* out, long l
 // CFM estimator input: rows [x | mu | spks | cond] (cond row) and [x | 0 | 0 | 0] (uncond row), bf16, 4*mel channels
 __global__ void pack_cfm_input_kernel(const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ spks,
                                       const float* __restrict__ cond, bf16* out, long out_bs, int T, int mel) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int C = 4 * mel;
     if (i >= (long)2 * T * C) return;
@@ -97,6 +103,7 @@ __global__ void pack_cfm_input_kernel(const float* __restrict__ x, const float* 
 
 // x += dt * ((1+r) v_c - r v_u)
 __global__ void euler_update_kernel(float* x, const float* __restrict__ v, long v_bs, long n, float dt, float r) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     x[i] += dt * ((1.f + r) * v[i] - r * v[v_bs + i]);
@@ -105,6 +112,7 @@ __global__ void euler_update_kernel(float* x, const float* __restrict__ v, long 
 // one CTA per (query row, head); generic head_dim (perceiver: 256).  q [Tq][ldq], k/v [Tk][ldk]
 __global__ void small_attention_kernel(const bf16* __restrict__ q, long ldq, const bf16* __restrict__ k, const bf16* __restrict__ v, long ldk,
                                        bf16* out, long ldo, int Tk, int hd, float scale) {
+    pdl_prologue();
     extern __shared__ float sm[];  // scores [Tk]
     const int qi = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const bf16* qr = q + (long)qi * ldq + h * hd;
@@ -136,38 +144,38 @@ void launch_norm(const NormParams& p, cudaStream_t st) {
     if (warps == 0) return;
     CBX_REQUIRE(p.C <= 32 * NORM_MAX_PER_LANE, "norm: row too wide for the register tile");
     ProfScope ps(PC_NORM, (double)warps * p.C * 6, st);
-    norm_kernel<<<g1(warps * 32, 256), 256, 0, st>>>(p);
+    launch_pdl(norm_kernel, g1(warps * 32, 256), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_gather_rows_bf16(const float* table, const int* idx, int n, int C, bf16* out, long ld, cudaStream_t st) {
-    gather_rows_bf16_kernel<<<g1((long)n * C), 256, 0, st>>>(table, idx, n, C, out, ld);
+    launch_pdl(gather_rows_bf16_kernel, dim3(g1((long)n * C)), dim3(256), 0, st, table, idx, n, C, out, ld);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_f32_to_bf16_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, int act, float act_param, cudaStream_t st) {
     ProfScope ps(PC_ELEMWISE, (double)rows * C * 6, st);
     if (rows == 0) return;
-    f32_to_bf16_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(in, ld_in, out, ld_out, rows, C, act, act_param);
+    launch_pdl(f32_to_bf16_rows_kernel, dim3(g1((long)rows * C)), dim3(256), 0, st, in, ld_in, out, ld_out, rows, C, act, act_param);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_add_rows(float* a, long lda, const float* b, long ldb, int rows, int C, cudaStream_t st) {
-    add_rows_kernel<<<g1((long)rows * C), 256, 0, st>>>(a, lda, b, ldb, rows, C);
+    launch_pdl(add_rows_kernel, dim3(g1((long)rows * C)), dim3(256), 0, st, a, lda, b, ldb, rows, C);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_upsample2(const float* in, bf16* out, long ld_out, int T, int C, cudaStream_t st) {
-    upsample2_kernel<<<g1((long)2 * T * C), 256, 0, st>>>(in, out, ld_out, T, C);
+    launch_pdl(upsample2_kernel, dim3(g1((long)2 * T * C)), dim3(256), 0, st, in, out, ld_out, T, C);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_pack_cfm_input(const float* x, const float* mu, const float* spks, const float* cond, bf16* out, long out_bs, int T, int mel, cudaStream_t st) {
     ProfScope ps(PC_ELEMWISE, (double)T * mel * 4 * 2 * 6, st);
-    pack_cfm_input_kernel<<<g1((long)2 * T * 4 * mel), 256, 0, st>>>(x, mu, spks, cond, out, out_bs, T, mel);
+    launch_pdl(pack_cfm_input_kernel, dim3(g1((long)2 * T * 4 * mel)), dim3(256), 0, st, x, mu, spks, cond, out, out_bs, T, mel);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_euler_update(float* x, const float* v, long v_bs, long n, float dt, float r, cudaStream_t st) {
     ProfScope ps(PC_ELEMWISE, (double)n * 16, st);
-    euler_update_kernel<<<g1(n), 256, 0, st>>>(x, v, v_bs, n, dt, r);
+    launch_pdl(euler_update_kernel, dim3(g1(n)), dim3(256), 0, st, x, v, v_bs, n, dt, r);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_small_attention(const bf16* q, long ldq, const bf16* k, const bf16* v, long ldk, bf16* out, long ldo, int Tq, int Tk, int H, int hd, float scale, cudaStream_t st) {
-    small_attention_kernel<<<dim3(Tq, H), 128, Tk * sizeof(float), st>>>(q, ldq, k, v, ldk, out, ldo, Tk, hd, scale);
+    launch_pdl(small_attention_kernel, dim3(Tq, H), dim3(128), Tk * sizeof(float), st, q, ldq, k, v, ldk, out, ldo, Tk, hd, scale);
     CBX_CHECK(cudaGetLastError());
 }

@@ -1,5 +1,6 @@
 // Per-launch CUDA-event profiler: bench.py runs one instrumented pass of the workload after the timed
 // steps and reads back, per kernel class, launch count, summed device time and summed algorithmic work.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -14,6 +15,11 @@ thread_local Rec t_cur;
 }  // namespace
 
 bool prof_enabled() { return g_on; }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* d = getenv("CBX_DISABLE_PDL"); v = (d && d[0] == '1') ? 0 : 1; }
+    return v == 1 && !g_on;   // per-launch event timing needs plain stream order
+}
 void prof_begin_launch(int cls, double work, cudaStream_t st) {
     t_cur.cls = cls; t_cur.work = work;
     cudaEventCreate(&t_cur.a); cudaEventCreate(&t_cur.b);

@@ -1,6 +1,7 @@
 // T3 speech-token decoder: weight registration, voice prefix (T3CondEnc + Perceiver), prefill,
 // batched decode steps (CUDA-graph replayed) and KV page management.  Host orchestration only;
 // the arithmetic is in gemm.cu / attention.cu / norm_act.cu / t3_kernels.cu.
+#include <cstdlib>
 #include "engine.h"
 
 using namespace dims;
@@ -82,6 +83,18 @@ void t3_alloc(cbx_engine* e) {
     m.slot_pages.assign(S, {});
     m.slot_maxnew.assign(S, 0);
     t3_kernels_init();
+    m.xa = e->scratch<float>((long)R * T3_D); m.xb = e->scratch<float>((long)R * T3_D);
+    m.opart = e->scratch<float>(4L * R * T3_D); m.dpart = e->scratch<float>(4L * R * T3_D);
+    m.apart = e->scratch<float>((long)R * T3_H * 8 * 66);
+    m.bar = e->scratch<unsigned int>(4);
+    m.d_layers = e->scratch<MegaLayer>(c.t3_layers);
+    std::vector<MegaLayer> hl(c.t3_layers);
+    for (int i = 0; i < c.t3_layers; i++) hl[i] = MegaLayer{m.layers[i].wqkv_f, m.layers[i].wo_f, m.layers[i].wgu_f, m.layers[i].wd_f, m.layers[i].ln1, m.layers[i].ln2};
+    CBX_CHECK(cudaMemcpy(m.d_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+    // The persistent megakernel owns all 148 SMs for a whole step, which blocks the S3Gen kernels that otherwise overlap
+    // with T3 on other streams (measured: 5.44 s vs 4.49 s per 200-word paragraph), so it is opt-in (CBX_T3_MEGA=1).
+    const char* en = getenv("CBX_T3_MEGA");
+    m.mega = (en && en[0] == '1') && t3_mega_init(c.max_seq);
 }
 
 static void gemm_lin(const Lin& l, const bf16* A, long lda, int M, float* outF, bf16* outB, long ldc, cudaStream_t st,
@@ -199,9 +212,28 @@ int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w,
     return slot;
 }
 
+static void enqueue_sampler(cbx_engine* e, int n, const float* noise, cudaStream_t st) {
+    T3Model& m = e->t3;
+    SamplerParams s; s.slots = m.d_slots; s.state = m.slot_state; s.slot_pos = m.slot_pos; s.logits = m.logits; s.ld_logits = T3_VPAD;
+    s.seen = m.seen; s.seen_stride = T3_VPAD; s.out_tokens = m.out_tokens; s.out_stride = m.out_stride; s.noise = noise; s.noise_stride = T3_V;
+    s.x = m.x; s.speech_emb = m.speech_emb; s.speech_pos = m.speech_pos; s.V = T3_V; s.dim = T3_D; s.eos = T3_EOS;
+    launch_sampler(s, n, st);
+}
+
 static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t st) {
     T3Model& m = e->t3;
     const int rows = 2 * n;
+    if (m.mega) {   // whole step = one persistent cooperative kernel + the sampler
+        MegaParams p;
+        p.layers = m.d_layers; p.n_layers = e->cfg.t3_layers; p.head_f = m.head_f; p.head_items = T3_VPAD / 16; p.vocab = T3_V; p.final_norm = m.final_norm;
+        p.x = m.x; p.xa = m.xa; p.xb = m.xb; p.qkv = m.qkv; p.attn = m.attn; p.act = m.act; p.opart = m.opart; p.dpart = m.dpart; p.apart = m.apart; p.logits = m.logits;
+        p.ld_logits = T3_VPAD; p.kv = m.kv; p.kv_layer_stride = m.kv_layer_stride; p.kv_half = m.kv_half; p.page_table = m.page_table; p.max_pages = m.max_pages;
+        p.slot_pos = m.slot_pos; p.row_map = m.d_rowmap; p.inv_freq = m.inv_freq; p.rows = rows; p.rows_total = 2 * e->cfg.max_streams; p.max_seq = e->cfg.max_seq;
+        p.bar = m.bar;
+        launch_t3_mega(p, e->cfg.max_seq, st);
+        enqueue_sampler(e, n, noise, st);
+        return;
+    }
     for (int li = 0; li < e->cfg.t3_layers; li++) {
         const T3Layer& l = m.layers[li];
         GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1; q.x = m.x; q.ldx_in = T3_D;
@@ -223,10 +255,7 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
     GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = 1; h.x = m.x; h.ldx_in = T3_D;
     h.row_map = m.d_rowmap; h.rows = rows; h.gain = m.final_norm; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
     launch_gemv(h, 8, st);
-    SamplerParams s; s.slots = m.d_slots; s.state = m.slot_state; s.slot_pos = m.slot_pos; s.logits = m.logits; s.ld_logits = T3_VPAD;
-    s.seen = m.seen; s.seen_stride = T3_VPAD; s.out_tokens = m.out_tokens; s.out_stride = m.out_stride; s.noise = noise; s.noise_stride = T3_V;
-    s.x = m.x; s.speech_emb = m.speech_emb; s.speech_pos = m.speech_pos; s.V = T3_V; s.dim = T3_D; s.eos = T3_EOS;
-    launch_sampler(s, n, st);
+    enqueue_sampler(e, n, noise, st);
 }
 
 void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* noise_dev, cudaStream_t st) {
@@ -242,7 +271,7 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
         CBX_CHECK(cudaStreamSynchronize(st));
         m.h_active = act;
     }
-    const long per_step = 5L * e->cfg.t3_layers + 2;
+    const long per_step = m.mega ? 2 : 5L * e->cfg.t3_layers + 2;
     if (noise_dev || prof_enabled()) {
         for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev ? noise_dev + (long)i * n * T3_V : nullptr, st);
     } else {

@@ -22,24 +22,58 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
     bf16* xs = reinterpret_cast<bf16*>(smem);                                   // [8*NT][ldx]
     float* part = reinterpret_cast<float*>(smem + (size_t)8 * NT * ldx * 2);    // [nwarps][S][16][8*NT]
 
-    // ---- stage input rows (optionally RMS-normalised) as bf16
-    for (int r = warp; r < 8 * NT; r += nwarps) {
-        bf16* dst = xs + (size_t)r * ldx;
-        if (r < p.rows) {
-            const float* src = p.x + (long)p.row_map[r] * p.ldx_in;
-            float scale = 1.f;
-            if (p.gain) {
-                float ss = 0.f;
-                for (int k = lane; k < p.K; k += 32) { float v = src[k]; ss += v * v; }
-                scale = rsqrtf(warp_sum(ss) / p.K + p.eps);
+    // weights do not depend on the previous kernel: fetch this warp's first batch of fragments before waiting for it
+    pdl_launch_dependents();
+    uint4 wpre[8];
+    {
+        const int KTp = p.K >> 4, perp = KTp / nwarps, strip0 = blockIdx.x * p.strips_per_cta;
+        const uint4* wp0 = reinterpret_cast<const uint4*>(p.Wf) + ((size_t)strip0 * KTp + warp * perp) * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < 8; u++) wpre[u] = (strip0 < p.n_strips && u < perp) ? __ldg(wp0 + (size_t)u * 32) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_wait();
+    // ---- stage input rows (optionally RMS-normalised) as bf16: every thread owns float4 columns of all rows, so the
+    // whole staging is one global round trip; per-row sums of squares are reduced through shared memory
+    {
+        float* red = part;   // [8*NT][nwarps] scratch inside the partial-sum area (free until the main loop ends)
+        constexpr int R = 8 * NT;
+        const int nvec = p.K >> 2;
+        for (int c0 = 0; c0 < nvec; c0 += blockDim.x) {
+            const int c = c0 + tid;
+            float4 v[R];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                v[r] = (r < p.rows && c < nvec) ? *reinterpret_cast<const float4*>(p.x + (long)p.row_map[r] * p.ldx_in + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.gain) {   // K == blockDim.x * 4 is not required: accumulate partial sums over the column passes
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    float ss = warp_sum(v[r].x * v[r].x + v[r].y * v[r].y + v[r].z * v[r].z + v[r].w * v[r].w);
+                    if (lane == 0) red[r * nwarps + warp] = (c0 == 0 ? 0.f : red[r * nwarps + warp]) + ss;
+                }
             }
-            for (int k = lane; k < p.K; k += 32) {
-                float v = src[k] * scale;
-                if (p.gain) v *= p.gain[k];
-                dst[k] = __float2bfloat16(v);
+            if (!p.gain) {
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (c < nvec) *reinterpret_cast<uint2*>(xs + (size_t)r * ldx + c * 4) = make_uint2(pack_bf16(v[r].x, v[r].y), pack_bf16(v[r].z, v[r].w));
             }
-        } else {
-            for (int k = lane; k < p.K; k += 32) dst[k] = __float2bfloat16(0.f);
+        }
+        if (p.gain) {
+            __syncthreads();
+            for (int c = tid; c < nvec; c += blockDim.x) {
+                const float4 gg = *reinterpret_cast<const float4*>(p.gain + c * 4);
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    uint2 o = make_uint2(0u, 0u);
+                    if (r < p.rows) {
+                        float ss = 0.f;
+                        for (int w = 0; w < nwarps; w++) ss += red[r * nwarps + w];
+                        const float scale = rsqrtf(ss / p.K + p.eps);
+                        const float4 a = *reinterpret_cast<const float4*>(p.x + (long)p.row_map[r] * p.ldx_in + c * 4);   // L1 hit
+                        o = make_uint2(pack_bf16(a.x * scale * gg.x, a.y * scale * gg.y), pack_bf16(a.z * scale * gg.z, a.w * scale * gg.w));
+                    }
+                    *reinterpret_cast<uint2*>(xs + (size_t)r * ldx + c * 4) = o;
+                }
+            }
         }
     }
     __syncthreads();
@@ -60,8 +94,10 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
             for (int kt = 0; kt < kt_per; kt += 8) {
                 uint4 w[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (kt + u < kt_per) w[u] = __ldg(wp + (size_t)(kt + u) * 32);
+                for (int u = 0; u < 8; u++) {
+                    if (sl == 0 && kt == 0) w[u] = wpre[u];
+                    else if (kt + u < kt_per) w[u] = __ldg(wp + (size_t)(kt + u) * 32);
+                }
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     if (kt + u < kt_per) {
@@ -125,12 +161,15 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
 // ------------------------------------------------------------------------------------------------
 constexpr int PAGE = 16, HD = 64;
 
-__global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeAttnParams p) {
+// Flash-decoding form: each of the 8 warps streams whole KV pages (K and V of a page are fetched together) and keeps an
+// online-softmax partial (m, l, o[64]); the partials are merged in shared memory -- two block barriers and two global
+// round trips instead of five and three.
+__global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams p) {
     __shared__ float qs[HD];
-    __shared__ float red[128];
-    __shared__ float osm[4][2][32];
-    extern __shared__ float sc[];  // [max positions]
+    __shared__ float wm[8], wl[8];
+    __shared__ float wo[8 * HD];
     const int h = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_prologue();
     const int row = p.row_map[r];
     const int slot = row >> 1;
     const int pos = p.slot_pos[slot];
@@ -140,14 +179,13 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeAttnParams
     bf16* vpool = p.kv + p.kv_half;
     if (tid < 32) {
         // rotate_half RoPE: pairs (d, d+32)
-        float inv = p.inv_freq[tid];
         float sn, cs;
-        sincosf((float)pos * inv, &sn, &cs);
-        float q0 = qkv[h * HD + tid], q1 = qkv[h * HD + tid + 32];
-        float k0 = qkv[p.H * HD + h * HD + tid], k1 = qkv[p.H * HD + h * HD + tid + 32];
+        sincosf((float)pos * p.inv_freq[tid], &sn, &cs);
+        const float q0 = qkv[h * HD + tid], q1 = qkv[h * HD + tid + 32];
+        const float k0 = qkv[p.H * HD + h * HD + tid], k1 = qkv[p.H * HD + h * HD + tid + 32];
         qs[tid] = (q0 * cs - q1 * sn) * 0.125f;
         qs[tid + 32] = (q1 * cs + q0 * sn) * 0.125f;
-        long base = (((long)pt[pos / PAGE] * p.H + h) * PAGE + (pos % PAGE)) * HD;
+        const long base = (((long)pt[pos / PAGE] * p.H + h) * PAGE + (pos % PAGE)) * HD;
         kpool[base + tid] = __float2bfloat16(k0 * cs - k1 * sn);
         kpool[base + tid + 32] = __float2bfloat16(k1 * cs + k0 * sn);
         vpool[base + tid] = __float2bfloat16(qkv[2 * p.H * HD + h * HD + tid]);
@@ -156,76 +194,70 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const DecodeAttnParams
     __syncthreads();
     const int n = pos + 1, npages = (n + PAGE - 1) / PAGE;
     const int pp = lane >> 1, half = lane & 1;
-    for (int pg = warp; pg < npages; pg += 4) {
-        const uint4* kp = reinterpret_cast<const uint4*>(kpool + (((long)pt[pg] * p.H + h) * PAGE + pp) * HD + half * 32);
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            uint4 u = kp[c];
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                float2 f = __bfloat1622float2(b2[e]);
-                s += f.x * qs[half * 32 + c * 8 + e * 2] + f.y * qs[half * 32 + c * 8 + e * 2 + 1];
-            }
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        int j = pg * PAGE + pp;
-        if (half == 0 && j < n) sc[j] = s;
-    }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int j = tid; j < n; j += 128) mx = fmaxf(mx, sc[j]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    __syncthreads();
-    float sum = 0.f;
-    for (int j = tid; j < n; j += 128) { float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
-    sum = warp_sum(sum);
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
-    const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+    float m = -INFINITY, lsum = 0.f;
     float acc[32];
 #pragma unroll
     for (int d = 0; d < 32; d++) acc[d] = 0.f;
-    for (int pg = warp; pg < npages; pg += 4) {
-        int j = pg * PAGE + pp;
-        if (j >= n) continue;   // stale page tail may hold non-finite values
-        float w = sc[j];
-        const uint4* vp = reinterpret_cast<const uint4*>(vpool + (((long)pt[pg] * p.H + h) * PAGE + pp) * HD + half * 32);
+    for (int pg = warp; pg < npages; pg += 8) {
+        const long off = (((long)pt[pg] * p.H + h) * PAGE + pp) * HD + half * 32;
+        const uint4* kp = reinterpret_cast<const uint4*>(kpool + off);
+        const uint4* vp = reinterpret_cast<const uint4*>(vpool + off);
+        uint4 ku[4], vu[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { ku[c] = kp[c]; vu[c] = vp[c]; }
+        float sc = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            uint4 u = vp[c];
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&ku[c]);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                float2 f = __bfloat1622float2(b2[e]);
-                acc[c * 8 + e * 2] += w * f.x;
-                acc[c * 8 + e * 2 + 1] += w * f.y;
+                const float2 f = __bfloat1622float2(b2[e]);
+                sc += f.x * qs[half * 32 + c * 8 + e * 2] + f.y * qs[half * 32 + c * 8 + e * 2 + 1];
+            }
+        }
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        if (pg * PAGE + pp >= n) sc = -INFINITY;           // stale tail of the last page
+        const float mnew = fmaxf(m, warp_max(sc));         // finite: every page holds at least one valid position
+        const float corr = expf(m - mnew), pj = expf(sc - mnew);
+        m = mnew;
+        lsum = lsum * corr + pj;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&vu[c]);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __bfloat1622float2(b2[e]);
+                acc[c * 8 + e * 2] = acc[c * 8 + e * 2] * corr + (pj > 0.f ? pj * f.x : 0.f);
+                acc[c * 8 + e * 2 + 1] = acc[c * 8 + e * 2 + 1] * corr + (pj > 0.f ? pj * f.y : 0.f);
             }
         }
     }
-    // reduce over the 16 lanes that share `half`
 #pragma unroll
     for (int d = 0; d < 32; d++) {
         float v = acc[d];
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
         acc[d] = v;
     }
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2); lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8); lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
     if (lane < 2) {
 #pragma unroll
-        for (int d = 0; d < 32; d++) osm[warp][lane][d] = acc[d];
+        for (int d = 0; d < 32; d++) wo[warp * HD + lane * 32 + d] = acc[d];
+        if (lane == 0) { wm[warp] = m; wl[warp] = lsum; }
     }
     __syncthreads();
     if (tid < HD) {
-        int hf = tid >> 5, d = tid & 31;
-        float v = osm[0][hf][d] + osm[1][hf][d] + osm[2][hf][d] + osm[3][hf][d];
-        p.out[(long)row * (p.H * HD) + h * HD + tid] = v * inv;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; w++) M = fmaxf(M, wm[w]);
+        float Lt = 0.f, O = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const float e = wm[w] == -INFINITY ? 0.f : expf(wm[w] - M);
+            Lt += wl[w] * e; O += wo[w * HD + tid] * e;
+        }
+        p.out[(long)row * (p.H * HD) + h * HD + tid] = O / Lt;
     }
 }
 
@@ -256,6 +288,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) {
+    pdl_prologue();
     __shared__ float red[32];
     __shared__ float es[SAMP_T * SAMP_E];
     __shared__ float wsum[32];
@@ -399,6 +432,7 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
 // ------------------------------------------------------------------------------------------------
 // x[b][t][:] for t < Lp: [cond prefix (Lc) | text_emb[tok]+text_pos[i] (row 1: pos only when cfg>0) | bos ...]
 __global__ void assemble_embeds_kernel(const AssembleParams p) {
+    pdl_prologue();
     const int t = blockIdx.x, b = blockIdx.y;
     float* out = p.x + ((long)b * p.Lp + t) * p.dim;
     for (int d = threadIdx.x; d < p.dim; d += blockDim.x) {
@@ -415,6 +449,7 @@ __global__ void assemble_embeds_kernel(const AssembleParams p) {
 
 // rotate q,k in the fused qkv buffer (bf16 [2][Lp][3*H*64]) and write k,v into the rows' KV pages
 __global__ void rope_kv_prefill_kernel(const RopeKvParams p) {
+    pdl_prologue();
     const int t = blockIdx.x, b = blockIdx.y;
     bf16* row = p.qkv + ((long)b * p.Lp + t) * (3 * p.H * HD);
     const int* pt = p.page_table + (long)(p.row0 + b) * p.max_pages;
@@ -437,6 +472,7 @@ __global__ void rope_kv_prefill_kernel(const RopeKvParams p) {
 
 __global__ void init_slot_kernel(T3SlotState* st, T3SlotState v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
                                  float* x, const float* speech_emb, const float* speech_pos, int dim) {
+    pdl_prologue();
     for (int i = threadIdx.x; i < seen_stride; i += blockDim.x) seen[(long)slot * seen_stride + i] = (i == bos) ? 1 : 0;
     for (int d = threadIdx.x; d < dim; d += blockDim.x) {
         float e = speech_emb[(long)bos * dim + d] + speech_pos[d];
@@ -447,12 +483,14 @@ __global__ void init_slot_kernel(T3SlotState* st, T3SlotState v, int* slot_pos, 
 }
 
 __global__ void prompt_embed_kernel(float* out, const float* __restrict__ emb, const float* __restrict__ pos, const int* __restrict__ ids, int n, int D) {
+    pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)n * D) return;
     int r = i / D, c = i % D;
     out[i] = emb[(long)ids[r] * D + c] + pos[(long)r * D + c];
 }
 __global__ void scale_vec_kernel(float* out, const float* __restrict__ w, float s, int n) {
+    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = w[i] * s;
 }
@@ -464,11 +502,11 @@ void t3_kernels_init() {
     CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 void launch_prompt_embed(float* out, const float* emb, const float* pos, const int* ids, int n, int D, cudaStream_t st) {
-    prompt_embed_kernel<<<cdiv((long)n * D, 256), 256, 0, st>>>(out, emb, pos, ids, n, D);
+    launch_pdl(prompt_embed_kernel, dim3(cdiv((long)n * D, 256)), dim3(256), 0, st, out, emb, pos, ids, n, D);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_scale_vec(float* out, const float* w, float s, int n, cudaStream_t st) {
-    scale_vec_kernel<<<cdiv(n, 256), 256, 0, st>>>(out, w, s, n);
+    launch_pdl(scale_vec_kernel, dim3(cdiv(n, 256)), dim3(256), 0, st, out, w, s, n);
     CBX_CHECK(cudaGetLastError());
 }
 
@@ -481,31 +519,31 @@ void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
     int grid = cdiv(p.n_strips, S);
     ProfScope ps(PC_GEMV, (double)p.n_strips * 16 * p.K * 2 + (double)p.rows * (p.K + p.N) * 4, st);
     CBX_REQUIRE(smem <= 200 * 1024, "gemv: staging exceeds shared memory");
-    if (NT == 1) gemv_kernel<1><<<grid, nwarps * 32, smem, st>>>(p);
-    else gemv_kernel<2><<<grid, nwarps * 32, smem, st>>>(p);
+    if (NT == 1) launch_pdl(gemv_kernel<1>, dim3(grid), dim3(nwarps * 32), smem, st, p);
+    else launch_pdl(gemv_kernel<2>, dim3(grid), dim3(nwarps * 32), smem, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st) {
     ProfScope ps(PC_DECODE_ATTN, 0.0, st);
-    decode_attn_kernel<<<dim3(p.H, rows), 128, (size_t)(max_pos + PAGE) * sizeof(float), st>>>(p);
+    launch_pdl(decode_attn_kernel, dim3(p.H, rows), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st) {
     CBX_REQUIRE(p.V <= SAMP_T * SAMP_E, "sampler: vocabulary too large for the register tile");
     ProfScope ps(PC_SAMPLER, (double)n_streams * 2 * p.V * 4, st);
-    sampler_kernel<<<n_streams, SAMP_T, 0, st>>>(p);
+    launch_pdl(sampler_kernel, dim3(n_streams), dim3(SAMP_T), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_assemble_embeds(const AssembleParams& p, cudaStream_t st) {
-    assemble_embeds_kernel<<<dim3(p.Lp, 2), 256, 0, st>>>(p);
+    launch_pdl(assemble_embeds_kernel, dim3(p.Lp, 2), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_rope_kv_prefill(const RopeKvParams& p, cudaStream_t st) {
-    rope_kv_prefill_kernel<<<dim3(p.Lp, 2), 256, 0, st>>>(p);
+    launch_pdl(rope_kv_prefill_kernel, dim3(p.Lp, 2), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
                       float* x, const float* speech_emb, const float* speech_pos, int dim, cudaStream_t st) {
-    init_slot_kernel<<<1, 256, 0, st>>>(st_dev, v, slot_pos, slot, seen, seen_stride, bos, x, speech_emb, speech_pos, dim);
+    launch_pdl(init_slot_kernel, dim3(1), dim3(256), 0, st, st_dev, v, slot_pos, slot, seen, seen_stride, bos, x, speech_emb, speech_pos, dim);
     CBX_CHECK(cudaGetLastError());
 }

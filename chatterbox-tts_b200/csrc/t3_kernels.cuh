@@ -72,3 +72,21 @@ void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, 
 void t3_kernels_init();
 void launch_prompt_embed(float* out, const float* emb, const float* pos, const int* ids, int n, int D, cudaStream_t st);
 void launch_scale_vec(float* out, const float* w, float s, int n, cudaStream_t st);
+
+// ---- persistent decode-step megakernel (t3_mega.cu)
+struct MegaLayer { const bf16 *wqkv_f, *wo_f, *wgu_f, *wd_f; const float *ln1, *ln2; };
+struct MegaParams {
+    const MegaLayer* layers = nullptr; int n_layers = 0;
+    const bf16* head_f = nullptr; int head_items = 0; int vocab = 0; const float* final_norm = nullptr; float eps = 1e-5f;
+    const float* x = nullptr;            // [rows_total][1024] step input (written by the sampler / slot init)
+    float *xa = nullptr, *xb = nullptr;  // residual stream double buffer
+    float *qkv = nullptr, *attn = nullptr, *act = nullptr, *opart = nullptr, *dpart = nullptr, *logits = nullptr; long ld_logits = 0;
+    float* apart = nullptr;              // attention split partials [rows_total*16][8][66] = {max, sum, o[64]}
+    bf16* kv = nullptr; long kv_layer_stride = 0, kv_half = 0;
+    const int* page_table = nullptr; int max_pages = 0; const int* slot_pos = nullptr; const int* row_map = nullptr;
+    const float* inv_freq = nullptr;
+    int rows = 0, rows_total = 0, max_seq = 0;
+    unsigned int* bar = nullptr;
+};
+bool t3_mega_init(int max_seq);
+void launch_t3_mega(const MegaParams& p, int max_seq, cudaStream_t st);

@@ -39,7 +39,12 @@ def main():
         pos = 34 + len(text) + 1 + 120
         wbytes = 30 * 16779264 * 2 + 8208 * 1024 * 2
         kvbytes = 122880 * pos * 2 * ns
-        out[f"t3_streams{ns}"] = {"ms_per_step": ms, "tok_s": ns * 1e3 / ms, "audio_s_per_s": ns * 1e3 / ms / 25, "prefill_ms": prefill_ms,
+        import ctypes as C
+        tr = (C.c_ulonglong * 16)()
+        eng.lib.cbx_t3_mega_trace(tr)
+        names = ["P1 stage", "P1 items", "bar", "P2 attn", "bar", "P3 stage", "P3 items", "bar", "P4 stage", "P4 items", "bar", "P5 items", "bar"]
+        trace = {f"{i:02d} {names[i]}": int(tr[i + 1]) - int(tr[i]) for i in range(13)}
+        out[f"t3_streams{ns}"] = {"layer1_phase_ns": trace, "ms_per_step": ms, "tok_s": ns * 1e3 / ms, "audio_s_per_s": ns * 1e3 / ms / 25, "prefill_ms": prefill_ms,
                                   "hbm_gbs": (wbytes + kvbytes) / (ms * 1e-3) / 1e9}
         for s in slots:
             eng.t3_close(s)

@@ -153,7 +153,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     text = synthetic_text(WORDS)
     sampling = SamplingDefaults(tokens_per_word=TOK_PER_WORD)
-    eng = TextToSpeechEngine(f"cuda:{local}", concurrent_requests=1, sampling=sampling, seed=0)
+    eng = TextToSpeechEngine(f"cuda:{local}", concurrent_requests=int(os.environ.get("BENCH_CONCURRENT", "8")), sampling=sampling, seed=0)
     lib = L.load()
 
     def barrier():
@@ -180,6 +180,29 @@ def run_b200(args):
                 first = (time.time() - t0) * 1e3
             nbytes += len(chunk)
         return nbytes, first
+
+    async def concurrent_leg(n_streams=8, words=100):
+        """BASELINE.json configs[2]: 8 concurrent streams batched on one B200, 100-word prompts, cached voice conditioning."""
+        texts = [synthetic_text(words, seed=1234 + i) for i in range(n_streams)]
+
+        async def one(i):
+            nb, t0, first = 0, time.time(), None
+            async for chunk in eng.stream(text=texts[i], output_format="raw_pcm", voice_id=None, request_id=f"c{i}", cancellation_token=None, **REQ):
+                if first is None and len(chunk):
+                    first = (time.time() - t0) * 1e3
+                nb += len(chunk)
+            return nb, first
+        await asyncio.gather(*[one(i) for i in range(n_streams)])      # warm-up: captures the S3Gen graphs of every lane
+        torch.cuda.synchronize()
+        t0 = time.time()
+        res = await asyncio.gather(*[one(i) for i in range(n_streams)])
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        audio = sum(r[0] for r in res) / 2 / 24000.0
+        firsts = sorted(r[1] for r in res if r[1] is not None)
+        return {"workload": "configs[2]: 8 concurrent streams on one B200, 100-word prompts, cached voice conditioning", "streams": n_streams,
+                "value": audio / dt, "unit": "audio-s/s", "per_stream_x_realtime": audio / dt / n_streams,
+                "first_chunk_ms_p50": firsts[len(firsts) // 2] if firsts else None, "seconds": dt}
 
     async def main():
         await eng.ainit()
@@ -267,6 +290,8 @@ def run_b200(args):
                 "gpu_launches": int(launches), "roofline": roof, "kernels": kern}
         if cpu:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_concurrent:
+            line["concurrent8"] = await concurrent_leg()
         print(json.dumps(line), flush=True)
 
     asyncio.run(main())
@@ -282,6 +307,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-concurrent", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -232,7 +232,9 @@ class TextToSpeechEngine:
         self.tts_semaphore = None
         self.request_executor = concurrent.futures.ThreadPoolExecutor(max_workers=n, thread_name_prefix="cbx-req")
         self.voice_conditioning_executor = concurrent.futures.ThreadPoolExecutor(max_workers=n, thread_name_prefix="cbx-voice")
-        self.native_kwargs = dict(max_streams=max(8, n), n_lanes=max(2, min(n, 8)))
+        # two S3Gen lanes: measured on B200, more lanes do not raise aggregate throughput (the per-call kernels are
+        # latency-bound and already span the SMs) and cost workspace + graph captures per lane
+        self.native_kwargs = dict(max_streams=max(8, n), n_lanes=2)
         self.native_kwargs.update(native_kwargs or {})
         self.native: Optional[NativeEngine] = None
         self.scheduler: Optional[T3Scheduler] = None

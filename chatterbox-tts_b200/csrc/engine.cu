@@ -45,11 +45,18 @@ __global__ void crossfade_pcm_kernel(const float* __restrict__ cur, long n, cons
     out[i] = (short)x;   // truncation toward zero, as torch .to(int16)
 }
 
+// Lanes are sticky per calling thread: a request thread keeps re-using one lane (its captured graphs and workspaces),
+// different request threads spread over the lanes.  Rotating a single request over all lanes doubled its latency.
 Lane& pick_lane(cbx_engine* e) {
-    std::lock_guard<std::mutex> g(e->lane_pick_mu);
-    Lane& L = *e->lanes[e->lane_rr % e->lanes.size()];
-    e->lane_rr++;
-    return L;
+    static thread_local cbx_engine* t_engine = nullptr;
+    static thread_local int t_lane = -1;
+    if (t_engine != e || t_lane < 0 || t_lane >= (int)e->lanes.size()) {
+        std::lock_guard<std::mutex> g(e->lane_pick_mu);
+        t_lane = e->lane_rr % (int)e->lanes.size();
+        e->lane_rr++;
+        t_engine = e;
+    }
+    return *e->lanes[t_lane];
 }
 
 }  // namespace
@@ -323,7 +330,10 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
     StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
     const Voice& v = e->voices[voice];
     const long Ls = 960L * n;
-    CBX_REQUIRE(m >= 0 && m <= Ls, "s3gen: cache_source longer than the generated source");
+    CBX_REQUIRE(m >= 0, "s3gen: negative cache_source length");
+    // upstream raises a shape error when the cache is longer than the new source (it can happen when an SOS id inside the
+    // accumulated tokens makes drop_invalid_tokens shorten the sequence); here the cache is clipped to the new length
+    if (m > Ls) m = Ls;
     flow_stage(e, L, v, tokens_h, n, L.st);
     const bool direct = phase_h || noise_d || prof_enabled();
     if (direct) {

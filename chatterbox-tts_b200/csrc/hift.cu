@@ -119,7 +119,8 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
     HiftModel& h = e->hift;
     CBX_REQUIRE(Tg >= 1 && Tg <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
     const long Ls = (long)Tg * H_UP, F = 120L * Tg + 1;
-    CBX_REQUIRE(m >= 0 && m <= Ls, "hift: cache_source longer than the generated source");
+    CBX_REQUIRE(m >= 0, "hift: negative cache_source length");
+    if (m > Ls) m = Ls;
     const long tlen[4] = {Tg, 8L * Tg, 40L * Tg, F};
     auto zero_tail = [&](bf16* buf, long T, int C) { CBX_CHECK(cudaMemsetAsync(buf + (H_HALO + T) * C, 0, (size_t)H_HALO * C * 2, st)); };
     zero_tail(L.h_stft, F, H_NSRC_PAD);

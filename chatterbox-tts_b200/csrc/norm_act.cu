@@ -5,45 +5,48 @@
 
 namespace {
 
-// one warp per row, the row cached in registers (C <= 32 * NORM_MAX_PER_LANE): one global read, two-pass statistics
-constexpr int NORM_MAX_PER_LANE = 32;
-__global__ void norm_kernel(NormParams p) {
+// One warp per row, the row cached in registers as float4 (C = 128 * V4).  Templated on the row width and the fused
+// activation: the generic version (runtime width, per-element activation switch) was 35% of an S3Gen call.
+template <int V4, int ACT>
+__global__ void __launch_bounds__(256) norm_kernel(NormParams p) {
     pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const long total = (long)p.rows * p.batch;
     if (warp >= total) return;
     const int b = warp / p.rows, r = warp % p.rows;
     const float* x = p.in + (long)b * p.in_bs + (long)r * p.ld_in;
-    float xv[NORM_MAX_PER_LANE];
+    constexpr int C = 128 * V4;
+    float4 v[V4];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_PER_LANE; i++) {
-        int c = lane + 32 * i;
-        xv[i] = c < p.C ? x[c] : 0.f;
-        s += xv[i];
+    for (int i = 0; i < V4; i++) {
+        v[i] = *reinterpret_cast<const float4*>(x + (i * 32 + lane) * 4);
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
-    const float mean = p.rms ? 0.f : warp_sum(s) / p.C;
-    float v = 0.f;
+    const float mean = p.rms ? 0.f : warp_sum(s) * (1.f / C);
+    float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_PER_LANE; i++) {
-        int c = lane + 32 * i;
-        float d = c < p.C ? xv[i] - mean : 0.f;
-        v += d * d;
+    for (int i = 0; i < V4; i++) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     }
-    const float rstd = rsqrtf(warp_sum(v) / p.C + p.eps);
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + p.eps);
     const float* add = p.add ? p.add + (long)b * p.add_bs : nullptr;
 #pragma unroll
-    for (int i = 0; i < NORM_MAX_PER_LANE; i++) {
-        int c = lane + 32 * i;
-        if (c < p.C) {
-            float y = (xv[i] - mean) * rstd * p.gain[c];
-            if (p.bias) y += p.bias[c];
-            y = act_apply(p.act, y, 0.f);
-            if (add) y += add[c];
-            y *= p.out_scale;
-            if (p.outF) p.outF[(long)b * p.outF_bs + (long)r * p.ld_outF + c] = y;
-            if (p.outB) p.outB[(long)b * p.outB_bs + (long)r * p.ld_outB + c] = __float2bfloat16(y);
+    for (int i = 0; i < V4; i++) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(p.gain + c);
+        float y[4] = {v[i].x * rstd * g.x, v[i].y * rstd * g.y, v[i].z * rstd * g.z, v[i].w * rstd * g.w};
+        if (p.bias) { const float4 bb = *reinterpret_cast<const float4*>(p.bias + c); y[0] += bb.x; y[1] += bb.y; y[2] += bb.z; y[3] += bb.w; }
+        if (ACT == ACT_MISH) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float sp = y[j] > 20.f ? y[j] : log1pf(expf(y[j])); y[j] = y[j] * tanhf(sp); }
         }
+        if (add) { const float4 aa = *reinterpret_cast<const float4*>(add + c); y[0] += aa.x; y[1] += aa.y; y[2] += aa.z; y[3] += aa.w; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) y[j] *= p.out_scale;
+        if (p.outF) *reinterpret_cast<float4*>(p.outF + (long)b * p.outF_bs + (long)r * p.ld_outF + c) = make_float4(y[0], y[1], y[2], y[3]);
+        if (p.outB) *reinterpret_cast<uint2*>(p.outB + (long)b * p.outB_bs + (long)r * p.ld_outB + c) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
     }
 }
 
@@ -142,10 +145,16 @@ static inline dim3 g1(long n, int t = 256) { return dim3((unsigned)((n + t - 1) 
 void launch_norm(const NormParams& p, cudaStream_t st) {
     long warps = (long)p.rows * p.batch;
     if (warps == 0) return;
-    CBX_REQUIRE(p.C <= 32 * NORM_MAX_PER_LANE, "norm: row too wide for the register tile");
+    CBX_REQUIRE(p.C == 256 || p.C == 512 || p.C == 1024, "norm: row width must be 256, 512 or 1024");
+    CBX_REQUIRE(p.act == ACT_NONE || p.act == ACT_MISH, "norm: only Mish is fused");
+    CBX_REQUIRE(p.ld_in % 4 == 0 && p.in_bs % 4 == 0 && p.ld_outF % 4 == 0 && p.outF_bs % 4 == 0 && p.ld_outB % 4 == 0 && p.outB_bs % 4 == 0 && p.add_bs % 4 == 0,
+                "norm: rows must be 16-byte aligned");
     ProfScope ps(PC_NORM, (double)warps * p.C * 6, st);
-    launch_pdl(norm_kernel, g1(warps * 32, 256), dim3(256), 0, st, p);
-    CBX_CHECK(cudaGetLastError());
+    const dim3 grid = g1(warps * 32, 256), block(256);
+    const bool mish = p.act == ACT_MISH;
+#define CBX_NORM(V4) (mish ? launch_pdl(norm_kernel<V4, ACT_MISH>, grid, block, 0, st, p) : launch_pdl(norm_kernel<V4, ACT_NONE>, grid, block, 0, st, p))
+    if (p.C == 256) CBX_NORM(2); else if (p.C == 512) CBX_NORM(4); else CBX_NORM(8);
+#undef CBX_NORM
 }
 void launch_gather_rows_bf16(const float* table, const int* idx, int n, int C, bf16* out, long ld, cudaStream_t st) {
     launch_pdl(gather_rows_bf16_kernel, dim3(g1((long)n * C)), dim3(256), 0, st, table, idx, n, C, out, ld);

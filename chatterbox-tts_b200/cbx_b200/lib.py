@@ -44,6 +44,7 @@ SIGNATURES = {
     "cbx_gemm_tc_launches": (C.c_longlong, []),
     "cbx_gemm_tc_trace": (_I, [_P]),
     "cbx_t3_mega_trace": (_I, [_P]),
+    "cbx_t3_mega_prof": (_I, [_P]),
     "cbx_profile_begin": (_I, []),
     "cbx_profile_end": (_I, [_P, _P, _P, _I]),
     "cbx_op_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),

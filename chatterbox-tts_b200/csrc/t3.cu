@@ -83,18 +83,20 @@ void t3_alloc(cbx_engine* e) {
     m.slot_pages.assign(S, {});
     m.slot_maxnew.assign(S, 0);
     t3_kernels_init();
-    m.xa = e->scratch<float>((long)R * T3_D); m.xb = e->scratch<float>((long)R * T3_D);
-    m.opart = e->scratch<float>(4L * R * T3_D); m.dpart = e->scratch<float>(4L * R * T3_D);
-    m.apart = e->scratch<float>((long)R * T3_H * 8 * 66);
-    m.bar = e->scratch<unsigned int>(4);
+    for (int i = 0; i < 6; i++) m.ll[i] = e->scratch<unsigned long long>((long)t3_mega_ll_words(i));
+    m.epoch = e->scratch<unsigned int>(4);
+    const unsigned int one = 1;
+    CBX_CHECK(cudaMemcpy(m.epoch, &one, 4, cudaMemcpyHostToDevice));
     m.d_layers = e->scratch<MegaLayer>(c.t3_layers);
     std::vector<MegaLayer> hl(c.t3_layers);
     for (int i = 0; i < c.t3_layers; i++) hl[i] = MegaLayer{m.layers[i].wqkv_f, m.layers[i].wo_f, m.layers[i].wgu_f, m.layers[i].wd_f, m.layers[i].ln1, m.layers[i].ln2};
     CBX_CHECK(cudaMemcpy(m.d_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
-    // The persistent megakernel owns all 148 SMs for a whole step, which blocks the S3Gen kernels that otherwise overlap
-    // with T3 on other streams (measured: 5.44 s vs 4.49 s per 200-word paragraph), so it is opt-in (CBX_T3_MEGA=1).
+    // CBX_T3_MEGA=1 runs the decode step as one persistent kernel (t3_mega.cu): 0.57 ms instead of 0.95 ms per step for one
+    // stream.  It is opt-in because a cooperative grid owns all SMs for the whole step, so the S3Gen kernels that otherwise
+    // share the GPU with T3 on other streams have to wait: measured on the pipelined 200-word paragraph 3.64 s vs 3.17 s, and
+    // with 16 rows the per-projection GEMV kernels are faster (1.55 ms vs 2.35 ms).  See DESIGN.md section 6.
     const char* en = getenv("CBX_T3_MEGA");
-    m.mega = (en && en[0] == '1') && t3_mega_init(c.max_seq);
+    m.mega = (en && en[0] == '1') && t3_mega_init(m.max_pages, hl, m.head_f, T3_VPAD / 16);
 }
 
 static void gemm_lin(const Lin& l, const bf16* A, long lda, int M, float* outF, bf16* outB, long ldc, cudaStream_t st,
@@ -226,11 +228,11 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
     if (m.mega) {   // whole step = one persistent cooperative kernel + the sampler
         MegaParams p;
         p.layers = m.d_layers; p.n_layers = e->cfg.t3_layers; p.head_f = m.head_f; p.head_items = T3_VPAD / 16; p.vocab = T3_V; p.final_norm = m.final_norm;
-        p.x = m.x; p.xa = m.xa; p.xb = m.xb; p.qkv = m.qkv; p.attn = m.attn; p.act = m.act; p.opart = m.opart; p.dpart = m.dpart; p.apart = m.apart; p.logits = m.logits;
-        p.ld_logits = T3_VPAD; p.kv = m.kv; p.kv_layer_stride = m.kv_layer_stride; p.kv_half = m.kv_half; p.page_table = m.page_table; p.max_pages = m.max_pages;
-        p.slot_pos = m.slot_pos; p.row_map = m.d_rowmap; p.inv_freq = m.inv_freq; p.rows = rows; p.rows_total = 2 * e->cfg.max_streams; p.max_seq = e->cfg.max_seq;
-        p.bar = m.bar;
-        launch_t3_mega(p, e->cfg.max_seq, st);
+        p.x = m.x; p.logits = m.logits; p.ld_logits = T3_VPAD;
+        p.ll_qkv = m.ll[0]; p.ll_ap = m.ll[1]; p.ll_y = m.ll[2]; p.ll_act = m.ll[3]; p.ll_z = m.ll[4]; p.cnt = reinterpret_cast<unsigned int*>(m.ll[5]); p.epoch = m.epoch;
+        p.kv = m.kv; p.kv_layer_stride = m.kv_layer_stride; p.kv_half = m.kv_half; p.page_table = m.page_table; p.max_pages = m.max_pages;
+        p.slot_pos = m.slot_pos; p.row_map = m.d_rowmap; p.inv_freq = m.inv_freq; p.rows = rows;
+        launch_t3_mega(p, st);
         enqueue_sampler(e, n, noise, st);
         return;
     }

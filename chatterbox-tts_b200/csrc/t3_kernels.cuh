@@ -1,5 +1,6 @@
 // Parameter blocks for the T3 kernels (t3_kernels.cu).
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 enum GemvEpi { GEMV_STORE = 0, GEMV_RESID = 1, GEMV_GLU = 2 };
@@ -79,14 +80,17 @@ struct MegaParams {
     const MegaLayer* layers = nullptr; int n_layers = 0;
     const bf16* head_f = nullptr; int head_items = 0; int vocab = 0; const float* final_norm = nullptr; float eps = 1e-5f;
     const float* x = nullptr;            // [rows_total][1024] step input (written by the sampler / slot init)
-    float *xa = nullptr, *xb = nullptr;  // residual stream double buffer
-    float *qkv = nullptr, *attn = nullptr, *act = nullptr, *opart = nullptr, *dpart = nullptr, *logits = nullptr; long ld_logits = 0;
-    float* apart = nullptr;              // attention split partials [rows_total*16][8][66] = {max, sum, o[64]}
+    float* logits = nullptr; long ld_logits = 0;
+    // flagged-word exchange areas (8-byte words {payload, tag}), double-buffered by layer parity, indexed by compact row
+    unsigned long long *ll_qkv = nullptr, *ll_ap = nullptr, *ll_y = nullptr, *ll_act = nullptr, *ll_z = nullptr;
+    unsigned int* cnt = nullptr;         // arrival counters [layers][32] (zeroed before every step)
+    unsigned int* epoch = nullptr;       // tag base of the next step (device counter, advanced by the kernel)
     bf16* kv = nullptr; long kv_layer_stride = 0, kv_half = 0;
     const int* page_table = nullptr; int max_pages = 0; const int* slot_pos = nullptr; const int* row_map = nullptr;
     const float* inv_freq = nullptr;
-    int rows = 0, rows_total = 0, max_seq = 0;
-    unsigned int* bar = nullptr;
+    int rows = 0;
+    const unsigned long long* sched = nullptr; const int* sched_count = nullptr; int l2_ahead = 0;   // filled by launch_t3_mega
 };
-bool t3_mega_init(int max_seq);
-void launch_t3_mega(const MegaParams& p, int max_seq, cudaStream_t st);
+bool t3_mega_init(int max_pages, const std::vector<MegaLayer>& layers, const bf16* head_f, int head_items);
+size_t t3_mega_ll_words(int which);   // 0 qkv, 1 attention partials, 2 y, 3 act, 4 z, 5 arrival counters
+void launch_t3_mega(const MegaParams& p, cudaStream_t st);

@@ -111,6 +111,9 @@ long long cbx_gemm_tc_launches(void);
 int cbx_gemm_tc_trace(unsigned long long* out_h);
 /* debug: %globaltimer stamps (ns) of CTA 0 through the five phases of layer 1 of the last T3 megakernel step */
 int cbx_t3_mega_trace(unsigned long long* out_h);
+/* debug: per CTA (256 x 4 int64) SM cycles thread 0 spent waiting for weight slots, waiting for arrival counters, and in total
+ * during the last T3 megakernel step */
+int cbx_t3_mega_prof(long long* out_h);
 
 /* per-launch profiler for bench.py's roofline pass: between begin and end every kernel launch is bracketed by
  * CUDA events on its stream (T3 steps run un-graphed); end() returns, per kernel class (0 gemm, 1 attention,

@@ -15,6 +15,7 @@ from cbx_b200.weights import random_state_dict, synthetic_conditionals
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     cfg = ModelConfig()
     eng = NativeEngine(cfg, max_streams=8, n_lanes=1)
     eng.load_state_dict(random_state_dict(cfg, 0))
@@ -40,15 +41,21 @@ def main():
         wbytes = 30 * 16779264 * 2 + 8208 * 1024 * 2
         kvbytes = 122880 * pos * 2 * ns
         import ctypes as C
-        tr = (C.c_ulonglong * 16)()
+        tr = (C.c_ulonglong * 32)()
         eng.lib.cbx_t3_mega_trace(tr)
-        names = ["P1 stage", "P1 items", "bar", "P2 attn", "bar", "P3 stage", "P3 items", "bar", "P4 stage", "P4 items", "bar", "P5 items", "bar"]
-        trace = {f"{i:02d} {names[i]}": int(tr[i + 1]) - int(tr[i]) for i in range(13)}
-        out[f"t3_streams{ns}"] = {"layer1_phase_ns": trace, "ms_per_step": ms, "tok_s": ns * 1e3 / ms, "audio_s_per_s": ns * 1e3 / ms / 25, "prefill_ms": prefill_ms,
+        names = ["P1 wait z + norm", "P1 qkv items", "P2 attention", "P3 o-proj", "P4 wait y", "P4 norm + gate/up", "P5 down"]
+        trace = {f"{i:02d} {names[i]}": int(tr[i + 1]) - int(tr[i]) for i in range(7)}
+        trace["detail_rel_to_P1_start"] = {k: int(tr[i]) - int(tr[0]) for k, i in (("z added", 16), ("norm done", 1), ("qkv done", 2), ("att polled", 8), ("att sync1", 9), ("att rope", 10), ("att loop", 11),
+                                                                                   ("att reduce", 12), ("att sync3", 13), ("att done", 3), ("oproj staged", 14), ("oproj done", 4), ("y added", 5),
+                                                                                   ("gu done", 6), ("act staged", 15), ("down done", 7))}
+        pr = (C.c_longlong * 1024)()
+        eng.lib.cbx_t3_mega_prof(pr)
+        prof = [(int(pr[4 * i]), int(pr[4 * i + 1]), int(pr[4 * i + 2])) for i in range(148)]
+        out[f"t3_streams{ns}"] = {"prof_cycles_mbar_cnt_total": prof, "layer1_phase_ns": trace, "ms_per_step": ms, "tok_s": ns * 1e3 / ms, "audio_s_per_s": ns * 1e3 / ms / 25, "prefill_ms": prefill_ms,
                                   "hbm_gbs": (wbytes + kvbytes) / (ms * 1e-3) / 1e9}
         for s in slots:
             eng.t3_close(s)
-    for n in (35, 70, 140, 245):
+    for n in (() if only == "t3" else (35, 70, 140, 245)):
         toks = [(i * 37) % 6561 for i in range(n)]
         for _ in range(2):
             eng.s3gen_infer(v, toks, seed=1)

@@ -14,6 +14,12 @@ class CbxConfig(C.Structure):
                 ("n_voices", C.c_int), ("n_lanes", C.c_int)]
 
 
+class S3GenCall(C.Structure):
+    """cbx_s3gen_call of include/cbx_b200.h"""
+    _fields_ = [("voice", C.c_int), ("tokens_h", C.c_void_p), ("n", C.c_int), ("cache_source_d", C.c_void_p), ("m", C.c_int64),
+                ("wav_out_d", C.c_void_p), ("source_out_d", C.c_void_p), ("mel_out_d", C.c_void_p), ("seed", C.c_uint64)]
+
+
 # every exported symbol of include/cbx_b200.h: name -> (restype, argtypes)
 _P, _I, _F, _L, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 SIGNATURES = {
@@ -35,6 +41,7 @@ SIGNATURES = {
     "cbx_t3_logits": (_I, [_P, _I, _P, _P]),
     "cbx_t3_close": (_I, [_P, _I]),
     "cbx_s3gen_infer": (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P, _P, _U64, _P]),
+    "cbx_s3gen_infer_batch": (_I, [_P, C.POINTER(S3GenCall), _I, _P]),
     "cbx_flow_infer": (_I, [_P, _I, _P, _I, _P, _P]),
     "cbx_hift_infer": (_I, [_P, _P, _I, _P, _L, _P, _P, _P, _P, _U64, _P]),
     "cbx_hift_f0": (_I, [_P, _P, _I, _P, _P]),

@@ -154,6 +154,27 @@ class NativeEngine:
                                          C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, _stream_ptr()))
         return (wav, src, mel) if return_mel else (wav, src)
 
+    def s3gen_infer_batch(self, calls, return_mel=False):
+        """calls: list of (voice, tokens, cache_source or None, seed) -> list of (wav, source[, mel]); one batched
+        token->mel pass for all calls (cbx_s3gen_infer_batch), results equal s3gen_infer call by call."""
+        dev = torch.device("cuda", self.device)
+        arr = (L.S3GenCall * len(calls))()
+        keep, outs = [], []
+        for i, (voice, tokens, cache_source, seed) in enumerate(calls):
+            tok = _i32(tokens).reshape(-1)
+            n = len(tok)
+            wav = torch.empty(1, 960 * n, device=dev, dtype=torch.float32)
+            src = torch.empty(1, 1, 960 * n, device=dev, dtype=torch.float32)
+            mel = torch.empty(2 * n, 80, device=dev, dtype=torch.float32) if return_mel else None
+            m = 0 if cache_source is None else cache_source.shape[-1]
+            cs = cache_source.contiguous() if m else None
+            keep.append((tok, cs))
+            arr[i] = L.S3GenCall(voice, tok.ctypes.data, n, cs.data_ptr() if m else None, m, wav.data_ptr(), src.data_ptr(),
+                                 mel.data_ptr() if return_mel else None, seed)
+            outs.append((wav, src, mel) if return_mel else (wav, src))
+        L.check(self.lib.cbx_s3gen_infer_batch(self.h, arr, len(calls), _stream_ptr()))
+        return outs
+
     def flow_infer(self, voice, tokens):
         tok = _i32(tokens).reshape(-1)
         mel = torch.empty(2 * len(tok), 80, device=torch.device("cuda", self.device), dtype=torch.float32)

@@ -35,19 +35,22 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
     const int g = lane >> 2, tg = lane & 3;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * BQ;
+    const int klen_raw = p.kv_len[(b / p.kv_div) & 7];
+    const int Tk = klen_raw > 0 ? klen_raw : p.T;   // valid keys (and valid queries) of this sequence
+    if (q0 >= Tk) return;                           // padded query tile: its rows are never consumed
     const bf16* Q = p.q + (long)b * p.q_bs + h * D;
     const bf16* K = p.k + (long)b * p.k_bs + h * D;
     const bf16* V = p.v + (long)b * p.v_bs + h * D;
     const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sK + KVS * STAGE_BYTES;
 
-    int n_stages = (p.T + BKV - 1) / BKV;
-    if (p.causal) n_stages = (min(p.T, q0 + BQ) + BKV - 1) / BKV;
+    int n_stages = (Tk + BKV - 1) / BKV;
+    if (p.causal) n_stages = (min(Tk, q0 + BQ) + BKV - 1) / BKV;
     load_rows<64>(sQ, Q, p.ldq, q0, p.T, tid);
 #pragma unroll
     for (int s = 0; s < KVS - 1; s++) {
         if (s < n_stages) {
-            load_rows<128>(sK + s * STAGE_BYTES, K, p.ldk, s * BKV, p.T, tid);
-            load_rows<128>(sV + s * STAGE_BYTES, V, p.ldv, s * BKV, p.T, tid);
+            load_rows<128>(sK + s * STAGE_BYTES, K, p.ldk, s * BKV, Tk, tid);
+            load_rows<128>(sV + s * STAGE_BYTES, V, p.ldv, s * BKV, Tk, tid);
         }
         cp_async_commit();
     }
@@ -67,8 +70,8 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
         {
             const int nk = st + KVS - 1;
             if (nk < n_stages) {
-                load_rows<128>(sK + (nk % KVS) * STAGE_BYTES, K, p.ldk, nk * BKV, p.T, tid);
-                load_rows<128>(sV + (nk % KVS) * STAGE_BYTES, V, p.ldv, nk * BKV, p.T, tid);
+                load_rows<128>(sK + (nk % KVS) * STAGE_BYTES, K, p.ldk, nk * BKV, Tk, tid);
+                load_rows<128>(sV + (nk % KVS) * STAGE_BYTES, V, p.ldv, nk * BKV, Tk, tid);
             }
             cp_async_commit();
         }
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
             for (int ks = 0; ks < 4; ks++) ldmatrix_x4(qf[ks], sQ + swz128(qw * 16 + (lane & 15), ks * 2 + (lane >> 4)));
         }
         const int kbase = st * BKV + kvh * 64;
-        const bool live = kbase < p.T && !(p.causal && kbase > q0 + qw * 16 + 15);   // warp-uniform: any key of this half visible?
+        const bool live = kbase < Tk && !(p.causal && kbase > q0 + qw * 16 + 15);   // warp-uniform: any key of this half visible?
         if (live) {
             const uint32_t sk = sK + buf * STAGE_BYTES + kvh * TILE_BYTES, sv = sV + buf * STAGE_BYTES + kvh * TILE_BYTES;
             float s[8][4];
@@ -105,10 +108,10 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
                     int kj = kbase + j * 8 + tg * 2 + (r & 1);
                     int qi = (r < 2) ? qi0 : qi1;
                     float v = s[j][r];
-                    if (p.relbias && kj < p.T && qi < p.T)
-                        v += p.relbias[(long)h * p.rb_hs + (long)qi * p.rb_ld + (p.T - 1 - qi + kj)];
+                    if (p.relbias && kj < Tk && qi < p.T)
+                        v += p.relbias[(long)b * p.rb_bs + (long)h * p.rb_hs + (long)qi * p.rb_ld + (p.T - 1 - qi + kj)];
                     v *= sl2;
-                    if (kj >= p.T || (p.causal && kj > qi)) v = -INFINITY;
+                    if (kj >= Tk || (p.causal && kj > qi)) v = -INFINITY;
                     s[j][r] = v;
                 }
             }

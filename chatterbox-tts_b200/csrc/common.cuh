@@ -190,7 +190,10 @@ struct AttnParams {
     const bf16 *q = nullptr, *k = nullptr, *v = nullptr; long ldq = 0, ldk = 0, ldv = 0; long q_bs = 0, k_bs = 0, v_bs = 0;
     bf16* o = nullptr; long ldo = 0; long o_bs = 0;
     int T = 0, H = 0, batch = 1; int causal = 0; float scale = 0.125f;
-    const float* relbias = nullptr; long rb_ld = 0; long rb_hs = 0;  // bias[h*rb_hs + i*rb_ld + (T-1-i+j)]
+    const float* relbias = nullptr; long rb_ld = 0; long rb_hs = 0; long rb_bs = 0;  // bias[b*rb_bs + h*rb_hs + i*rb_ld + (T-1-i+j)]
+    // ragged batches (sequences right-padded to T): keys >= kv_len[b / kv_div] are masked and query tiles beyond it are
+    // skipped; 0 = the full T
+    int kv_len[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int kv_div = 1;
 };
 void launch_attention(const AttnParams& p, cudaStream_t st);
 void attention_init();

@@ -95,7 +95,8 @@ int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
         v.prompt_feat = e->scratch<float>(2L * cfg->max_prompt_tokens * MEL);
         v.spks = e->scratch<float>(MEL);
     }
-    for (int i = 0; i < cfg->n_lanes; i++) { Lane* L = new Lane(); lane_alloc(e, *L); e->lanes.push_back(L); }
+    for (int i = 0; i < cfg->n_lanes; i++) { Lane* L = new Lane(); lane_alloc(e, *L, 1); e->lanes.push_back(L); }
+    e->batch_lane = new Lane(); lane_alloc(e, *e->batch_lane, FLOW_MAXB);
     CBX_CHECK(cudaDeviceSynchronize());
     *out = e;
     CBX_API_END
@@ -119,6 +120,7 @@ void cbx_engine_destroy(cbx_engine* e) {
     for (auto& kv : e->t3.step_graphs) cudaGraphExecDestroy(kv.second);
     for (auto& t : e->tensors) cudaFree(t.ptr);
     for (void* p : e->scratch_allocs) cudaFree(p);
+    if (e->batch_lane) e->lanes.push_back(e->batch_lane);
     for (Lane* L : e->lanes) { for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second); cudaFreeHost(L->g_dyn_h); cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
     cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
     delete e;
@@ -334,11 +336,14 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
     // upstream raises a shape error when the cache is longer than the new source (it can happen when an SOS id inside the
     // accumulated tokens makes drop_invalid_tokens shorten the sequence); here the cache is clipped to the new length
     if (m > Ls) m = Ls;
-    flow_stage(e, L, v, tokens_h, n, L.st);
+    L.nb = 1; L.call[0].v = &v; L.call[0].n = n;
+    const int* toks[1] = {tokens_h};
+    flow_stage(e, L, toks, L.st);
     const bool direct = phase_h || noise_d || prof_enabled();
     if (direct) {
         // explicit SineGen randomness (parity tests) or per-launch profiling: plain launches
-        flow_run(e, L, v, n, L.st);
+        flow_run(e, L, L.st);
+        CBX_CHECK(cudaMemcpyAsync(L.mel, L.melb, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
         hift_infer(e, L, 2 * n, cache_source_d, m, wav_out_d, source_out_d, phase_h, noise_d, seed, L.st);
     } else {
         // steady state: the whole device-side call (~5k launches) is one CUDA graph per (voice, prompt, n) shape
@@ -353,7 +358,8 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
             cudaGraph_t graph;
             CBX_CHECK(cudaStreamBeginCapture(L.st, cudaStreamCaptureModeThreadLocal));
             try {
-                flow_run(e, L, v, n, L.st);
+                flow_run(e, L, L.st);
+                CBX_CHECK(cudaMemcpyAsync(L.mel, L.melb, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
                 hift_infer(e, L, 2 * n, L.g_cache, 0, L.g_wav, L.g_src, nullptr, nullptr, 0, L.st, L.g_dyn);
             } catch (...) {
                 cudaGraph_t junk; cudaStreamEndCapture(L.st, &junk);
@@ -374,6 +380,39 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
         CBX_CHECK(cudaMemcpyAsync(source_out_d, L.g_src, (size_t)Ls * 4, cudaMemcpyDeviceToDevice, L.st));
     }
     if (mel_out_d) CBX_CHECK(cudaMemcpyAsync(mel_out_d, L.mel, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    br.finish();
+    CBX_API_END
+}
+
+int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_calls, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && calls && n_calls >= 1 && n_calls <= FLOW_MAXB, "s3gen batch: between 1 and 8 calls");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = *e->batch_lane;
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    const int* toks[FLOW_MAXB];
+    L.nb = n_calls;
+    for (int b = 0; b < n_calls; b++) {
+        const cbx_s3gen_call& c = calls[b];
+        CBX_REQUIRE(c.tokens_h && c.wav_out_d && c.source_out_d, "s3gen batch: null pointer in call");
+        CBX_REQUIRE(c.voice >= 0 && c.voice < e->cfg.n_voices && e->voices[c.voice].valid, "voice slot is empty");
+        CBX_REQUIRE(c.n >= 3, "s3gen: needs at least 3 tokens (reference pads, src/tts_streaming.py:675-677)");
+        CBX_REQUIRE(c.m >= 0, "s3gen: negative cache_source length");
+        L.call[b].v = &e->voices[c.voice]; L.call[b].n = c.n; toks[b] = c.tokens_h;
+    }
+    flow_stage(e, L, toks, L.st);
+    // the token -> mel part (encoder + 10 CFM steps, ~95 % of the launches) runs once for the whole batch: every GEMM /
+    // norm / attention launch covers all calls, so the per-launch latency that bounds a single call is shared
+    flow_run(e, L, L.st);
+    const long mel_bs = 2L * e->cfg.max_s3_tokens * MEL;
+    for (int b = 0; b < n_calls; b++) {   // the vocoder runs per call (different lengths, source caches and seeds)
+        const cbx_s3gen_call& c = calls[b];
+        const long Ls = 960L * c.n;
+        CBX_CHECK(cudaMemcpyAsync(L.mel, L.melb + b * mel_bs, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+        hift_infer(e, L, 2 * c.n, c.cache_source_d, c.m > Ls ? Ls : c.m, c.wav_out_d, c.source_out_d, nullptr, nullptr, c.seed, L.st);
+        if (c.mel_out_d) CBX_CHECK(cudaMemcpyAsync(c.mel_out_d, L.mel, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    }
     br.finish();
     CBX_API_END
 }

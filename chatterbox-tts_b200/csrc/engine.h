@@ -75,8 +75,13 @@ struct Voice {
     int n_prompt = 0, n_feat = 0; int* prompt_token = nullptr; float* prompt_feat = nullptr; float* spks = nullptr;
 };
 
-struct Lane {   // S3Gen workspace (one call at a time)
+struct FlowCall { const Voice* v = nullptr; int n = 0; int Tt = 0; };   // one S3Gen call of a batch: voice, new tokens, prompt + new tokens
+constexpr int FLOW_MAXB = 8;
+
+struct Lane {   // S3Gen workspace: one batch of up to `bmax` calls at a time
     std::mutex lock; cudaStream_t st; cudaEvent_t ev_in, ev_out;
+    int bmax = 1, nb = 1, Ttm = 0; FlowCall call[FLOW_MAXB];   // current batch; sequences are right-padded to Ttm tokens
+    float* melb = nullptr;   // [bmax][2*max_s3_tokens][80] CFM output per call
     // encoder
     int* tok; bf16 *e_in, *e_xb, *e_y1, *e_xn, *e_qkv, *e_pos, *e_p, *e_o, *e_ff, *e_up, *e_upc; float *e_tmp, *e_x, *e_bd;
     // cfm
@@ -100,6 +105,7 @@ struct cbx_engine {
     std::vector<Voice> voices; std::mutex voice_mu;
     std::mutex t3_mu; cudaStream_t t3_st; cudaEvent_t t3_ev_in, t3_ev_out;
     std::vector<Lane*> lanes; std::mutex lane_pick_mu; int lane_rr = 0;
+    Lane* batch_lane = nullptr;   // workspace of cbx_s3gen_infer_batch (FLOW_MAXB calls)
     long gpu_launches = 0;
 
     template <typename T> T* reg(const std::string& name, int dtype, long numel);
@@ -118,17 +124,17 @@ void t3_close(cbx_engine* e, int slot);
 
 void flow_build(cbx_engine* e);
 void flow_finalize(cbx_engine* e, cudaStream_t st);
-void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st);   // -> L.mel [2n][80]
+void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st);   // single call -> L.mel [2n][80]
 
 void hift_build(cbx_engine* e);
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr);
-void flow_stage(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st);
-void flow_run(cbx_engine* e, Lane& L, const Voice& v, int n, cudaStream_t st);
+void flow_stage(cbx_engine* e, Lane& L, const int* const* tokens_h, cudaStream_t st);   // L.nb / L.call[] set by the caller
+void flow_run(cbx_engine* e, Lane& L, cudaStream_t st);                                  // -> L.melb
 void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st);
 void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* cache_src_dev, long m, float* src_out,
                  const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr);
-void lane_alloc(cbx_engine* e, Lane& L);
+void lane_alloc(cbx_engine* e, Lane& L, int bmax);
 
 template <typename T> T* cbx_engine::reg(const std::string& name, int dtype, long numel) {
     CBX_REQUIRE(index.find(name) == index.end(), "duplicate tensor " + name);

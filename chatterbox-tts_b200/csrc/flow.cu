@@ -1,6 +1,7 @@
 // S3Gen token->mel: UpsampleConformerEncoder + CausalConditionalCFM (10 Euler steps, CFG-batched
 // ConditionalDecoder).  Activations are time-major channels-last; every conv is an implicit GEMM over
 // zero-haloed bf16 buffers; residual streams stay fp32.  Host orchestration only.
+#include <algorithm>
 #include <cmath>
 #include "engine.h"
 
@@ -104,25 +105,33 @@ void flow_finalize(cbx_engine* e, cudaStream_t st) {
 }
 
 static constexpr int CH = 2;   // causal halo rows (k=3)
+static constexpr int EP = 8;   // pad rows per sequence slab of the encoder conv inputs (look-ahead 3 / left pads 2, 4)
 
-void lane_alloc(cbx_engine* e, Lane& L) {
+// A lane runs `nb` calls at once (nb = 1: the classic single call).  Sequences are right-padded to the longest one:
+// Ttm tokens / T = 2*Ttm frames.  Padding is exact: the estimator's convolutions are causal, LayerNorm / linears are
+// per frame, attention masks keys beyond each sequence's length, and the one look-ahead conv of the encoder reads
+// rows that are explicitly zeroed behind each sequence (the reference right-pads with zeros).
+void lane_alloc(cbx_engine* e, Lane& L, int bmax) {
     const cbx_config& c = e->cfg;
+    const long B = bmax;
+    L.bmax = bmax;
     const long Tt = c.max_prompt_tokens + c.max_s3_tokens, T = 2 * Tt, Tg = 2L * c.max_s3_tokens;
     CBX_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     CBX_CHECK(cudaEventCreateWithFlags(&L.ev_in, cudaEventDisableTiming));
     CBX_CHECK(cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
-    L.tok = e->scratch<int>(Tt);
-    L.e_in = e->scratch<bf16>(T * F_D); L.e_xb = e->scratch<bf16>((T + 8) * F_D); L.e_y1 = e->scratch<bf16>((T + 8) * F_D);
-    L.e_xn = e->scratch<bf16>(T * F_D); L.e_qkv = e->scratch<bf16>(T * 4 * F_D); L.e_pos = e->scratch<bf16>(2 * T * F_D); L.e_p = e->scratch<bf16>(2 * T * F_D);
-    L.e_o = e->scratch<bf16>(T * F_D); L.e_ff = e->scratch<bf16>(T * F_FFN); L.e_up = e->scratch<bf16>((T + 8) * F_D); L.e_upc = e->scratch<bf16>(T * F_D);
-    L.e_tmp = e->scratch<float>(T * F_D); L.e_x = e->scratch<float>(T * F_D); L.e_bd = e->scratch<float>((long)F_H * T * 2 * T);
-    L.mu = e->scratch<float>(T * MEL); L.cond = e->scratch<float>(T * MEL); L.x = e->scratch<float>(T * MEL); L.v = e->scratch<float>(2 * T * MEL);
+    L.tok = e->scratch<int>(B * Tt);
+    L.e_in = e->scratch<bf16>(B * T * F_D); L.e_xb = e->scratch<bf16>(B * (T + EP) * F_D); L.e_y1 = e->scratch<bf16>(B * (T + EP) * F_D);
+    L.e_xn = e->scratch<bf16>(B * T * F_D); L.e_qkv = e->scratch<bf16>(B * T * 4 * F_D); L.e_pos = e->scratch<bf16>(2 * T * F_D); L.e_p = e->scratch<bf16>(2 * T * F_D);
+    L.e_o = e->scratch<bf16>(B * T * F_D); L.e_ff = e->scratch<bf16>(B * T * F_FFN); L.e_up = e->scratch<bf16>(B * (T + EP) * F_D); L.e_upc = e->scratch<bf16>(B * T * F_D);
+    L.e_tmp = e->scratch<float>(B * T * F_D); L.e_x = e->scratch<float>(B * T * F_D); L.e_bd = e->scratch<float>(B * F_H * T * 2 * T);
+    L.mu = e->scratch<float>(B * T * MEL); L.cond = e->scratch<float>(B * T * MEL); L.x = e->scratch<float>(B * T * MEL); L.v = e->scratch<float>(2 * B * T * MEL);
     const long TH = T + CH;
-    L.c_in = e->scratch<bf16>(2 * TH * C_IN); L.c_hb = e->scratch<bf16>(2 * TH * C_CH); L.c_inb = e->scratch<bf16>(2 * TH * C_CH);
-    L.c_upin = e->scratch<bf16>(2 * TH * 2 * C_CH); L.c_xn = e->scratch<bf16>(2 * T * C_CH); L.c_qkv = e->scratch<bf16>(2 * T * 3 * C_INNER);
-    L.c_o = e->scratch<bf16>(2 * T * C_INNER); L.c_ff = e->scratch<bf16>(2 * T * C_FF); L.c_fb = e->scratch<bf16>(2 * T * C_CH);
-    L.c_tmp = e->scratch<float>(2 * T * C_CH); L.c_tmp2 = e->scratch<float>(2 * T * C_CH); L.c_h = e->scratch<float>(2 * T * C_CH);
-    // hift
+    L.c_in = e->scratch<bf16>(2 * B * TH * C_IN); L.c_hb = e->scratch<bf16>(2 * B * TH * C_CH); L.c_inb = e->scratch<bf16>(2 * B * TH * C_CH);
+    L.c_upin = e->scratch<bf16>(2 * B * TH * 2 * C_CH); L.c_xn = e->scratch<bf16>(2 * B * T * C_CH); L.c_qkv = e->scratch<bf16>(2 * B * T * 3 * C_INNER);
+    L.c_o = e->scratch<bf16>(2 * B * T * C_INNER); L.c_ff = e->scratch<bf16>(2 * B * T * C_FF); L.c_fb = e->scratch<bf16>(2 * B * T * C_CH);
+    L.c_tmp = e->scratch<float>(2 * B * T * C_CH); L.c_tmp2 = e->scratch<float>(2 * B * T * C_CH); L.c_h = e->scratch<float>(2 * B * T * C_CH);
+    L.melb = e->scratch<float>(B * Tg * MEL);
+    // hift (one call at a time)
     const long HH = H_HALO;
     L.mel = e->scratch<float>(Tg * MEL); L.h_mel = e->scratch<bf16>((Tg + 2 * HH) * MEL);
     L.h_f0a = e->scratch<bf16>((Tg + 2 * HH) * H_F0CH); L.h_f0b = e->scratch<bf16>((Tg + 2 * HH) * H_F0CH);
@@ -143,101 +152,128 @@ void lane_alloc(cbx_engine* e, Lane& L) {
     CBX_CHECK(cudaMallocHost(&L.g_dyn_h, sizeof(SourceDyn)));
 }
 
-// ---------------------------------------------------------------------------------------------- encoder
-static void conformer_layer(cbx_engine* e, Lane& L, const ConformerLayer& l, int T, cudaStream_t st) {
-    NormParams n; n.in = L.e_x; n.ld_in = F_D; n.rows = T; n.C = F_D; n.gain = l.nm.g; n.bias = l.nm.b; n.eps = 1e-12f; n.outB = L.e_xn; n.ld_outB = F_D;
-    launch_norm(n, st);
-    GemmParams g = mk(l.qkv4, L.e_xn, F_D, T, F_D, 0); g.outB = L.e_qkv; g.ldc = 4 * F_D; launch_gemm(g, st);        // [q+u | q+v | k | v]
-    g = mk(l.pos, L.e_pos, F_D, 2 * T - 1, F_D, 0); g.outB = L.e_p; g.ldc = F_D; launch_gemm(g, st);
-    const long ldbd = 2L * T;
-    GemmParams b; b.A = L.e_qkv + F_D; b.lda = 4 * F_D; b.kc = 64; b.a_bs = 64; b.W = L.e_p; b.ldw = F_D; b.w_bs = 64; b.M = T; b.N = 2 * T - 1; b.K = 64;
-    b.batch = F_H; b.outF = L.e_bd; b.ldc = ldbd; b.c_bs = (long)T * ldbd;
-    launch_gemm(b, st);
-    AttnParams a; a.q = L.e_qkv; a.k = L.e_qkv + 2 * F_D; a.v = L.e_qkv + 3 * F_D; a.ldq = a.ldk = a.ldv = 4 * F_D; a.o = L.e_o; a.ldo = F_D;
-    a.T = T; a.H = F_H; a.batch = 1; a.scale = 0.125f; a.relbias = L.e_bd; a.rb_ld = ldbd; a.rb_hs = (long)T * ldbd;
-    launch_attention(a, st);
-    g = mk(l.out, L.e_o, F_D, T, F_D, 0); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
-    n.gain = l.nf.g; n.bias = l.nf.b; launch_norm(n, st);
-    g = mk(l.w1, L.e_xn, F_D, T, F_D, 0); g.act = ACT_SILU; g.outB = L.e_ff; g.ldc = F_FFN; launch_gemm(g, st);
-    g = mk(l.w2, L.e_ff, F_FFN, T, F_FFN, 0); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
-    e->gpu_launches += 9;
+// per-sequence key lengths for the attention kernel (nothing to mask when every sequence fills the padded length)
+static void set_kv_len(AttnParams& a, const Lane& L, int frames_per_token, int div) {
+    bool ragged = false;
+    for (int b = 0; b < L.nb; b++) ragged = ragged || L.call[b].Tt != L.Ttm;
+    a.kv_div = div;
+    if (ragged) for (int b = 0; b < L.nb; b++) a.kv_len[b] = frames_per_token * L.call[b].Tt;
 }
 
-static void embed_stage(cbx_engine* e, Lane& L, const Lin& lin, const LNp& ln, const bf16* in, int T, cudaStream_t st) {
-    GemmParams g = mk(lin, in, F_D, T, F_D, 0); g.outF = L.e_tmp; g.ldc = F_D; launch_gemm(g, st);
-    NormParams n; n.in = L.e_tmp; n.ld_in = F_D; n.rows = T; n.C = F_D; n.gain = ln.g; n.bias = ln.b; n.eps = 1e-5f; n.out_scale = sqrtf((float)F_D);
-    n.outF = L.e_x; n.ld_outF = F_D; n.outB = L.e_xb; n.ld_outB = F_D;
+// ---------------------------------------------------------------------------------------------- encoder
+// rows: padded sequence length at this stage (Ttm before the upsample, 2*Ttm after); all activations are [nb][rows][C]
+static void conformer_layer(cbx_engine* e, Lane& L, const ConformerLayer& l, int rows, int fpt, cudaStream_t st) {
+    const int B = L.nb, M = B * rows;
+    NormParams n; n.in = L.e_x; n.ld_in = F_D; n.rows = M; n.C = F_D; n.gain = l.nm.g; n.bias = l.nm.b; n.eps = 1e-12f; n.outB = L.e_xn; n.ld_outB = F_D;
     launch_norm(n, st);
-    launch_relpos_table(L.e_pos, T, F_D, st);
+    GemmParams g = mk(l.qkv4, L.e_xn, F_D, M, F_D, 0); g.outB = L.e_qkv; g.ldc = 4 * F_D; launch_gemm(g, st);        // [q+u | q+v | k | v]
+    g = mk(l.pos, L.e_pos, F_D, 2 * rows - 1, F_D, 0); g.outB = L.e_p; g.ldc = F_D; launch_gemm(g, st);
+    const long ldbd = 2L * rows, bd_bs = (long)F_H * rows * ldbd;
+    for (int b = 0; b < B; b++) {   // (q+v) P^T per head: the head index is the GEMM batch, so calls are looped
+        GemmParams bd; bd.A = L.e_qkv + (long)b * rows * 4 * F_D + F_D; bd.lda = 4 * F_D; bd.kc = 64; bd.a_bs = 64; bd.W = L.e_p; bd.ldw = F_D; bd.w_bs = 64;
+        bd.M = rows; bd.N = 2 * rows - 1; bd.K = 64; bd.batch = F_H; bd.outF = L.e_bd + b * bd_bs; bd.ldc = ldbd; bd.c_bs = (long)rows * ldbd;
+        launch_gemm(bd, st);
+    }
+    AttnParams a; a.q = L.e_qkv; a.k = L.e_qkv + 2 * F_D; a.v = L.e_qkv + 3 * F_D; a.ldq = a.ldk = a.ldv = 4 * F_D; a.o = L.e_o; a.ldo = F_D;
+    a.q_bs = a.k_bs = a.v_bs = (long)rows * 4 * F_D; a.o_bs = (long)rows * F_D;
+    a.T = rows; a.H = F_H; a.batch = B; a.scale = 0.125f; a.relbias = L.e_bd; a.rb_ld = ldbd; a.rb_hs = (long)rows * ldbd; a.rb_bs = bd_bs;
+    set_kv_len(a, L, fpt, 1);
+    launch_attention(a, st);
+    g = mk(l.out, L.e_o, F_D, M, F_D, 0); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
+    n.gain = l.nf.g; n.bias = l.nf.b; launch_norm(n, st);
+    g = mk(l.w1, L.e_xn, F_D, M, F_D, 0); g.act = ACT_SILU; g.outB = L.e_ff; g.ldc = F_FFN; launch_gemm(g, st);
+    g = mk(l.w2, L.e_ff, F_FFN, M, F_FFN, 0); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
+    e->gpu_launches += 8 + B;
+}
+
+// Linear + LayerNorm + sqrt(d) scale: in [nb][rows][512] (contiguous) -> e_x fp32 (contiguous) and e_xb bf16 slabs of rows+EP
+static void embed_stage(cbx_engine* e, Lane& L, const Lin& lin, const LNp& ln, const bf16* in, int rows, cudaStream_t st) {
+    const int B = L.nb;
+    GemmParams g = mk(lin, in, F_D, B * rows, F_D, 0); g.outF = L.e_tmp; g.ldc = F_D; launch_gemm(g, st);
+    NormParams n; n.in = L.e_tmp; n.ld_in = F_D; n.in_bs = (long)rows * F_D; n.rows = rows; n.batch = B; n.C = F_D; n.gain = ln.g; n.bias = ln.b; n.eps = 1e-5f;
+    n.out_scale = sqrtf((float)F_D);
+    n.outF = L.e_x; n.ld_outF = F_D; n.outF_bs = (long)rows * F_D; n.outB = L.e_xb; n.ld_outB = F_D; n.outB_bs = (long)(rows + EP) * F_D;
+    launch_norm(n, st);
+    launch_relpos_table(L.e_pos, rows, F_D, st);
     e->gpu_launches += 3;
 }
 
-static void encoder(cbx_engine* e, Lane& L, int Tt, cudaStream_t st) {
+static void encoder(cbx_engine* e, Lane& L, cudaStream_t st) {
     FlowModel& f = e->flow;
-    launch_gather_rows_bf16(f.tok_emb, L.tok, Tt, F_D, L.e_in, F_D, st);
+    const int B = L.nb, Tt = L.Ttm, T = 2 * Tt;
+    const long sl1 = (long)(Tt + EP) * F_D, sl2 = (long)(T + EP) * F_D;   // slab strides of the conv inputs
+    launch_gather_rows_bf16(f.tok_emb, L.tok, B * Tt, F_D, L.e_in, F_D, st);
     embed_stage(e, L, f.embed, f.embed_ln, L.e_in, Tt, st);
     // PreLookaheadLayer: right-pad 3 -> conv k4 -> leaky_relu -> left-pad 2 -> conv k3 -> + x
-    CBX_CHECK(cudaMemsetAsync(L.e_xb + (long)Tt * F_D, 0, 3L * F_D * 2, st));
-    GemmParams g = mk(f.pl1, L.e_xb, F_D, Tt, F_D, F_D); g.act = ACT_LRELU; g.act_param = 0.01f; g.outB = L.e_y1 + 2 * F_D; g.ldc = F_D; launch_gemm(g, st);
-    CBX_CHECK(cudaMemsetAsync(L.e_y1, 0, 2L * F_D * 2, st));
-    g = mk(f.pl2, L.e_y1, F_D, Tt, F_D, F_D); g.res = L.e_x; g.ldr = F_D; g.outF = L.e_x; g.ldc = F_D; launch_gemm(g, st);
-    for (auto& l : f.enc) conformer_layer(e, L, l, Tt, st);
+    for (int b = 0; b < B; b++) CBX_CHECK(cudaMemsetAsync(L.e_xb + b * sl1 + (long)L.call[b].Tt * F_D, 0, 3L * F_D * 2, st));
+    GemmParams g = mk(f.pl1, L.e_xb, F_D, Tt, F_D, F_D); g.batch = B; g.a_bs = sl1; g.act = ACT_LRELU; g.act_param = 0.01f; g.outB = L.e_y1 + 2 * F_D; g.ldc = F_D; g.c_bs = sl1;
+    launch_gemm(g, st);
+    for (int b = 0; b < B; b++) CBX_CHECK(cudaMemsetAsync(L.e_y1 + b * sl1, 0, 2L * F_D * 2, st));
+    g = mk(f.pl2, L.e_y1, F_D, Tt, F_D, F_D); g.batch = B; g.a_bs = sl1; g.res = L.e_x; g.ldr = F_D; g.r_bs = (long)Tt * F_D; g.outF = L.e_x; g.ldc = F_D; g.c_bs = (long)Tt * F_D;
+    launch_gemm(g, st);
+    for (auto& l : f.enc) conformer_layer(e, L, l, Tt, 1, st);
     // Upsample1D: nearest x2 -> left-pad 4 -> conv k5
-    const int T = 2 * Tt;
-    CBX_CHECK(cudaMemsetAsync(L.e_up, 0, 4L * F_D * 2, st));
-    launch_upsample2(L.e_x, L.e_up + 4 * F_D, F_D, Tt, F_D, st);
-    g = mk(f.upconv, L.e_up, F_D, T, F_D, F_D); g.outB = L.e_upc; g.ldc = F_D; launch_gemm(g, st);
+    for (int b = 0; b < B; b++) {
+        CBX_CHECK(cudaMemsetAsync(L.e_up + b * sl2, 0, 4L * F_D * 2, st));
+        launch_upsample2(L.e_x + (long)b * Tt * F_D, L.e_up + b * sl2 + 4 * F_D, F_D, Tt, F_D, st);
+    }
+    g = mk(f.upconv, L.e_up, F_D, T, F_D, F_D); g.batch = B; g.a_bs = sl2; g.outB = L.e_upc; g.ldc = F_D; g.c_bs = (long)T * F_D; launch_gemm(g, st);
     embed_stage(e, L, f.up_embed, f.up_embed_ln, L.e_upc, T, st);
-    for (auto& l : f.up) conformer_layer(e, L, l, T, st);
-    NormParams n; n.in = L.e_x; n.ld_in = F_D; n.rows = T; n.C = F_D; n.gain = f.after_norm.g; n.bias = f.after_norm.b; n.eps = 1e-5f; n.outB = L.e_xn; n.ld_outB = F_D;
+    for (auto& l : f.up) conformer_layer(e, L, l, T, 2, st);
+    NormParams n; n.in = L.e_x; n.ld_in = F_D; n.rows = B * T; n.C = F_D; n.gain = f.after_norm.g; n.bias = f.after_norm.b; n.eps = 1e-5f; n.outB = L.e_xn; n.ld_outB = F_D;
     launch_norm(n, st);
-    g = mk(f.enc_proj, L.e_xn, F_D, T, F_D, 0); g.outF = L.mu; g.ldc = MEL; launch_gemm(g, st);
-    e->gpu_launches += 7;
+    g = mk(f.enc_proj, L.e_xn, F_D, B * T, F_D, 0); g.outF = L.mu; g.ldc = MEL; launch_gemm(g, st);
+    e->gpu_launches += 6 + B;
 }
 
 // ---------------------------------------------------------------------------------------------- estimator
-// all estimator tensors are [2][T(+halo)][C]; batch stride passed explicitly
+// all estimator tensors are [2*nb][T(+halo)][C] (rows 2b, 2b+1 = conditional / unconditional pass of call b)
 static void tfm_block(cbx_engine* e, Lane& L, const TfmP& t, int T, cudaStream_t st) {
+    const int NB = 2 * L.nb;
     const long bs = (long)T * C_CH;
-    NormParams n; n.in = L.c_h; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = 2; n.C = C_CH; n.gain = t.n1.g; n.bias = t.n1.b; n.eps = 1e-5f;
+    NormParams n; n.in = L.c_h; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = NB; n.C = C_CH; n.gain = t.n1.g; n.bias = t.n1.b; n.eps = 1e-5f;
     n.outB = L.c_xn; n.ld_outB = C_CH; n.outB_bs = bs;
     launch_norm(n, st);
-    GemmParams g = mk(t.qkv, L.c_xn, C_CH, 2 * T, C_CH, 0); g.outB = L.c_qkv; g.ldc = 3 * C_INNER; launch_gemm(g, st);
+    GemmParams g = mk(t.qkv, L.c_xn, C_CH, NB * T, C_CH, 0); g.outB = L.c_qkv; g.ldc = 3 * C_INNER; launch_gemm(g, st);
     AttnParams a; a.q = L.c_qkv; a.k = L.c_qkv + C_INNER; a.v = L.c_qkv + 2 * C_INNER; a.ldq = a.ldk = a.ldv = 3 * C_INNER;
-    a.q_bs = a.k_bs = a.v_bs = (long)T * 3 * C_INNER; a.o = L.c_o; a.ldo = C_INNER; a.o_bs = (long)T * C_INNER; a.T = T; a.H = 8; a.batch = 2; a.scale = 0.125f;
+    a.q_bs = a.k_bs = a.v_bs = (long)T * 3 * C_INNER; a.o = L.c_o; a.ldo = C_INNER; a.o_bs = (long)T * C_INNER; a.T = T; a.H = 8; a.batch = NB; a.scale = 0.125f;
+    set_kv_len(a, L, 2, 2);
     launch_attention(a, st);
-    g = mk(t.out, L.c_o, C_INNER, 2 * T, C_INNER, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
+    g = mk(t.out, L.c_o, C_INNER, NB * T, C_INNER, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
     n.gain = t.n3.g; n.bias = t.n3.b; launch_norm(n, st);
-    g = mk(t.ff0, L.c_xn, C_CH, 2 * T, C_CH, 0); g.act = ACT_GELU; g.outB = L.c_ff; g.ldc = C_FF; launch_gemm(g, st);
-    g = mk(t.ff2, L.c_ff, C_FF, 2 * T, C_FF, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
+    g = mk(t.ff0, L.c_xn, C_CH, NB * T, C_CH, 0); g.act = ACT_GELU; g.outB = L.c_ff; g.ldc = C_FF; launch_gemm(g, st);
+    g = mk(t.ff2, L.c_ff, C_FF, NB * T, C_FF, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
     e->gpu_launches += 7;
 }
 
-// resnet: in = haloed bf16 [2][CH+T][cin] -> L.c_h fp32 [2][T][256]
+// resnet: in = haloed bf16 [2nb][CH+T][cin] -> L.c_h fp32 [2nb][T][256]
 static void resnet(cbx_engine* e, Lane& L, const ResnetP& r, const float* tproj, const bf16* in, int T, cudaStream_t st) {
+    const int NB = 2 * L.nb;
     const long TH = T + CH, bs = (long)T * C_CH;
-    GemmParams g = mk(r.c1, in, r.cin, T, r.cin, r.cin); g.batch = 2; g.a_bs = TH * r.cin; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
-    NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = 2; n.C = C_CH; n.gain = r.n1.g; n.bias = r.n1.b; n.eps = 1e-5f; n.act = ACT_MISH;
+    GemmParams g = mk(r.c1, in, r.cin, T, r.cin, r.cin); g.batch = NB; g.a_bs = TH * r.cin; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = NB; n.C = C_CH; n.gain = r.n1.g; n.bias = r.n1.b; n.eps = 1e-5f; n.act = ACT_MISH;
     n.add = tproj; n.add_bs = 0; n.outB = L.c_hb + CH * C_CH; n.ld_outB = C_CH; n.outB_bs = TH * C_CH;
     launch_norm(n, st);
-    g = mk(r.c2, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
-    NormParams n2; n2.in = L.c_tmp; n2.ld_in = C_CH; n2.in_bs = bs; n2.rows = T; n2.batch = 2; n2.C = C_CH; n2.gain = r.n2.g; n2.bias = r.n2.b; n2.eps = 1e-5f; n2.act = ACT_MISH;
+    g = mk(r.c2, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    NormParams n2; n2.in = L.c_tmp; n2.ld_in = C_CH; n2.in_bs = bs; n2.rows = T; n2.batch = NB; n2.C = C_CH; n2.gain = r.n2.g; n2.bias = r.n2.b; n2.eps = 1e-5f; n2.act = ACT_MISH;
     n2.outF = L.c_tmp2; n2.ld_outF = C_CH; n2.outF_bs = bs;
     launch_norm(n2, st);
-    g = mk(r.res, in + CH * r.cin, r.cin, T, r.cin, 0); g.batch = 2; g.a_bs = TH * r.cin; g.res = L.c_tmp2; g.ldr = C_CH; g.r_bs = bs; g.outF = L.c_h; g.ldc = C_CH; g.c_bs = bs;
+    g = mk(r.res, in + CH * r.cin, r.cin, T, r.cin, 0); g.batch = NB; g.a_bs = TH * r.cin; g.res = L.c_tmp2; g.ldr = C_CH; g.r_bs = bs; g.outF = L.c_h; g.ldc = C_CH; g.c_bs = bs;
     launch_gemm(g, st);
     e->gpu_launches += 5;
 }
 
 static void to_bf16_haloed(cbx_engine* e, Lane& L, bf16* dst, int ld, int col0, int T, cudaStream_t st) {
-    // L.c_h fp32 [2][T][256] -> dst [2][CH+T][ld] columns [col0, col0+256)
-    for (int b = 0; b < 2; b++)
+    // L.c_h fp32 [2nb][T][256] -> dst [2nb][CH+T][ld] columns [col0, col0+256)
+    const int NB = 2 * L.nb;
+    for (int b = 0; b < NB; b++)
         launch_f32_to_bf16_rows(L.c_h + (long)b * T * C_CH, C_CH, dst + ((long)b * (T + CH) + CH) * ld + col0, ld, T, C_CH, ACT_NONE, 0.f, st);
-    e->gpu_launches += 2;
+    e->gpu_launches += NB;
 }
 
 static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) {
     FlowModel& f = e->flow;
+    const int NB = 2 * L.nb;
     const int nb = e->cfg.cfm_blocks, nmid = e->cfg.cfm_mid, nsteps = e->cfg.cfm_steps, nres = nmid + 2;
     const long TH = T + CH, bs = (long)T * C_CH;
     auto tp = [&](int r) { return f.tproj + ((long)r * nsteps + step) * C_CH; };
@@ -246,7 +282,7 @@ static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) 
     for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[j], T, st);
     to_bf16_haloed(e, L, L.c_upin, 2 * C_CH, C_CH, T, st);          // skip connection -> channels [256,512) of the up-stage input
     to_bf16_haloed(e, L, L.c_hb, C_CH, 0, T, st);
-    GemmParams g = mk(f.down_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
+    GemmParams g = mk(f.down_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
     launch_gemm(g, st);
     for (int i = 0; i < nmid; i++) {
         resnet(e, L, f.resnets[1 + i], tp(1 + i), L.c_inb, T, st);
@@ -257,41 +293,55 @@ static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) 
     resnet(e, L, f.resnets[nres - 1], tp(nres - 1), L.c_upin, T, st);
     for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[(nres - 1) * nb + j], T, st);
     to_bf16_haloed(e, L, L.c_hb, C_CH, 0, T, st);
-    g = mk(f.up_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
+    g = mk(f.up_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
     launch_gemm(g, st);
-    g = mk(f.final_conv, L.c_inb, C_CH, T, C_CH, C_CH); g.batch = 2; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
-    NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = 2; n.C = C_CH; n.gain = f.final_ln.g; n.bias = f.final_ln.b; n.eps = 1e-5f; n.act = ACT_MISH;
+    g = mk(f.final_conv, L.c_inb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = NB; n.C = C_CH; n.gain = f.final_ln.g; n.bias = f.final_ln.b; n.eps = 1e-5f; n.act = ACT_MISH;
     n.outB = L.c_fb; n.ld_outB = C_CH; n.outB_bs = bs;
     launch_norm(n, st);
-    g = mk(f.final_proj, L.c_fb, C_CH, 2 * T, C_CH, 0); g.outF = L.v; g.ldc = MEL; launch_gemm(g, st);
+    g = mk(f.final_proj, L.c_fb, C_CH, NB * T, C_CH, 0); g.outF = L.v; g.ldc = MEL; launch_gemm(g, st);
     e->gpu_launches += 5;
 }
 
-// host -> device staging of one call's tokens (not graph-captured)
-void flow_stage(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st) {
+// host -> device staging of the batch's tokens (not graph-captured): L.call[0..nb) must be set
+void flow_stage(cbx_engine* e, Lane& L, const int* const* tokens_h, cudaStream_t st) {
     const cbx_config& c = e->cfg;
-    CBX_REQUIRE(n >= 1 && n <= c.max_s3_tokens, "s3gen: token count out of range");
-    const int T = 2 * (v.n_prompt + n);
-    CBX_REQUIRE(v.n_feat <= T, "s3gen: prompt_feat longer than the encoded sequence");
-    CBX_REQUIRE(T <= NOISE_LEN, "s3gen: sequence exceeds the CFM noise buffer");
-    for (int i = 0; i < n; i++) CBX_REQUIRE(tokens_h[i] >= 0 && tokens_h[i] < F_V, "s3gen: token id out of range");
-    CBX_CHECK(cudaMemcpyAsync(L.tok, v.prompt_token, (size_t)v.n_prompt * 4, cudaMemcpyDeviceToDevice, st));
-    CBX_CHECK(cudaMemcpyAsync(L.tok + v.n_prompt, tokens_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    CBX_CHECK(cudaStreamSynchronize(st));   // tokens_h may be a transient host buffer
+    CBX_REQUIRE(L.nb >= 1 && L.nb <= L.bmax, "s3gen: batch exceeds the lane's capacity");
+    L.Ttm = 0;
+    for (int b = 0; b < L.nb; b++) {
+        FlowCall& k = L.call[b];
+        CBX_REQUIRE(k.n >= 1 && k.n <= c.max_s3_tokens, "s3gen: token count out of range");
+        k.Tt = k.v->n_prompt + k.n;
+        CBX_REQUIRE(k.v->n_feat <= 2 * k.Tt, "s3gen: prompt_feat longer than the encoded sequence");
+        CBX_REQUIRE(2 * k.Tt <= NOISE_LEN, "s3gen: sequence exceeds the CFM noise buffer");
+        for (int i = 0; i < k.n; i++) CBX_REQUIRE(tokens_h[b][i] >= 0 && tokens_h[b][i] < F_V, "s3gen: token id out of range");
+        L.Ttm = std::max(L.Ttm, k.Tt);
+    }
+    if (L.nb > 1) CBX_CHECK(cudaMemsetAsync(L.tok, 0, (size_t)L.nb * L.Ttm * 4, st));   // pad ids (their rows are never consumed)
+    for (int b = 0; b < L.nb; b++) {
+        const FlowCall& k = L.call[b];
+        CBX_CHECK(cudaMemcpyAsync(L.tok + (long)b * L.Ttm, k.v->prompt_token, (size_t)k.v->n_prompt * 4, cudaMemcpyDeviceToDevice, st));
+        CBX_CHECK(cudaMemcpyAsync(L.tok + (long)b * L.Ttm + k.v->n_prompt, tokens_h[b], (size_t)k.n * 4, cudaMemcpyHostToDevice, st));
+    }
+    CBX_CHECK(cudaStreamSynchronize(st));   // tokens_h may be transient host buffers
 }
 
-// device-only part (CUDA-graph capturable): L.tok -> L.mel
-void flow_run(cbx_engine* e, Lane& L, const Voice& v, int n, cudaStream_t st) {
+// device-only part (CUDA-graph capturable for a fixed batch shape): L.tok -> L.melb[b] = [2 n_b][80] at stride 2*max_s3_tokens*80
+void flow_run(cbx_engine* e, Lane& L, cudaStream_t st) {
     FlowModel& f = e->flow;
     const cbx_config& c = e->cfg;
-    const int Tt = v.n_prompt + n, T = 2 * Tt, L1 = v.n_feat;
-    encoder(e, L, Tt, st);
-    CBX_CHECK(cudaMemsetAsync(L.cond, 0, (size_t)T * MEL * 4, st));
-    CBX_CHECK(cudaMemcpyAsync(L.cond, v.prompt_feat, (size_t)L1 * MEL * 4, cudaMemcpyDeviceToDevice, st));
-    CBX_CHECK(cudaMemcpyAsync(L.x, f.noise, (size_t)T * MEL * 4, cudaMemcpyDeviceToDevice, st));
+    const int B = L.nb, T = 2 * L.Ttm;
+    const long xs = (long)T * MEL;
+    encoder(e, L, st);
+    CBX_CHECK(cudaMemsetAsync(L.cond, 0, (size_t)B * xs * 4, st));
+    for (int b = 0; b < B; b++) {
+        const Voice& v = *L.call[b].v;
+        CBX_CHECK(cudaMemcpyAsync(L.cond + b * xs, v.prompt_feat, (size_t)v.n_feat * MEL * 4, cudaMemcpyDeviceToDevice, st));
+        CBX_CHECK(cudaMemcpyAsync(L.x + b * xs, f.noise, (size_t)xs * 4, cudaMemcpyDeviceToDevice, st));
+    }
     // causal halos of the estimator inputs
     const long TH = T + CH;
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < 2 * B; b++) {
         CBX_CHECK(cudaMemsetAsync(L.c_in + b * TH * C_IN, 0, (size_t)CH * C_IN * 2, st));
         CBX_CHECK(cudaMemsetAsync(L.c_hb + b * TH * C_CH, 0, (size_t)CH * C_CH * 2, st));
         CBX_CHECK(cudaMemsetAsync(L.c_inb + b * TH * C_CH, 0, (size_t)CH * C_CH * 2, st));
@@ -299,15 +349,23 @@ void flow_run(cbx_engine* e, Lane& L, const Voice& v, int n, cudaStream_t st) {
     }
     const int ns = c.cfm_steps;
     for (int k = 0; k < ns; k++) {
-        launch_pack_cfm_input(L.x, L.mu, v.spks, L.cond, L.c_in + CH * C_IN, TH * C_IN, T, MEL, st);
+        for (int b = 0; b < B; b++)
+            launch_pack_cfm_input(L.x + b * xs, L.mu + b * xs, L.call[b].v->spks, L.cond + b * xs, L.c_in + ((long)2 * b * TH + CH) * C_IN, TH * C_IN, T, MEL, st);
         estimator(e, L, T, k, st);
-        launch_euler_update(L.x, L.v, (long)T * MEL, (long)T * MEL, f.t_span[ns + k], c.cfm_cfg_rate, st);
-        e->gpu_launches += 2;
+        for (int b = 0; b < B; b++) launch_euler_update(L.x + b * xs, L.v + (long)2 * b * xs, xs, xs, f.t_span[ns + k], c.cfm_cfg_rate, st);
+        e->gpu_launches += 2 * B;
     }
-    CBX_CHECK(cudaMemcpyAsync(L.mel, L.x + (long)L1 * MEL, (size_t)(T - L1) * MEL * 4, cudaMemcpyDeviceToDevice, st));
+    const long mel_bs = 2L * c.max_s3_tokens * MEL;
+    for (int b = 0; b < B; b++) {
+        const FlowCall& k = L.call[b];
+        CBX_CHECK(cudaMemcpyAsync(L.melb + b * mel_bs, L.x + b * xs + (long)k.v->n_feat * MEL, (size_t)(2 * k.Tt - k.v->n_feat) * MEL * 4, cudaMemcpyDeviceToDevice, st));
+    }
 }
 
 void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int n, cudaStream_t st) {
-    flow_stage(e, L, v, tokens_h, n, st);
-    flow_run(e, L, v, n, st);
+    L.nb = 1; L.call[0].v = &v; L.call[0].n = n;
+    const int* toks[1] = {tokens_h};
+    flow_stage(e, L, toks, st);
+    flow_run(e, L, st);
+    CBX_CHECK(cudaMemcpyAsync(L.mel, L.melb, (size_t)2 * n * MEL * 4, cudaMemcpyDeviceToDevice, st));
 }

@@ -86,6 +86,16 @@ int cbx_t3_close(cbx_engine* e, int slot);
 int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, const float* cache_source_d, int64_t m,
                     float* wav_out_d, float* source_out_d, float* mel_out_d, const float* phase_h, const float* noise_d,
                     uint64_t seed, void* stream);
+/* The same call for up to 8 requests at once (concurrent streams, or the text chunks of one request): the token -> mel
+ * part runs as ONE batch padded to the longest sequence (exact: causal convolutions, per-frame norms / linears, attention
+ * masked per sequence), the vocoder per call.  Results equal cbx_s3gen_infer call by call. */
+typedef struct cbx_s3gen_call {
+    int voice; const int32_t* tokens_h; int n;
+    const float* cache_source_d; int64_t m;
+    float* wav_out_d; float* source_out_d; float* mel_out_d /* optional */;
+    uint64_t seed;
+} cbx_s3gen_call;
+int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_calls, void* stream);
 /* the two halves of the call above, for teacher-forced parity checks */
 int cbx_flow_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, float* mel_out_d, void* stream);
 int cbx_hift_infer(cbx_engine* e, const float* mel_d /*[frames][80]*/, int frames, const float* cache_source_d, int64_t m,

@@ -249,6 +249,44 @@ def test_s3gen_end_to_end_shapes(tiny, tiny_cfg, dev):
     assert torch.allclose(wav2, wav, atol=1e-6), "same tokens + full cache_source => same audio"
 
 
+def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev):
+    """cbx_s3gen_infer_batch pads the calls to the longest sequence and runs one token->mel pass; padding is exact
+    (causal convs, per-frame norms, per-sequence attention masks, zeroed look-ahead rows), so every call must
+    reproduce its single-call result: mel to float rounding (GEMM tile membership changes nothing in the K order,
+    only the padded tail differs), waveform likewise with the same seed and source cache."""
+    from cbx_b200.weights import synthetic_conditionals
+    eng, sd_dev, conds, voice = tiny
+    c2 = synthetic_conditionals(tiny_cfg, 77, prompt_tokens=23)    # a second voice with a different prompt length
+    c2["gen"]["prompt_feat"] = c2["gen"]["prompt_feat"].to(torch.bfloat16).float()
+    v2 = eng.voice_put("w", c2["t3"], c2["gen"])
+    g = torch.Generator().manual_seed(9)
+    lens = [35, 3, 70, 41, 12]
+    voices = [voice, v2, voice, v2, voice]
+    toks = [torch.randint(0, 6561, (n,), generator=g).numpy().astype(np.int32) for n in lens]
+    single = []
+    for v, t in zip(voices, toks):
+        wav, src, mel = eng.s3gen_infer(v, t, seed=5, return_mel=True)
+        single.append((wav.clone(), src.clone(), mel.clone()))
+    torch.cuda.synchronize()
+    # second pass with source caches: the batch must honour per-call cache_source too
+    caches = [s[1][..., : 960 * 2].contiguous() if i % 2 == 0 else None for i, s in enumerate(single)]
+    single2 = [eng.s3gen_infer(v, t, cache_source=c, seed=6, return_mel=True) for v, t, c in zip(voices, toks, caches)]
+    single2 = [tuple(x.clone() for x in s) for s in single2]
+    batch = eng.s3gen_infer_batch([(v, t, None, 5) for v, t in zip(voices, toks)], return_mel=True)
+    batch2 = eng.s3gen_infer_batch([(v, t, c, 6) for v, t, c in zip(voices, toks, caches)], return_mel=True)
+    torch.cuda.synchronize()
+    for ref, got in list(zip(single, batch)) + list(zip(single2, batch2)):
+        assert got[2].shape == ref[2].shape
+        assert _rel(got[2], ref[2]) < 1e-5, f"mel differs: {_rel(got[2], ref[2])}"
+        assert torch.equal(got[1], ref[1]) or _rel(got[1], ref[1]) < 1e-4
+        assert _rel(got[0], ref[0]) < 1e-3
+    # one-call batch == single call
+    one = eng.s3gen_infer_batch([(voice, toks[0], None, 5)], return_mel=True)[0]
+    torch.cuda.synchronize()
+    assert _rel(one[2], single[0][2]) < 1e-6 and _rel(one[0], single[0][0]) < 1e-5
+    eng.voice_drop("w")
+
+
 def test_crossfade_pcm(tiny, dev):
     eng = tiny[0]
     g = torch.Generator().manual_seed(0)

@@ -10,14 +10,18 @@ lead/trail trim (:702-707), equal-power crossfade state machine (:710-746, :756-
 int16 truncation (:149-155).
 
 What is different (B200-first): T3 decode steps of all concurrent requests are batched
-into one GEMV pass per step by a scheduler thread; S3Gen slices run on engine lanes in parallel with
-T3; crossfade + PCM conversion are one device kernel; there is one thread per request instead of
-three asyncio tasks racing a cancel event per token.
+into one GEMV pass per step by a scheduler thread; the text chunks of one request decode concurrently
+(they are independent: the reference re-primes T3 and resets the S3Gen cache per chunk, :453-491, :648-653)
+and their audio is emitted in order; S3Gen slices of all chunks / requests that are ready at the same time go
+through ONE batched token->mel pass (cbx_s3gen_infer_batch); crossfade + PCM conversion are one device kernel.
 """
 import asyncio
+import collections
 import concurrent.futures
 import contextlib
+import heapq
 import os
+import queue
 import threading
 import time
 import zlib
@@ -198,6 +202,102 @@ class T3Scheduler(threading.Thread):
             self.lock.notify_all()
 
 
+class S3GenBatcher(threading.Thread):
+    """Collects the S3Gen calls that are pending at the same moment (slices of concurrent requests, or of the text
+    chunks of one request) and runs them as one batch: while a batch is on the GPU the next one accumulates.  A single
+    pending call takes the per-lane CUDA-graph path."""
+
+    def __init__(self, native, max_batch: int = 8):
+        super().__init__(daemon=True, name="cbx-s3gen-batcher")
+        self.native, self.max_batch = native, max_batch
+        self.on_gpu = not getattr(native, "is_fake", False)
+        self.can_batch = hasattr(native, "s3gen_infer_batch")
+        self.jobs = collections.deque()
+        self.cv = threading.Condition()
+        self.running = True
+        self.batches = collections.Counter()   # batch size -> count (bench / tests)
+        self.start()
+
+    def infer(self, voice, toks, cache_source, seed):
+        """Blocking call with s3gen_infer's result; the tensors are complete (the batcher synchronised its stream)."""
+        job = {"args": (voice, toks, cache_source, seed), "done": threading.Event(), "out": None, "err": None}
+        with self.cv:
+            self.jobs.append(job)
+            self.cv.notify_all()
+        job["done"].wait()
+        if job["err"] is not None:
+            raise job["err"]
+        return job["out"]
+
+    def run(self):
+        st = None
+        if self.on_gpu:
+            torch.cuda.set_device(self.native.device)
+            st = torch.cuda.Stream()
+        while True:
+            with self.cv:
+                while self.running and not self.jobs:
+                    self.cv.wait(0.5)
+                if not self.running:
+                    for j in self.jobs:
+                        j["err"] = RuntimeError("engine is shutting down")
+                        j["done"].set()
+                    return
+                batch = [self.jobs.popleft() for _ in range(min(len(self.jobs), self.max_batch if self.can_batch else 1))]
+            try:
+                with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                    if len(batch) == 1:
+                        v, t, c, sd = batch[0]["args"]
+                        outs = [self.native.s3gen_infer(v, t, cache_source=c, seed=sd)]
+                    else:
+                        outs = self.native.s3gen_infer_batch([j["args"] for j in batch])
+                    if st is not None:
+                        st.synchronize()
+                self.batches[len(batch)] += 1
+                for j, o in zip(batch, outs):
+                    j["out"] = o
+            except BaseException as ex:
+                for j in batch:
+                    j["err"] = ex
+            for j in batch:
+                j["done"].set()
+
+    def stop(self):
+        self.running = False
+        with self.cv:
+            self.cv.notify_all()
+
+
+class PrioritySlots:
+    """Counting semaphore whose waiters are served lowest (priority, arrival) first: T3 stream slots go to the earliest
+    text chunks, so a request's later chunks never starve another request's first chunk."""
+
+    def __init__(self, n: int):
+        self.free, self.cv, self.waiters, self.seq = n, threading.Condition(), [], 0
+
+    def acquire(self, prio: int, cancelled=None) -> bool:
+        with self.cv:
+            self.seq += 1
+            me = (prio, self.seq)
+            heapq.heappush(self.waiters, me)
+            while not (self.free > 0 and self.waiters[0] == me):
+                if cancelled is not None and cancelled():
+                    self.waiters.remove(me)
+                    heapq.heapify(self.waiters)
+                    self.cv.notify_all()
+                    return False
+                self.cv.wait(0.05)
+            heapq.heappop(self.waiters)
+            self.free -= 1
+            self.cv.notify_all()
+            return True
+
+    def release(self):
+        with self.cv:
+            self.free += 1
+            self.cv.notify_all()
+
+
 def drop_invalid_tokens(x: List[int], sos=6561, eos=6562) -> List[int]:
     """chatterbox.models.s3tokenizer.drop_invalid_tokens (reference call site :667): keep what lies
     between the first SOS (exclusive) and the first EOS (exclusive)."""
@@ -235,6 +335,11 @@ class TextToSpeechEngine:
         # two S3Gen lanes: measured on B200, more lanes do not raise aggregate throughput (the per-call kernels are
         # latency-bound and already span the SMs) and cost workspace + graph captures per lane
         self.native_kwargs = dict(max_streams=max(8, n), n_lanes=2)
+        # text chunks of one request that may be in flight at once (T3 decoding + S3Gen), ahead of the chunk being emitted
+        self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "4"))
+        self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=4 * max(8, n), thread_name_prefix="cbx-chunk")
+        self.s3gen: Optional[S3GenBatcher] = None
+        self.t3_slots: Optional[PrioritySlots] = None
         self.native_kwargs.update(native_kwargs or {})
         self.native: Optional[NativeEngine] = None
         self.scheduler: Optional[T3Scheduler] = None
@@ -259,6 +364,8 @@ class TextToSpeechEngine:
             self.tokenizer = SyntheticTokenizer(self.cfg.t3.text_vocab)
             self.voice_cache["default"] = 0
             self.scheduler = T3Scheduler(self.native, max_batch=8)
+            self.s3gen = S3GenBatcher(self.native)
+            self.t3_slots = PrioritySlots(self.native_kwargs["max_streams"])
             self._ready = True
             return
         torch.cuda.set_device(self.gpu_id)
@@ -279,6 +386,8 @@ class TextToSpeechEngine:
         self.default_conds = synthetic_conditionals(self.cfg)      # stands in for conds.pt (tts.conds, :399-404)
         self.voice_cache["default"] = self.native.voice_put("default", self.default_conds["t3"], self.default_conds["gen"])
         self.scheduler = T3Scheduler(self.native, max_batch=min(8, self.native_kwargs["max_streams"]))
+        self.s3gen = S3GenBatcher(self.native)
+        self.t3_slots = PrioritySlots(self.native_kwargs["max_streams"] - 1)   # one slot stays free for warm-up / direct opens
         # warm-up, as the reference does (:274-326): 4 T3 tokens with cfg 0, one tiny S3Gen call
         text = [self.cfg.t3.start_text_token] + self.tokenizer.text_to_tokens("compiling")[0].tolist() + [self.cfg.t3.stop_text_token]
         s = self.scheduler.open(self.voice_cache["default"], text, 0.0, 0.8, self.sampling, 0, 4)
@@ -290,6 +399,9 @@ class TextToSpeechEngine:
     def shutdown(self):
         if self.scheduler:
             self.scheduler.stop()
+        if self.s3gen:
+            self.s3gen.stop()
+        self.chunk_executor.shutdown(wait=True)
         self.request_executor.shutdown(wait=True)
         self.voice_conditioning_executor.shutdown(wait=True)
         if self.native:
@@ -374,95 +486,146 @@ class TextToSpeechEngine:
                 host = pcm.cpu()          # stream-ordered D2H of n_out int16 samples
                 emit(host.numpy().tobytes())
 
+            cancelled = (lambda: token is not None and token.is_cancelled())
             streams = [None] * len(chunks)
+            outq = [queue.Queue() for _ in chunks]           # per chunk: (cur, last) items, then None (or an exception)
+            first_slice_ready = threading.Event()            # chunk 0 has the tokens of its first slice (or is done)
+            window = threading.Semaphore(max(1, self.chunk_parallelism))   # chunks in flight ahead of the emitter
+            stop = threading.Event()
 
-            def open_chunk(i):
-                ids = self.tokenizer.text_to_tokens(chunks[i])[0].tolist()
-                ids = [self.cfg.t3.start_text_token] + ids + [self.cfg.t3.stop_text_token]
-                max_new = self.sampling.max_new_tokens
-                if self.sampling.tokens_per_word:
-                    max_new = max(1, self.sampling.tokens_per_word * len(chunks[i].split()))
-                streams[i] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + i, max_new)
-
-            open_chunk(0)
-            for ci in range(len(chunks)):
-                if token is not None and token.is_cancelled():
-                    break
-                s = streams[ci]
-                is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
-                consumed, slice_idx, acc, cache_source, prev_len = 0, 0, [], None, 0
-                opened_next = False
-                while True:
-                    if not self._wait_tokens(s, consumed + slice_len + look_ahead, token):
-                        break
-                    # T3 of the next text chunk starts as soon as this one has finished decoding
-                    if s.finished and not opened_next and ci + 1 < len(chunks):
-                        open_chunk(ci + 1)
-                        opened_next = True
-                    avail = len(s.tokens) - consumed
-                    if avail >= slice_len + look_ahead:
-                        new, last = s.tokens[consumed: consumed + slice_len], False
-                    elif s.finished:
-                        if avail <= 0:
+            def chunk_worker(ci):
+                """T3 stream + S3Gen slices of one text chunk (reference _t3_producer_task / _s3gen_producer_task per chunk)."""
+                have_slot = False
+                try:
+                    if self._backend is None:
+                        torch.cuda.set_device(self.gpu_id)
+                    if not self.t3_slots.acquire(ci, lambda: cancelled() or stop.is_set()):
+                        return
+                    have_slot = True
+                    ids = self.tokenizer.text_to_tokens(chunks[ci])[0].tolist()
+                    ids = [self.cfg.t3.start_text_token] + ids + [self.cfg.t3.stop_text_token]
+                    max_new = self.sampling.max_new_tokens
+                    if self.sampling.tokens_per_word:
+                        max_new = max(1, self.sampling.tokens_per_word * len(chunks[ci].split()))
+                    s = streams[ci] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + ci, max_new)
+                    is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
+                    consumed, slice_idx, acc, cache_source, prev_len = 0, 0, [], None, 0
+                    while not stop.is_set():
+                        if not self._wait_tokens(s, consumed + slice_len + look_ahead, token):
                             break
-                        new, last = s.tokens[consumed:], True
-                    else:
-                        continue
-                    consumed += len(new)
-                    slice_idx += 1
-                    first_slice = slice_idx == 1
-                    acc = acc + new if overlap == "full" else new
-                    toks = list(acc)
-                    if last:
-                        toks = toks + [self.cfg.t3.stop_text_token]          # reference appends hp.stop_text_token (0)
-                    toks = [t for t in drop_invalid_tokens(toks) if t < SPEECH_VOCAB]
-                    if len(toks) == 0:
+                        if s.finished and have_slot:          # decoding is over: the slot can serve the next chunk
+                            self.t3_slots.release()
+                            have_slot = False
+                        if ci == 0:
+                            first_slice_ready.set()
+                        avail = len(s.tokens) - consumed
+                        if avail >= slice_len + look_ahead:
+                            new, last = s.tokens[consumed: consumed + slice_len], False
+                        elif s.finished:
+                            if avail <= 0:
+                                break
+                            new, last = s.tokens[consumed:], True
+                        else:
+                            continue
+                        consumed += len(new)
+                        slice_idx += 1
+                        first_slice = slice_idx == 1
+                        acc = acc + new if overlap == "full" else new
+                        toks = list(acc)
+                        if last:
+                            toks = toks + [self.cfg.t3.stop_text_token]          # reference appends hp.stop_text_token (0)
+                        toks = [t for t in drop_invalid_tokens(toks) if t < SPEECH_VOCAB]
+                        if len(toks) == 0:
+                            if last:
+                                break
+                            continue
+                        if len(toks) < 3:
+                            toks = toks + [0] * (3 - len(toks))
+                        wav, src = self.s3gen.infer(voice, toks, cache_source, base_seed + 7919 * ci + slice_idx)
+                        cur = wav[0]
+                        if overlap == "full":
+                            cache_source = src
+                            full_len = cur.shape[0]
+                            if not first_slice:
+                                cur = cur[prev_len:]
+                            prev_len = full_len
+                        if is_first_chunk and first_slice and lead > 0 and cur.shape[0] > lead:
+                            cur = cur[lead:]
+                        if is_last_chunk and last and trail > 0 and cur.shape[0] > trail:
+                            cur = cur[:-trail]
+                        outq[ci].put((cur, last))
                         if last:
                             break
-                        continue
-                    if len(toks) < 3:
-                        toks = toks + [0] * (3 - len(toks))
-                    wav, src = nat.s3gen_infer(voice, toks, cache_source=cache_source, seed=base_seed + 7919 * ci + slice_idx)
-                    cur = wav[0]
-                    if overlap == "full":
-                        cache_source = src
-                        full_len = cur.shape[0]
-                        if not first_slice:
-                            cur = cur[prev_len:]
-                        prev_len = full_len
-                    if is_first_chunk and first_slice and lead > 0 and cur.shape[0] > lead:
-                        cur = cur[lead:]
-                    if is_last_chunk and last and trail > 0 and cur.shape[0] > trail:
-                        cur = cur[:-trail]
-                    n = cur.shape[0]
-                    # crossfade state machine (reference :710-746)
-                    if not first_sent:
-                        if fade_len > 0 and n > fade_len:
-                            send(cur, n - fade_len, None)
-                            prev_tail = cur[n - fade_len:]
-                        else:
-                            send(cur, n, None)
-                            prev_tail = None
-                        first_sent = True
+                except BaseException as ex:
+                    outq[ci].put(ex)
+                finally:
+                    if ci == 0:
+                        first_slice_ready.set()
+                    if have_slot:
+                        self.t3_slots.release()
+                    if streams[ci] is not None and not streams[ci].finished:
+                        sched.cancel(streams[ci])
+                    outq[ci].put(None)
+
+            def opener():
+                """Starts the chunk workers in order, at most `chunk_parallelism` ahead of the emitter; chunks after the
+                first wait until chunk 0 holds its first slice, so the first audio is not slowed down by their prefills."""
+                for ci in range(len(chunks)):
+                    while not window.acquire(timeout=0.05):
+                        if stop.is_set() or cancelled():
+                            break
                     else:
-                        can_fade = fade_len > 0 and prev_tail is not None and prev_tail.shape[0] == fade_len and n > fade_len
-                        if can_fade:
-                            body = n - 2 * fade_len if n > 2 * fade_len else 0
-                            send(cur, fade_len + body, prev_tail)
-                            prev_tail = cur[n - fade_len:]
+                        if ci == 1:
+                            while not first_slice_ready.wait(0.05):
+                                if stop.is_set() or cancelled():
+                                    break
+                        if not (stop.is_set() or cancelled()):
+                            self.chunk_executor.submit(chunk_worker, ci)
+                            continue
+                    outq[ci].put(None)      # never started (cancelled / stopped)
+
+            threading.Thread(target=opener, daemon=True, name="cbx-opener").start()
+            try:
+                for ci in range(len(chunks)):
+                    while True:
+                        item = outq[ci].get()
+                        if item is None:
+                            break
+                        if isinstance(item, BaseException):
+                            raise item
+                        if cancelled():
+                            continue
+                        cur, last = item
+                        n = cur.shape[0]
+                        # crossfade state machine (reference :710-746)
+                        if not first_sent:
+                            if fade_len > 0 and n > fade_len:
+                                send(cur, n - fade_len, None)
+                                prev_tail = cur[n - fade_len:]
+                            else:
+                                send(cur, n, None)
+                                prev_tail = None
+                            first_sent = True
                         else:
-                            if prev_tail is not None:
-                                send(prev_tail, prev_tail.shape[0], None)
-                            prev_tail = cur[n - fade_len:] if (fade_len > 0 and n > fade_len) else cur
-                    if last:
+                            can_fade = fade_len > 0 and prev_tail is not None and prev_tail.shape[0] == fade_len and n > fade_len
+                            if can_fade:
+                                body = n - 2 * fade_len if n > 2 * fade_len else 0
+                                send(cur, fade_len + body, prev_tail)
+                                prev_tail = cur[n - fade_len:]
+                            else:
+                                if prev_tail is not None:
+                                    send(prev_tail, prev_tail.shape[0], None)
+                                prev_tail = cur[n - fade_len:] if (fade_len > 0 and n > fade_len) else cur
+                    window.release()
+                    if cancelled():
                         break
-                if not opened_next and ci + 1 < len(chunks) and not (token is not None and token.is_cancelled()):
-                    open_chunk(ci + 1)
-            if prev_tail is not None and prev_tail.shape[0] > 0 and not (token is not None and token.is_cancelled()):
-                send(prev_tail, prev_tail.shape[0], None)     # reference `finally` flush (:756-760)
-            for s in streams:
-                if s is not None and not s.finished:
-                    sched.cancel(s)
+                if prev_tail is not None and prev_tail.shape[0] > 0 and not cancelled():
+                    send(prev_tail, prev_tail.shape[0], None)     # reference `finally` flush (:756-760)
+            finally:
+                stop.set()
+                for s in streams:
+                    if s is not None and not s.finished:
+                        sched.cancel(s)
 
     # ------------------------------------------------------------------ public API (reference stream :815-968)
     async def stream(self, text: str, output_format: str, voice_id: Optional[str], cfg_guidance_weight: float,

@@ -265,10 +265,8 @@ static void resnet(cbx_engine* e, Lane& L, const ResnetP& r, const float* tproj,
 
 static void to_bf16_haloed(cbx_engine* e, Lane& L, bf16* dst, int ld, int col0, int T, cudaStream_t st) {
     // L.c_h fp32 [2nb][T][256] -> dst [2nb][CH+T][ld] columns [col0, col0+256)
-    const int NB = 2 * L.nb;
-    for (int b = 0; b < NB; b++)
-        launch_f32_to_bf16_rows(L.c_h + (long)b * T * C_CH, C_CH, dst + ((long)b * (T + CH) + CH) * ld + col0, ld, T, C_CH, ACT_NONE, 0.f, st);
-    e->gpu_launches += NB;
+    launch_f32_to_bf16_slabs(L.c_h, C_CH, (long)T * C_CH, dst + (long)CH * ld + col0, ld, (long)(T + CH) * ld, T, C_CH, 2 * L.nb, st);
+    e->gpu_launches += 1;
 }
 
 static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) {

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a: C[128 x BN] tile per CTA, operands staged by TMA into a
 // SWIZZLE_128B smem ring, one elected thread issues tcgen05.mma (M=128, N=BN, K=16 per instruction) into a
-// TMEM accumulator, four epilogue warps read it back with tcgen05.ld and apply the fused epilogue.
+// TMEM accumulator, then all eight warps read it back with tcgen05.ld and apply the fused epilogue.  Two CTAs per SM.
 // The A operand is described by a 4-D tensor map (channel, row, tap, batch): row stride lda, tap stride
 // tap_stride -- conv1d over time-major channels-last activations becomes plain TMA boxes (implicit GEMM).
 #include <cuda.h>
@@ -13,7 +13,9 @@ namespace {
 constexpr int TM = 128, TK = 64, A_BYTES = TM * TK * 2;
 __device__ unsigned long long g_tc_trace[16];
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = BN <= 64 ? 8 : (BN <= 128 ? 6 : 4);
+    // shallow rings (K is 256..1024 here) so that TWO CTAs fit one SM: the prologue / epilogue of one tile overlaps the
+    // main loop of the other, which is what multi-wave (batched) launches need; the ring doubles as the epilogue tile
+    static constexpr int STAGES = BN <= 64 ? 4 : 3;
     static constexpr int B_BYTES = BN * TK * 2;
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -57,7 +59,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 template <int BN, int ACT, int ACT2>
-__global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                          const GemmParams p, int kc_blocks, int w_batched) {
     using C = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (threadIdx.x == 0) TC_TRACE(1);
+    // warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer; afterwards all 8 warps run the epilogue
+    // (TMEM lane quarter = warp % 4, column half = warp / 4)
     if (warp == 0) {
         if (lane == 0) {   // TMA producer
             for (int kb = 0; kb < KB; kb++) {
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
                 tma_load_3d(sB + s * C::B_BYTES, &tmW, full0 + 8 * s, kb * TK, n0, w_batched ? b : 0);
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {   // MMA issuer
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
@@ -116,8 +121,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
             umma_commit(tmem_full);
             TC_TRACE(3);
         }
-    } else {               // epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
-        const int q = warp & 3, half = (warp - 2) >> 2, et = threadIdx.x - 64;
+        __syncwarp();
+    }
+    {
+        const int q = warp & 3, half = warp >> 2, et = threadIdx.x;
         constexpr int LDT = BN + 4, CPR = BN / 8, RSTEP = 256 / CPR;
         const int cc = (et % CPR) * 8;
         ColOps co;
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_kernel(const __grid_constant__
             }
         }
         if (threadIdx.x == 64) TC_TRACE(7);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __syncthreads();
         if (threadIdx.x == 64) TC_TRACE(8);
         epilogue_rows<ACT, ACT2>(p, b, m0, et / CPR, RSTEP, TM, tile, LDT, cc, co);
     }
@@ -185,7 +192,7 @@ bool launch_tc(const GemmParams& p, cudaStream_t st) {
     }
     dim3 grid(cdiv(p.M, TM), cdiv(p.N, BN), p.batch);
     bool done = false;
-#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { launch_pdl(gemm_tc_kernel<BN, A1, A2>, grid, dim3(320), C::SMEM, st, tmA, tmW, p, p.kc / TK, w_batched); done = true; }
+#define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { launch_pdl(gemm_tc_kernel<BN, A1, A2>, grid, dim3(256), C::SMEM, st, tmA, tmW, p, p.kc / TK, w_batched); done = true; }
     CBX_FOR_ACT_PAIRS(CBX_LAUNCH)
 #undef CBX_LAUNCH
     if (!done) return false;

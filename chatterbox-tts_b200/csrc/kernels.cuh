@@ -16,6 +16,7 @@ struct NormParams {
 void launch_norm(const NormParams& p, cudaStream_t st);
 void launch_gather_rows_bf16(const float* table, const int* idx, int n, int C, bf16* out, long ld, cudaStream_t st);
 void launch_f32_to_bf16_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, int act, float act_param, cudaStream_t st);
+void launch_f32_to_bf16_slabs(const float* in, long ld_in, long in_bs, bf16* out, long ld_out, long out_bs, int rows, int C, int batch, cudaStream_t st);
 void launch_add_rows(float* a, long lda, const float* b, long ldb, int rows, int C, cudaStream_t st);
 void launch_upsample2(const float* in, bf16* out, long ld_out, int T, int C, cudaStream_t st);
 void launch_pack_cfm_input(const float* x, const float* mu, const float* spks, const float* cond, bf16* out, long out_bs, int T, int mel, cudaStream_t st);

@@ -67,6 +67,17 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ in, long ld_in
     out[(long)r * ld_out + c] = __float2bfloat16(act_apply(act, in[(long)r * ld_in + c], act_param));
 }
 
+// batched form: slab b of `rows` rows at in + b*in_bs -> out + b*out_bs (4 columns per thread; C % 4 == 0)
+__global__ void f32_to_bf16_slabs_kernel(const float* __restrict__ in, long ld_in, long in_bs, bf16* out, long ld_out, long out_bs, int rows, int C) {
+    pdl_prologue();
+    const int b = blockIdx.y;
+    const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= (long)rows * C) return;
+    const int r = i / C, c = i % C;
+    const float4 v = *reinterpret_cast<const float4*>(in + b * in_bs + (long)r * ld_in + c);
+    *reinterpret_cast<uint2*>(out + b * out_bs + (long)r * ld_out + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+}
+
 __global__ void add_rows_kernel(float* a, long lda, const float* b, long ldb, int rows, int C) {
     pdl_prologue();
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,6 +175,13 @@ void launch_f32_to_bf16_rows(const float* in, long ld_in, bf16* out, long ld_out
     ProfScope ps(PC_ELEMWISE, (double)rows * C * 6, st);
     if (rows == 0) return;
     launch_pdl(f32_to_bf16_rows_kernel, dim3(g1((long)rows * C)), dim3(256), 0, st, in, ld_in, out, ld_out, rows, C, act, act_param);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_f32_to_bf16_slabs(const float* in, long ld_in, long in_bs, bf16* out, long ld_out, long out_bs, int rows, int C, int batch, cudaStream_t st) {
+    ProfScope ps(PC_ELEMWISE, (double)rows * C * 6 * batch, st);
+    if (rows == 0 || batch == 0) return;
+    CBX_REQUIRE(C % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && in_bs % 4 == 0 && out_bs % 4 == 0, "f32_to_bf16_slabs: 4-column alignment");
+    launch_pdl(f32_to_bf16_slabs_kernel, dim3(g1((long)rows * C / 4).x, batch), dim3(256), 0, st, in, ld_in, in_bs, out, ld_out, out_bs, rows, C);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_add_rows(float* a, long lda, const float* b, long ldb, int rows, int C, cudaStream_t st) {

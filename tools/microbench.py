@@ -24,7 +24,7 @@ def main():
     out = {}
     text = [255] + [(7 * i) % 700 + 1 for i in range(145)] + [0]
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    for ns in (1, 2, 4, 8):
+    for ns in (() if only == "s3b" else (1, 2, 4, 8)):
         t0 = time.time()
         slots = [eng.t3_open(v, text, seed=i, max_new=1000) for i in range(ns)]
         torch.cuda.synchronize()
@@ -55,7 +55,7 @@ def main():
                                   "hbm_gbs": (wbytes + kvbytes) / (ms * 1e-3) / 1e9}
         for s in slots:
             eng.t3_close(s)
-    for n in (() if only == "t3" else (35, 70, 140, 245)):
+    for n in (() if only in ("t3", "s3b") else (35, 70, 140, 245)):
         toks = [(i * 37) % 6561 for i in range(n)]
         for _ in range(2):
             eng.s3gen_infer(v, toks, seed=1)
@@ -76,6 +76,22 @@ def main():
         T = 2 * (194 + n)
         flops = 2 * (66.08e6 + 57344 * T) * T * 20
         out[f"s3gen_n{n}"] = {"ms": ms, "flow_eager_ms": fms, "T": T, "cfm_tflops_vs_graph_total": flops / (ms * 1e-3) / 1e12, "audio_s": n * 0.04}
+    if only in ("", "s3b"):
+        for n in (35, 140):
+            toks = [[(i * 37 + 11 * b) % 6561 for i in range(n + (b % 3))] for b in range(8)]
+            for B in (1, 2, 4, 8):
+                calls = [(v, toks[b], None, 1 + b) for b in range(B)]
+                eng.s3gen_infer_batch(calls)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                a, b_ = ev(), ev()
+                a.record()
+                for _ in range(2):
+                    eng.s3gen_infer_batch(calls)
+                b_.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b_) / 2
+                out[f"s3gen_batch_n{n}_B{B}"] = {"ms": ms, "wall_ms": (time.time() - t0) * 500, "ms_per_call": ms / B, "audio_s_per_s": B * n * 0.04 / (ms * 1e-3)}
     out["gemm_tc_launches"] = int(eng.lib.cbx_gemm_tc_launches())
     print(json.dumps(out, indent=1))
     eng.close()

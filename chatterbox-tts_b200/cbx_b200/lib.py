@@ -49,6 +49,7 @@ SIGNATURES = {
     "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
     "cbx_gpu_launches": (_L, [_P]),
     "cbx_gemm_tc_launches": (C.c_longlong, []),
+    "cbx_attn_tc_launches": (C.c_longlong, []),
     "cbx_gemm_tc_trace": (_I, [_P]),
     "cbx_t3_mega_trace": (_I, [_P]),
     "cbx_t3_mega_prof": (_I, [_P]),

@@ -197,3 +197,5 @@ struct AttnParams {
 };
 void launch_attention(const AttnParams& p, cudaStream_t st);
 void attention_init();
+void attention_tc_init();
+bool launch_attention_tc(const AttnParams& p, cudaStream_t st);   // false: not applicable (bias / causal / alignment)

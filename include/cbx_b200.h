@@ -116,6 +116,8 @@ int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const fl
 int64_t cbx_gpu_launches(cbx_engine* e);
 /* GEMM launches that took the tcgen05/TMA path (process-wide; 0 means the mma.sync fallback served everything) */
 long long cbx_gemm_tc_launches(void);
+/* attention launches served by the tcgen05 flash-attention kernel (process-wide) */
+long long cbx_attn_tc_launches(void);
 /* debug: %globaltimer stamps (ns) of the last tcgen05 GEMM's CTA 0: start, setup done, first TMA landed, MMAs issued,
  * accumulator ready, epilogue done, teardown */
 int cbx_gemm_tc_trace(unsigned long long* out_h);

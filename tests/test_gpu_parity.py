@@ -62,7 +62,7 @@ def test_gemm_op(dev, M, N, K):
         assert _rel(out, ref) < 1e-5
 
 
-@pytest.mark.parametrize("T,H,B,causal", [(64, 8, 2, 0), (100, 8, 1, 0), (333, 16, 2, 1), (1000, 8, 2, 0)])
+@pytest.mark.parametrize("T,H,B,causal", [(64, 8, 2, 0), (100, 8, 1, 0), (333, 16, 2, 1), (1000, 8, 2, 0), (128, 8, 1, 0), (458, 8, 16, 0), (129, 1, 1, 0)])
 def test_attention_op(dev, T, H, B, causal):
     from cbx_b200 import lib as L
     lib = L.load()
@@ -74,6 +74,11 @@ def test_attention_op(dev, T, H, B, causal):
     q, k, v = (t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(H * 64, dim=-1))
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=bool(causal)).transpose(1, 2).reshape(B, T, H * 64)
     assert _rel(out.float(), ref) < 1e-2   # P is rounded to bf16 before the PV product
+    if not causal:   # full attention without bias must be served by the tcgen05 kernel
+        before = lib.cbx_attn_tc_launches()
+        L.check(lib.cbx_op_attention(qkv.data_ptr(), out.data_ptr(), T, H, B, causal, None))
+        torch.cuda.synchronize()
+        assert lib.cbx_attn_tc_launches() == before + 1
 
 
 def _text(L, seed=3):

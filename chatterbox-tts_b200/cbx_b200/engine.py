@@ -202,10 +202,27 @@ class T3Scheduler(threading.Thread):
             self.lock.notify_all()
 
 
+class _S3Job:
+    """One S3Gen call in flight: `dep` is the job whose source output is this call's cache_source (the previous slice of
+    the same text chunk under the "full" overlap strategy), or None."""
+    __slots__ = ("voice", "toks", "dep", "seed", "done", "out", "err", "dropped")
+
+    def __init__(self, voice, toks, dep, seed):
+        self.voice, self.toks, self.dep, self.seed = voice, toks, dep, seed
+        self.done, self.out, self.err, self.dropped = threading.Event(), None, None, False
+
+    def wait(self):
+        self.done.wait()
+        if self.err is not None:
+            raise self.err
+        return self.out
+
+
 class S3GenBatcher(threading.Thread):
-    """Collects the S3Gen calls that are pending at the same moment (slices of concurrent requests, or of the text
-    chunks of one request) and runs them as one batch: while a batch is on the GPU the next one accumulates.  A single
-    pending call takes the per-lane CUDA-graph path."""
+    """Collects the S3Gen calls that are pending at the same moment (slices of concurrent requests, of the text chunks
+    of one request, and consecutive slices of one chunk) and runs them as one batch: while a batch is on the GPU the
+    next one accumulates.  A single pending call takes the per-lane CUDA-graph path.  Jobs are served in submission
+    order, so a job's dependency is either finished or an earlier member of the same batch (chained on the device)."""
 
     def __init__(self, native, max_batch: int = 8):
         super().__init__(daemon=True, name="cbx-s3gen-batcher")
@@ -218,16 +235,21 @@ class S3GenBatcher(threading.Thread):
         self.batches = collections.Counter()   # batch size -> count (bench / tests)
         self.start()
 
-    def infer(self, voice, toks, cache_source, seed):
-        """Blocking call with s3gen_infer's result; the tensors are complete (the batcher synchronised its stream)."""
-        job = {"args": (voice, toks, cache_source, seed), "done": threading.Event(), "out": None, "err": None}
+    def submit(self, voice, toks, dep: Optional[_S3Job], seed) -> _S3Job:
+        job = _S3Job(voice, toks, dep, seed)
         with self.cv:
             self.jobs.append(job)
             self.cv.notify_all()
-        job["done"].wait()
-        if job["err"] is not None:
-            raise job["err"]
-        return job["out"]
+        return job
+
+    def infer(self, voice, toks, cache_source, seed):
+        """Blocking single call (cache_source given as a finished tensor)."""
+        dep = None
+        if cache_source is not None:
+            dep = _S3Job(voice, None, None, 0)
+            dep.out = (None, cache_source)
+            dep.done.set()
+        return self.submit(voice, toks, dep, seed).wait()
 
     def run(self):
         st = None
@@ -240,27 +262,47 @@ class S3GenBatcher(threading.Thread):
                     self.cv.wait(0.5)
                 if not self.running:
                     for j in self.jobs:
-                        j["err"] = RuntimeError("engine is shutting down")
-                        j["done"].set()
+                        j.err = RuntimeError("engine is shutting down")
+                        j.done.set()
                     return
                 batch = [self.jobs.popleft() for _ in range(min(len(self.jobs), self.max_batch if self.can_batch else 1))]
+            live = []
+            for j in batch:
+                # a dropped job (cancelled request) or one whose dependency failed is not run
+                if j.dropped or (j.dep is not None and (j.dep.dropped or j.dep.err is not None)):
+                    j.dropped, j.err = True, (j.dep.err if j.dep is not None and j.dep.err is not None else _Cancelled())
+                    j.done.set()
+                else:
+                    live.append(j)
+            if not live:
+                continue
             try:
                 with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
-                    if len(batch) == 1:
-                        v, t, c, sd = batch[0]["args"]
-                        outs = [self.native.s3gen_infer(v, t, cache_source=c, seed=sd)]
+                    def cache_of(j, pos):
+                        if j.dep is None:
+                            return None
+                        if j.dep.done.is_set():
+                            return j.dep.out[1]
+                        return pos[id(j.dep)]           # earlier member of this batch: chained on the device
+                    if len(live) == 1:
+                        j = live[0]
+                        outs = [self.native.s3gen_infer(j.voice, j.toks, cache_source=cache_of(j, {}), seed=j.seed)]
                     else:
-                        outs = self.native.s3gen_infer_batch([j["args"] for j in batch])
+                        pos, calls = {}, []
+                        for i, j in enumerate(live):
+                            calls.append((j.voice, j.toks, cache_of(j, pos), j.seed))
+                            pos[id(j)] = i
+                        outs = self.native.s3gen_infer_batch(calls)
                     if st is not None:
                         st.synchronize()
-                self.batches[len(batch)] += 1
-                for j, o in zip(batch, outs):
-                    j["out"] = o
+                self.batches[len(live)] += 1
+                for j, o in zip(live, outs):
+                    j.out = o
             except BaseException as ex:
-                for j in batch:
-                    j["err"] = ex
-            for j in batch:
-                j["done"].set()
+                for j in live:
+                    j.err = ex
+            for j in live:
+                j.done.set()
 
     def stop(self):
         self.running = False
@@ -336,7 +378,7 @@ class TextToSpeechEngine:
         # latency-bound and already span the SMs) and cost workspace + graph captures per lane
         self.native_kwargs = dict(max_streams=max(8, n), n_lanes=2)
         # text chunks of one request that may be in flight at once (T3 decoding + S3Gen), ahead of the chunk being emitted
-        self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "4"))
+        self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "8"))
         self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=4 * max(8, n), thread_name_prefix="cbx-chunk")
         self.s3gen: Optional[S3GenBatcher] = None
         self.t3_slots: Optional[PrioritySlots] = None
@@ -487,6 +529,7 @@ class TextToSpeechEngine:
                 emit(host.numpy().tobytes())
 
             cancelled = (lambda: token is not None and token.is_cancelled())
+            jobs = []                                         # every S3Gen job of this request (dropped on cancel)
             streams = [None] * len(chunks)
             outq = [queue.Queue() for _ in chunks]           # per chunk: (cur, last) items, then None (or an exception)
             first_slice_ready = threading.Event()            # chunk 0 has the tokens of its first slice (or is done)
@@ -509,7 +552,7 @@ class TextToSpeechEngine:
                         max_new = max(1, self.sampling.tokens_per_word * len(chunks[ci].split()))
                     s = streams[ci] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + ci, max_new)
                     is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
-                    consumed, slice_idx, acc, cache_source, prev_len = 0, 0, [], None, 0
+                    consumed, slice_idx, acc, prev_job = 0, 0, [], None
                     while not stop.is_set():
                         if not self._wait_tokens(s, consumed + slice_len + look_ahead, token):
                             break
@@ -541,19 +584,12 @@ class TextToSpeechEngine:
                             continue
                         if len(toks) < 3:
                             toks = toks + [0] * (3 - len(toks))
-                        wav, src = self.s3gen.infer(voice, toks, cache_source, base_seed + 7919 * ci + slice_idx)
-                        cur = wav[0]
-                        if overlap == "full":
-                            cache_source = src
-                            full_len = cur.shape[0]
-                            if not first_slice:
-                                cur = cur[prev_len:]
-                            prev_len = full_len
-                        if is_first_chunk and first_slice and lead > 0 and cur.shape[0] > lead:
-                            cur = cur[lead:]
-                        if is_last_chunk and last and trail > 0 and cur.shape[0] > trail:
-                            cur = cur[:-trail]
-                        outq[ci].put((cur, last))
+                        # submitted without waiting for the previous slice: its source cache is chained (job dependency), so
+                        # consecutive slices of this chunk can ride in the same batch when T3 runs ahead of S3Gen
+                        job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx)
+                        prev_job = job
+                        jobs.append(job)
+                        outq[ci].put((job, first_slice, last))
                         if last:
                             break
                 except BaseException as ex:
@@ -587,6 +623,7 @@ class TextToSpeechEngine:
             threading.Thread(target=opener, daemon=True, name="cbx-opener").start()
             try:
                 for ci in range(len(chunks)):
+                    prev_len = 0
                     while True:
                         item = outq[ci].get()
                         if item is None:
@@ -595,7 +632,18 @@ class TextToSpeechEngine:
                             raise item
                         if cancelled():
                             continue
-                        cur, last = item
+                        job, first_slice, last = item
+                        wav, src = job.wait()
+                        cur = wav[0]
+                        if overlap == "full":                 # keep only what the previous slice has not already produced
+                            full_len = cur.shape[0]
+                            if not first_slice:
+                                cur = cur[prev_len:]
+                            prev_len = full_len
+                        if ci == 0 and first_slice and lead > 0 and cur.shape[0] > lead:
+                            cur = cur[lead:]
+                        if ci == len(chunks) - 1 and last and trail > 0 and cur.shape[0] > trail:
+                            cur = cur[:-trail]
                         n = cur.shape[0]
                         # crossfade state machine (reference :710-746)
                         if not first_sent:
@@ -623,6 +671,9 @@ class TextToSpeechEngine:
                     send(prev_tail, prev_tail.shape[0], None)     # reference `finally` flush (:756-760)
             finally:
                 stop.set()
+                for j in jobs:
+                    if not j.done.is_set():
+                        j.dropped = True
                 for s in streams:
                     if s is not None and not s.finished:
                         sched.cancel(s)

@@ -155,8 +155,10 @@ class NativeEngine:
         return (wav, src, mel) if return_mel else (wav, src)
 
     def s3gen_infer_batch(self, calls, return_mel=False):
-        """calls: list of (voice, tokens, cache_source or None, seed) -> list of (wav, source[, mel]); one batched
-        token->mel pass for all calls (cbx_s3gen_infer_batch), results equal s3gen_infer call by call."""
+        """calls: list of (voice, tokens, cache_source, seed) -> list of (wav, source[, mel]); one batched token->mel pass
+        for all calls (cbx_s3gen_infer_batch), results equal s3gen_infer call by call.  cache_source is a tensor, None, or
+        the index of an EARLIER call of this batch whose source output is the cache (the vocoder runs call by call in
+        order, so consecutive slices of one text chunk can share a batch)."""
         dev = torch.device("cuda", self.device)
         arr = (L.S3GenCall * len(calls))()
         keep, outs = [], []
@@ -166,8 +168,13 @@ class NativeEngine:
             wav = torch.empty(1, 960 * n, device=dev, dtype=torch.float32)
             src = torch.empty(1, 1, 960 * n, device=dev, dtype=torch.float32)
             mel = torch.empty(2 * n, 80, device=dev, dtype=torch.float32) if return_mel else None
-            m = 0 if cache_source is None else cache_source.shape[-1]
-            cs = cache_source.contiguous() if m else None
+            if isinstance(cache_source, int):
+                assert 0 <= cache_source < i, "a chained cache_source must refer to an earlier call of the batch"
+                cs = outs[cache_source][1]
+                m = cs.shape[-1]
+            else:
+                m = 0 if cache_source is None else cache_source.shape[-1]
+                cs = cache_source.contiguous() if m else None
             keep.append((tok, cs))
             arr[i] = L.S3GenCall(voice, tok.ctypes.data, n, cs.data_ptr() if m else None, m, wav.data_ptr(), src.data_ptr(),
                                  mel.data_ptr() if return_mel else None, seed)

@@ -139,6 +139,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def t3_step_leg(eng, pk):
+    import torch
+    nat = eng.native
+    out = {}
+    text = [255] + [(7 * i) % 700 + 1 for i in range(145)] + [0]
+    for name, persistent in (("gemv_kernels", False), ("persistent_kernel", True)):
+        try:
+            nat.t3_set_persistent(persistent)
+            slot = nat.t3_open(eng.voice_cache["default"], text, seed=1, max_new=1000)
+            nat.t3_step([slot], 20)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            nat.t3_step([slot], 200)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 200
+            nat.t3_close(slot)
+            pos = 34 + len(text) + 1 + 120
+            nbytes = 30 * 16779264 * 2 + 8208 * 1024 * 2 + 122880 * pos * 2
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            out[name] = {"ms_per_step": ms, "bytes_per_step": nbytes, "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"],
+                         "tokens_per_s": 1e3 / ms}
+        except Exception as ex:   # report, never hide
+            out[name] = {"error": str(ex)}
+    nat.t3_set_persistent(False)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 leg
 def run_b200(args):
     import ctypes as C
@@ -274,6 +303,18 @@ def run_b200(args):
         gv = next((k for k in kern if k["kernel"].startswith("gemv")), None)
         if gv:
             roof["t3_decode_gemv"] = {"bound": "hbm", "achieved": gv["rate"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gv["rate"] / pk["hbm_gbs"]}
+        # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), when there is one
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as fh:
+                tr = json.load(fh)
+            key = "gemm_tc_kernel" if dom == 0 else ("attn_tc_kernel" if dom == 1 else "gemv_kernel")
+            if key in tr:
+                roof["traffic"] = tr[key]["dram_bytes_per_launch"]
+                roof["traffic_note"] = tr[key].get("note", "")
+        except Exception:
+            pass
+        # T3 decode step alone, both implementations (200 steps of one stream, CUDA events): bytes = weights + KV read
+        roof["t3_step"] = t3_step_leg(eng, pk)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             a, dt, th = oracle_sample()
@@ -283,6 +324,7 @@ def run_b200(args):
         line = {"metric": "audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "configs[1]: single stream per GPU, 200-word paragraph streamed in chunks, cfg 0.5, temp 0.8, slice 35, overlap full, crossfade 30 ms, 10 speech tokens/word, fixed seed",
+                           "chunk_parallelism": eng.chunk_parallelism,
                            "audio_s_per_step": audio_s / args.steps, "weights": "random-init seed 0", "l2": "no flush needed: every T3 step streams 1.02 GB of weights (> 126 MB L2)"},
                 "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(4 * (WORDS * 6 + WORDS * TOK_PER_WORD * 4)), "d2h_bytes_per_step": int(e2e_bytes / args.steps + 4 * WORDS * TOK_PER_WORD),
@@ -292,6 +334,7 @@ def run_b200(args):
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_concurrent:
             line["concurrent8"] = await concurrent_leg()
+        line["s3gen_batch_sizes"] = {str(k): int(v) for k, v in sorted(eng.s3gen.batches.items())}
         print(json.dumps(line), flush=True)
 
     asyncio.run(main())

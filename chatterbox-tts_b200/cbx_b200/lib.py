@@ -36,6 +36,7 @@ SIGNATURES = {
     "cbx_voice_drop": (_I, [_P, _I]),
     "cbx_t3_open": (_I, [_P, _I, _P, _I, _F, _F, _F, _F, _F, _U64, _I, C.POINTER(_I), _P]),
     "cbx_t3_step": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cbx_t3_set_persistent": (_I, [_P, _I]),
     "cbx_t3_poll": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _P]),
     "cbx_t3_tokens": (_I, [_P, _I, _I, _I, _P, _P]),
     "cbx_t3_logits": (_I, [_P, _I, _P, _P]),

@@ -119,6 +119,9 @@ class NativeEngine:
             assert noise.is_cuda and noise.dtype == torch.float32 and noise.numel() == n_steps * len(s) * SPEECH_V
         L.check(self.lib.cbx_t3_step(self.h, s.ctypes.data, len(s), n_steps, nptr, _stream_ptr()))
 
+    def t3_set_persistent(self, on: bool):
+        L.check(self.lib.cbx_t3_set_persistent(self.h, 1 if on else 0))
+
     def t3_poll(self, slot):
         n, d = C.c_int(), C.c_int()
         L.check(self.lib.cbx_t3_poll(self.h, slot, C.byref(n), C.byref(d), _stream_ptr()))

@@ -221,6 +221,15 @@ int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps,
     CBX_API_END
 }
 
+int cbx_t3_set_persistent(cbx_engine* e, int on) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e, "null engine");
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    CBX_REQUIRE(!on || e->t3.mega_ok, "persistent T3 kernel is not available on this device");
+    e->t3.mega = on != 0;
+    CBX_API_END
+}
+
 int cbx_t3_poll(cbx_engine* e, int slot, int* n_generated, int* done, void* stream) {
     CBX_API_BEGIN
     CBX_REQUIRE(e && slot >= 0 && slot < e->cfg.max_streams, "slot out of range");

@@ -91,12 +91,14 @@ void t3_alloc(cbx_engine* e) {
     std::vector<MegaLayer> hl(c.t3_layers);
     for (int i = 0; i < c.t3_layers; i++) hl[i] = MegaLayer{m.layers[i].wqkv_f, m.layers[i].wo_f, m.layers[i].wgu_f, m.layers[i].wd_f, m.layers[i].ln1, m.layers[i].ln2};
     CBX_CHECK(cudaMemcpy(m.d_layers, hl.data(), hl.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
-    // CBX_T3_MEGA=1 runs the decode step as one persistent kernel (t3_mega.cu): 0.57 ms instead of 0.95 ms per step for one
-    // stream.  It is opt-in because a cooperative grid owns all SMs for the whole step, so the S3Gen kernels that otherwise
-    // share the GPU with T3 on other streams have to wait: measured on the pipelined 200-word paragraph 3.64 s vs 3.17 s, and
-    // with 16 rows the per-projection GEMV kernels are faster (1.55 ms vs 2.35 ms).  See DESIGN.md section 6.
+    // The decode step has two implementations: per-projection GEMV kernels (default) and one persistent kernel
+    // (t3_mega.cu; 0.57 ms instead of 0.95 ms per step for one stream).  The persistent kernel is opt-in (CBX_T3_MEGA=1 or
+    // cbx_t3_set_persistent) because a cooperative grid owns all SMs for the whole step, so the S3Gen kernels that
+    // otherwise share the GPU with T3 on other streams have to wait (measured on the pipelined 200-word paragraph: 3.64 s
+    // vs 3.17 s), and with 16 rows the GEMV kernels are faster (1.55 ms vs 2.35 ms).  See DESIGN.md section 6.
+    m.mega_ok = t3_mega_init(m.max_pages, hl, m.head_f, T3_VPAD / 16);
     const char* en = getenv("CBX_T3_MEGA");
-    m.mega = (en && en[0] == '1') && t3_mega_init(m.max_pages, hl, m.head_f, T3_VPAD / 16);
+    m.mega = m.mega_ok && en && en[0] == '1';
 }
 
 static void gemm_lin(const Lin& l, const bf16* A, long lda, int M, float* outF, bf16* outB, long ldc, cudaStream_t st,
@@ -277,7 +279,8 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
     if (noise_dev || prof_enabled()) {
         for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev ? noise_dev + (long)i * n * T3_V : nullptr, st);
     } else {
-        auto it = m.step_graphs.find(n);
+        const int gkey = n + (m.mega ? 1000 : 0);
+        auto it = m.step_graphs.find(gkey);
         if (it == m.step_graphs.end()) {
             cudaGraph_t graph;
             CBX_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -286,7 +289,7 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
             cudaGraphExec_t exec;
             CBX_CHECK(cudaGraphInstantiate(&exec, graph, 0));
             CBX_CHECK(cudaGraphDestroy(graph));
-            it = m.step_graphs.emplace(n, exec).first;
+            it = m.step_graphs.emplace(gkey, exec).first;
         }
         for (int i = 0; i < n_steps; i++) CBX_CHECK(cudaGraphLaunch(it->second, st));
     }

@@ -71,6 +71,9 @@ int cbx_t3_open(cbx_engine* e, int voice, const int32_t* text_ids_h, int n_text,
 /* next() on up to max_streams generators at once: n_steps decode steps for the given slots (batched rows).
  * noise_d: optional explicit Exp(1) sampling noise [n_steps][n_slots][8194] (parity tests); NULL = Philox(seed). */
 int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps, const float* noise_d, void* stream);
+/* selects the decode-step implementation: 0 = per-projection GEMV kernels (default), 1 = one persistent kernel per step
+ * (lower latency for one or two streams, but it owns every SM while it runs; also enabled by CBX_T3_MEGA=1) */
+int cbx_t3_set_persistent(cbx_engine* e, int on);
 /* blocking reads of a stream's progress / tokens / last-step logits (2 x 8194: cond row, uncond row) */
 int cbx_t3_poll(cbx_engine* e, int slot, int* n_generated, int* done, void* stream);
 int cbx_t3_tokens(cbx_engine* e, int slot, int from, int count, int32_t* out_h, void* stream);

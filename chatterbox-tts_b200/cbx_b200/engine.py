@@ -218,22 +218,30 @@ class _S3Job:
         return self.out
 
 
-class S3GenBatcher(threading.Thread):
+class S3GenBatcher:
     """Collects the S3Gen calls that are pending at the same moment (slices of concurrent requests, of the text chunks
     of one request, and consecutive slices of one chunk) and runs them as one batch: while a batch is on the GPU the
-    next one accumulates.  A single pending call takes the per-lane CUDA-graph path.  Jobs are served in submission
-    order, so a job's dependency is either finished or an earlier member of the same batch (chained on the device)."""
+    next one accumulates.  Jobs are taken in submission
+    order; a job runs only when its dependency is finished or an earlier member of the same batch (chained on the
+    device).  `workers` threads can run batches concurrently (the native side has two batch workspaces); measured on the
+    pipelined workloads one worker is better (two fragment the batches: 41 vs 54 audio-s/s at 8 concurrent streams)."""
 
-    def __init__(self, native, max_batch: int = 8):
-        super().__init__(daemon=True, name="cbx-s3gen-batcher")
-        self.native, self.max_batch = native, max_batch
+    def __init__(self, native, max_batch: int = None, workers: int = None):
+        self.native = native
+        self.max_batch = max_batch or int(os.environ.get("CBX_S3GEN_MAX_BATCH", "8"))
         self.on_gpu = not getattr(native, "is_fake", False)
         self.can_batch = hasattr(native, "s3gen_infer_batch")
         self.jobs = collections.deque()
         self.cv = threading.Condition()
         self.running = True
         self.batches = collections.Counter()   # batch size -> count (bench / tests)
-        self.start()
+        n = workers or int(os.environ.get("CBX_S3GEN_WORKERS", "1"))
+        # after the first pending job shows up, wait this long for companions (slices of concurrent requests become ready
+        # within a decode round of each other): one batch of 8 beats a single call followed by a batch of 7
+        self.gather_s = float(os.environ.get("CBX_S3GEN_GATHER_MS", "2")) * 1e-3
+        self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
+        for t in self.threads:
+            t.start()
 
     def submit(self, voice, toks, dep: Optional[_S3Job], seed) -> _S3Job:
         job = _S3Job(voice, toks, dep, seed)
@@ -251,6 +259,21 @@ class S3GenBatcher(threading.Thread):
             dep.done.set()
         return self.submit(voice, toks, dep, seed).wait()
 
+    def _take(self):
+        """Under self.cv: the longest prefix-ordered set of runnable jobs, at most max_batch."""
+        batch, members, keep = [], set(), collections.deque()
+        limit = self.max_batch if self.can_batch else 1
+        while self.jobs:
+            j = self.jobs.popleft()
+            ready = j.dep is None or j.dep.done.is_set() or id(j.dep) in members
+            if ready and len(batch) < limit:
+                batch.append(j)
+                members.add(id(j))
+            else:
+                keep.append(j)      # its dependency is in another worker's batch (or the batch is full): stays queued, in order
+        self.jobs = keep
+        return batch
+
     def run(self):
         st = None
         if self.on_gpu:
@@ -258,14 +281,19 @@ class S3GenBatcher(threading.Thread):
             st = torch.cuda.Stream()
         while True:
             with self.cv:
-                while self.running and not self.jobs:
-                    self.cv.wait(0.5)
+                batch = []
+                while self.running:
+                    if self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch:
+                        self.cv.wait(self.gather_s)
+                    batch = self._take() if self.jobs else []
+                    if batch:
+                        break
+                    self.cv.wait(0.01 if self.jobs else 0.5)
                 if not self.running:
-                    for j in self.jobs:
+                    for j in list(self.jobs) + batch:
                         j.err = RuntimeError("engine is shutting down")
                         j.done.set()
                     return
-                batch = [self.jobs.popleft() for _ in range(min(len(self.jobs), self.max_batch if self.can_batch else 1))]
             live = []
             for j in batch:
                 # a dropped job (cancelled request) or one whose dependency failed is not run
@@ -274,35 +302,40 @@ class S3GenBatcher(threading.Thread):
                     j.done.set()
                 else:
                     live.append(j)
-            if not live:
-                continue
-            try:
-                with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
-                    def cache_of(j, pos):
-                        if j.dep is None:
-                            return None
-                        if j.dep.done.is_set():
+            if live:
+                try:
+                    with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                        def cache_of(j, pos):
+                            if j.dep is None:
+                                return None
+                            if id(j.dep) in pos:
+                                return pos[id(j.dep)]       # earlier member of this batch: chained on the device
                             return j.dep.out[1]
-                        return pos[id(j.dep)]           # earlier member of this batch: chained on the device
-                    if len(live) == 1:
-                        j = live[0]
-                        outs = [self.native.s3gen_infer(j.voice, j.toks, cache_source=cache_of(j, {}), seed=j.seed)]
-                    else:
-                        pos, calls = {}, []
-                        for i, j in enumerate(live):
-                            calls.append((j.voice, j.toks, cache_of(j, pos), j.seed))
-                            pos[id(j)] = i
-                        outs = self.native.s3gen_infer_batch(calls)
-                    if st is not None:
-                        st.synchronize()
-                self.batches[len(live)] += 1
-                for j, o in zip(live, outs):
-                    j.out = o
-            except BaseException as ex:
+                        if not self.can_batch:
+                            j = live[0]
+                            outs = [self.native.s3gen_infer(j.voice, j.toks, cache_source=cache_of(j, {}), seed=j.seed)]
+                        else:
+                            # one call also goes through the batch entry point (plain launches): it is as fast as the per-lane
+                            # CUDA graph of cbx_s3gen_infer (the GPU, not the launch rate, bounds a call) and never stalls on
+                            # capturing a graph for a token count it has not seen yet
+                            pos, calls = {}, []
+                            for i, j in enumerate(live):
+                                calls.append((j.voice, j.toks, cache_of(j, pos), j.seed))
+                                pos[id(j)] = i
+                            outs = self.native.s3gen_infer_batch(calls)
+                        if st is not None:
+                            st.synchronize()
+                    with self.cv:
+                        self.batches[len(live)] += 1
+                    for j, o in zip(live, outs):
+                        j.out = o
+                except BaseException as ex:
+                    for j in live:
+                        j.err = ex
                 for j in live:
-                    j.err = ex
-            for j in live:
-                j.done.set()
+                    j.done.set()
+            with self.cv:
+                self.cv.notify_all()     # jobs that were waiting for this batch's outputs are runnable now
 
     def stop(self):
         self.running = False
@@ -381,6 +414,7 @@ class TextToSpeechEngine:
         self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "8"))
         self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=4 * max(8, n), thread_name_prefix="cbx-chunk")
         self.s3gen: Optional[S3GenBatcher] = None
+        self._pinned_pool: queue.Queue = queue.Queue()
         self.t3_slots: Optional[PrioritySlots] = None
         self.native_kwargs.update(native_kwargs or {})
         self.native: Optional[NativeEngine] = None
@@ -475,6 +509,19 @@ class TextToSpeechEngine:
         self.put_conditionals(voice_id, c["t3"], c["gen"])
 
     # ------------------------------------------------------------------ helpers
+    def _pinned_get(self):
+        """A pinned int16 staging buffer (one S3Gen call of PCM at most) from the engine's pool, or None without a GPU."""
+        if self._backend is not None or self.device_sink:
+            return None
+        try:
+            return self._pinned_pool.get_nowait()
+        except queue.Empty:
+            return torch.empty(960 * 1100, dtype=torch.int16, pin_memory=True)
+
+    def _pinned_put(self, buf):
+        if buf is not None:
+            self._pinned_pool.put(buf)
+
     def _wait_tokens(self, s: _T3Stream, n: int, token: Optional[CancellationToken]):
         """Blocks until the stream holds >= n tokens or is finished."""
         with s.cv:
@@ -525,14 +572,27 @@ class TextToSpeechEngine:
                 if self.device_sink:
                     emit(int(n_out))
                     return
-                host = pcm.cpu()          # stream-ordered D2H of n_out int16 samples
-                emit(host.numpy().tobytes())
+                # stream-ordered D2H into a pinned staging buffer: one async copy + one stream sync (a pageable .cpu() is a
+                # multi-call staged copy that queues behind the launch bursts of the S3Gen thread inside the driver)
+                if pinned is not None and n_out <= pinned.shape[0]:
+                    pinned[:n_out].copy_(pcm, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    data = pinned[:n_out].numpy().tobytes()
+                else:
+                    data = pcm.cpu().numpy().tobytes()
+                if not first_sent:
+                    trace("first_pcm_host")
+                emit(data)
 
+            pinned = self._pinned_get()
             cancelled = (lambda: token is not None and token.is_cancelled())
+            tr = self.stats.setdefault("trace", collections.deque(maxlen=64))
+            trace = (lambda label: tr.append((label, round((time.time() - t_start) * 1e3, 1))))
+            trace("start")
             jobs = []                                         # every S3Gen job of this request (dropped on cancel)
             streams = [None] * len(chunks)
             outq = [queue.Queue() for _ in chunks]           # per chunk: (cur, last) items, then None (or an exception)
-            first_slice_ready = threading.Event()            # chunk 0 has the tokens of its first slice (or is done)
+            first_slice_ready = threading.Event()            # chunk 0's first slice has been synthesised (or chunk 0 is done)
             window = threading.Semaphore(max(1, self.chunk_parallelism))   # chunks in flight ahead of the emitter
             stop = threading.Event()
 
@@ -551,6 +611,8 @@ class TextToSpeechEngine:
                     if self.sampling.tokens_per_word:
                         max_new = max(1, self.sampling.tokens_per_word * len(chunks[ci].split()))
                     s = streams[ci] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + ci, max_new)
+                    if ci == 0:
+                        trace("t3_open")
                     is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
                     consumed, slice_idx, acc, prev_job = 0, 0, [], None
                     while not stop.is_set():
@@ -559,8 +621,6 @@ class TextToSpeechEngine:
                         if s.finished and have_slot:          # decoding is over: the slot can serve the next chunk
                             self.t3_slots.release()
                             have_slot = False
-                        if ci == 0:
-                            first_slice_ready.set()
                         avail = len(s.tokens) - consumed
                         if avail >= slice_len + look_ahead:
                             new, last = s.tokens[consumed: consumed + slice_len], False
@@ -586,6 +646,8 @@ class TextToSpeechEngine:
                             toks = toks + [0] * (3 - len(toks))
                         # submitted without waiting for the previous slice: its source cache is chained (job dependency), so
                         # consecutive slices of this chunk can ride in the same batch when T3 runs ahead of S3Gen
+                        if ci == 0 and first_slice:
+                            trace("slice1_tokens")
                         job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx)
                         prev_job = job
                         jobs.append(job)
@@ -605,7 +667,8 @@ class TextToSpeechEngine:
 
             def opener():
                 """Starts the chunk workers in order, at most `chunk_parallelism` ahead of the emitter; chunks after the
-                first wait until chunk 0 holds its first slice, so the first audio is not slowed down by their prefills."""
+                first wait until chunk 0's first slice has been synthesised, so the first audio does not compete with their
+                prefills and decode steps for the GPU."""
                 for ci in range(len(chunks)):
                     while not window.acquire(timeout=0.05):
                         if stop.is_set() or cancelled():
@@ -633,7 +696,13 @@ class TextToSpeechEngine:
                         if cancelled():
                             continue
                         job, first_slice, last = item
-                        wav, src = job.wait()
+                        try:
+                            wav, src = job.wait()
+                        except BaseException:
+                            first_slice_ready.set()
+                            raise
+                        if not first_slice_ready.is_set():
+                            trace("slice1_audio")
                         cur = wav[0]
                         if overlap == "full":                 # keep only what the previous slice has not already produced
                             full_len = cur.shape[0]
@@ -664,6 +733,8 @@ class TextToSpeechEngine:
                                 if prev_tail is not None:
                                     send(prev_tail, prev_tail.shape[0], None)
                                 prev_tail = cur[n - fade_len:] if (fade_len > 0 and n > fade_len) else cur
+                        first_slice_ready.set()          # later chunks may start: the first audio no longer competes with them
+                    first_slice_ready.set()
                     window.release()
                     if cancelled():
                         break
@@ -671,6 +742,7 @@ class TextToSpeechEngine:
                     send(prev_tail, prev_tail.shape[0], None)     # reference `finally` flush (:756-760)
             finally:
                 stop.set()
+                self._pinned_put(pinned)
                 for j in jobs:
                     if not j.done.is_set():
                         j.dropped = True

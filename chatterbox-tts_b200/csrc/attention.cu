@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
     const int g = lane >> 2, tg = lane & 3;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * BQ;
-    const int klen_raw = p.kv_len[(b / p.kv_div) & 7];
+    const int klen_raw = p.kv_len[(b / p.kv_div) & 15];
     const int Tk = klen_raw > 0 ? klen_raw : p.T;   // valid keys (and valid queries) of this sequence
     if (q0 >= Tk) return;                           // padded query tile: its rows are never consumed
     const bf16* Q = p.q + (long)b * p.q_bs + h * D;

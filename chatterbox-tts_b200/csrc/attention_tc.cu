@@ -68,7 +68,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 struct AttnTcArgs {
     bf16* o; long ldo, o_bs;
     int T, H; float sl2;           // sl2 = scale * log2(e): scores are kept in the log2 domain
-    int kv_len[8]; int kv_div;
+    int kv_len[16]; int kv_div;
 };
 
 __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qt * BQ;
-    const int klen_raw = p.kv_len[(b / p.kv_div) & 7];
+    const int klen_raw = p.kv_len[(b / p.kv_div) & 15];
     const int Tk = klen_raw > 0 ? klen_raw : p.T;
     pdl_launch_dependents();
     if (q0 >= Tk) return;                           // padded query tile of a ragged batch: never consumed
@@ -286,7 +286,7 @@ bool launch_attention_tc(const AttnParams& p, cudaStream_t st) {
         !make_map(&tv, p.v, p.ldv, p.v_bs, p.T, p.H, p.batch)) return false;
     AttnTcArgs a;
     a.o = p.o; a.ldo = p.ldo; a.o_bs = p.o_bs; a.T = p.T; a.H = p.H; a.sl2 = p.scale * 1.4426950408889634f;
-    for (int i = 0; i < 8; i++) a.kv_len[i] = p.kv_len[i];
+    for (int i = 0; i < 16; i++) a.kv_len[i] = p.kv_len[i];
     a.kv_div = p.kv_div;
     ProfScope ps(PC_ATTN, 4.0 * p.T * p.T * D * p.H * p.batch, st);
     launch_pdl(attn_tc_kernel, dim3(cdiv(p.T, BQ), p.H, p.batch), dim3(THREADS), SMEM, st, tq, tk, tv, a);

@@ -193,7 +193,7 @@ struct AttnParams {
     const float* relbias = nullptr; long rb_ld = 0; long rb_hs = 0; long rb_bs = 0;  // bias[b*rb_bs + h*rb_hs + i*rb_ld + (T-1-i+j)]
     // ragged batches (sequences right-padded to T): keys >= kv_len[b / kv_div] are masked and query tiles beyond it are
     // skipped; 0 = the full T
-    int kv_len[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int kv_div = 1;
+    int kv_len[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int kv_div = 1;
 };
 void launch_attention(const AttnParams& p, cudaStream_t st);
 void attention_init();

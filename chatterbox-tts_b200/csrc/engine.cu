@@ -96,7 +96,7 @@ int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
         v.spks = e->scratch<float>(MEL);
     }
     for (int i = 0; i < cfg->n_lanes; i++) { Lane* L = new Lane(); lane_alloc(e, *L, 1); e->lanes.push_back(L); }
-    e->batch_lane = new Lane(); lane_alloc(e, *e->batch_lane, FLOW_MAXB);
+    for (int i = 0; i < 2; i++) { Lane* L = new Lane(); lane_alloc(e, *L, FLOW_MAXB); e->batch_lanes.push_back(L); }
     CBX_CHECK(cudaDeviceSynchronize());
     *out = e;
     CBX_API_END
@@ -120,7 +120,7 @@ void cbx_engine_destroy(cbx_engine* e) {
     for (auto& kv : e->t3.step_graphs) cudaGraphExecDestroy(kv.second);
     for (auto& t : e->tensors) cudaFree(t.ptr);
     for (void* p : e->scratch_allocs) cudaFree(p);
-    if (e->batch_lane) e->lanes.push_back(e->batch_lane);
+    for (Lane* L : e->batch_lanes) e->lanes.push_back(L);
     for (Lane* L : e->lanes) { for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second); cudaFreeHost(L->g_dyn_h); cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
     cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
     delete e;
@@ -395,10 +395,14 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
 
 int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_calls, void* stream) {
     CBX_API_BEGIN
-    CBX_REQUIRE(e && e->finalized && calls && n_calls >= 1 && n_calls <= FLOW_MAXB, "s3gen batch: between 1 and 8 calls");
+    CBX_REQUIRE(e && e->finalized && calls && n_calls >= 1 && n_calls <= FLOW_MAXB, "s3gen batch: between 1 and 16 calls");
     CBX_CHECK(cudaSetDevice(e->device));
-    Lane& L = *e->batch_lane;
-    std::lock_guard<std::mutex> g(L.lock);
+    // take whichever batch workspace is free (two batches may overlap on the GPU: their kernels are latency-bound)
+    Lane* Lp = e->batch_lanes[0];
+    std::unique_lock<std::mutex> g(Lp->lock, std::try_to_lock);
+    if (!g.owns_lock()) { Lp = e->batch_lanes[1]; g = std::unique_lock<std::mutex>(Lp->lock, std::try_to_lock); }
+    if (!g.owns_lock()) { Lp = e->batch_lanes[0]; g = std::unique_lock<std::mutex>(Lp->lock); }
+    Lane& L = *Lp;
     StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
     const int* toks[FLOW_MAXB];
     L.nb = n_calls;

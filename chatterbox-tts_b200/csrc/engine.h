@@ -76,7 +76,7 @@ struct Voice {
 };
 
 struct FlowCall { const Voice* v = nullptr; int n = 0; int Tt = 0; };   // one S3Gen call of a batch: voice, new tokens, prompt + new tokens
-constexpr int FLOW_MAXB = 8;
+constexpr int FLOW_MAXB = 16;
 
 struct Lane {   // S3Gen workspace: one batch of up to `bmax` calls at a time
     std::mutex lock; cudaStream_t st; cudaEvent_t ev_in, ev_out;
@@ -105,7 +105,7 @@ struct cbx_engine {
     std::vector<Voice> voices; std::mutex voice_mu;
     std::mutex t3_mu; cudaStream_t t3_st; cudaEvent_t t3_ev_in, t3_ev_out;
     std::vector<Lane*> lanes; std::mutex lane_pick_mu; int lane_rr = 0;
-    Lane* batch_lane = nullptr;   // workspace of cbx_s3gen_infer_batch (FLOW_MAXB calls)
+    std::vector<Lane*> batch_lanes;   // workspaces of cbx_s3gen_infer_batch (FLOW_MAXB calls each): two batches can be in flight
     long gpu_launches = 0;
 
     template <typename T> T* reg(const std::string& name, int dtype, long numel);

@@ -89,7 +89,7 @@ int cbx_t3_close(cbx_engine* e, int slot);
 int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, const float* cache_source_d, int64_t m,
                     float* wav_out_d, float* source_out_d, float* mel_out_d, const float* phase_h, const float* noise_d,
                     uint64_t seed, void* stream);
-/* The same call for up to 8 requests at once (concurrent streams, or the text chunks of one request): the token -> mel
+/* The same call for up to 16 requests at once (concurrent streams, or the text chunks of one request): the token -> mel
  * part runs as ONE batch padded to the longest sequence (exact: causal convolutions, per-frame norms / linears, attention
  * masked per sequence), the vocoder per call.  Results equal cbx_s3gen_infer call by call. */
 typedef struct cbx_s3gen_call {

@@ -278,6 +278,14 @@ def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev):
         assert _rel(got[2], ref[2]) < 1e-5, f"mel differs: {_rel(got[2], ref[2])}"
         assert torch.equal(got[1], ref[1]) or _rel(got[1], ref[1]) < 1e-4
         assert _rel(got[0], ref[0]) < 1e-3
+    # more than 8 calls in one batch (the capacity is 16), lengths all different
+    lens12 = [3 + 5 * i for i in range(12)]
+    toks12 = [torch.randint(0, 6561, (n,), generator=g).numpy().astype(np.int32) for n in lens12]
+    ref12 = [eng.s3gen_infer(voices[i % 5], t, seed=9, return_mel=True)[2].clone() for i, t in enumerate(toks12)]
+    got12 = eng.s3gen_infer_batch([(voices[i % 5], t, None, 9) for i, t in enumerate(toks12)], return_mel=True)
+    torch.cuda.synchronize()
+    for a, b in zip(ref12, got12):
+        assert _rel(b[2], a) < 1e-5
     # one-call batch == single call
     one = eng.s3gen_infer_batch([(voice, toks[0], None, 5)], return_mel=True)[0]
     torch.cuda.synchronize()

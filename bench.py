@@ -139,6 +139,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def aggregate_ranks(ms, e2e_ms, audio_s, e2e_audio_s, world, device):
+    """Replicas only: every rank runs the same work on its own GPU.  The job's time is the MAX over ranks
+    (device-timed), the job's output is the SUM of what the ranks produced; no data-path collective exists."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms, e2e_ms], device=device, dtype=torch.float64)
+    a = torch.tensor([audio_s, e2e_audio_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    return {"ms_max": ms_max, "e2e_ms_max": e2e_ms_max, "value": float(a[0]) / (ms_max / 1e3), "e2e_value": float(a[1]) / (e2e_ms_max / 1e3)}
+
+
 def t3_step_leg(eng, pk):
     import torch
     nat = eng.native
@@ -264,14 +278,10 @@ def run_b200(args):
         torch.cuda.synchronize()
         barrier()
         e2e_s = time.time() - t0
-        t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max, e2e_ms_max = float(t[0]), float(t[1])
         audio_s = samples / 24000.0
-        value = world * audio_s / (ms_max / 1e3)
         e2e_audio = e2e_bytes / 2 / 24000.0
-        e2e_val = world * e2e_audio / (e2e_ms_max / 1e3)
+        agg = aggregate_ranks(ms, e2e_s * 1e3, audio_s, e2e_audio, world, "cuda")
+        ms_max, e2e_ms_max, value, e2e_val = agg["ms_max"], agg["e2e_ms_max"], agg["value"], agg["e2e_value"]
         if rank != 0:
             return
         # instrumented pass for the roofline (rank 0)

@@ -1,6 +1,7 @@
 // C-ABI of libcbx_b200.so (see include/cbx_b200.h): engine lifecycle, checkpoint upload,
 // voice cache, T3 streams, S3Gen calls, PCM conversion.  No torch types, no CPU fallback.
 #include <cstring>
+#include <cstdlib>
 #include "engine.h"
 
 using namespace dims;
@@ -85,7 +86,13 @@ int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
     gemm_init(); attention_init();
     t3_build(e); flow_build(e); hift_build(e);
     t3_alloc(e);
-    CBX_CHECK(cudaStreamCreateWithFlags(&e->t3_st, cudaStreamNonBlocking));
+    {   // CBX_T3_PRIORITY=1 runs T3 at the highest stream priority (its ~150 short dependent kernels per step queue behind the
+        // wide S3Gen launches).  Off by default: measured on the pipelined paragraph it lowers throughput (38 vs 44 audio-s/s)
+        int lo = 0, hi = 0;
+        CBX_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char* pr = getenv("CBX_T3_PRIORITY");
+        CBX_CHECK(cudaStreamCreateWithPriority(&e->t3_st, cudaStreamNonBlocking, (pr && pr[0] == '1') ? hi : lo));
+    }
     CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_in, cudaEventDisableTiming));
     CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_out, cudaEventDisableTiming));
     e->voices.resize(cfg->n_voices);

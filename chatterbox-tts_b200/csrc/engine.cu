@@ -125,6 +125,7 @@ void cbx_engine_destroy(cbx_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& kv : e->t3.step_graphs) cudaGraphExecDestroy(kv.second);
+    t3_mega_free(&e->t3.mega_state);
     for (auto& t : e->tensors) cudaFree(t.ptr);
     for (void* p : e->scratch_allocs) cudaFree(p);
     for (Lane* L : e->batch_lanes) e->lanes.push_back(L);

@@ -39,7 +39,7 @@ struct T3Model {
     int* out_tokens = nullptr; int out_stride = 0; float *x, *qkv, *attn, *act, *logits;
     int *d_slots = nullptr, *d_rowmap = nullptr;   // active set staging [max_streams], [2*max_streams]
     // megakernel state
-    bool mega = false, mega_ok = false; MegaLayer* d_layers = nullptr; unsigned long long* ll[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; unsigned int* epoch = nullptr;
+    bool mega = false, mega_ok = false; MegaState mega_state; MegaLayer* d_layers = nullptr; unsigned long long* ll[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; unsigned int* epoch = nullptr;
     // prefill workspace
     float* pf_x; bf16 *pf_xn, *pf_qkv, *pf_att, *pf_act; int* pf_text; int pf_max = 0;
     // host side

@@ -96,7 +96,7 @@ void t3_alloc(cbx_engine* e) {
     // cbx_t3_set_persistent) because a cooperative grid owns all SMs for the whole step, so the S3Gen kernels that
     // otherwise share the GPU with T3 on other streams have to wait (measured on the pipelined 200-word paragraph: 3.64 s
     // vs 3.17 s), and with 16 rows the GEMV kernels are faster (1.55 ms vs 2.35 ms).  See DESIGN.md section 6.
-    m.mega_ok = t3_mega_init(m.max_pages, hl, m.head_f, T3_VPAD / 16);
+    m.mega_ok = t3_mega_init(m.max_pages, hl, m.head_f, T3_VPAD / 16, &m.mega_state);
     const char* en = getenv("CBX_T3_MEGA");
     m.mega = m.mega_ok && en && en[0] == '1';
 }
@@ -234,7 +234,7 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         p.ll_qkv = m.ll[0]; p.ll_ap = m.ll[1]; p.ll_y = m.ll[2]; p.ll_act = m.ll[3]; p.ll_z = m.ll[4]; p.cnt = reinterpret_cast<unsigned int*>(m.ll[5]); p.epoch = m.epoch;
         p.kv = m.kv; p.kv_layer_stride = m.kv_layer_stride; p.kv_half = m.kv_half; p.page_table = m.page_table; p.max_pages = m.max_pages;
         p.slot_pos = m.slot_pos; p.row_map = m.d_rowmap; p.inv_freq = m.inv_freq; p.rows = rows;
-        launch_t3_mega(p, st);
+        launch_t3_mega(p, m.mega_state, st);
         enqueue_sampler(e, n, noise, st);
         return;
     }

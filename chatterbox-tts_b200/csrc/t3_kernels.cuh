@@ -91,6 +91,8 @@ struct MegaParams {
     int rows = 0;
     const unsigned long long* sched = nullptr; const int* sched_count = nullptr; int l2_ahead = 0;   // filled by launch_t3_mega
 };
-bool t3_mega_init(int max_pages, const std::vector<MegaLayer>& layers, const bf16* head_f, int head_items);
+struct MegaState { unsigned long long* sched = nullptr; int* sched_count = nullptr; int grid = 0, max_pages = 0; };   // per engine
+bool t3_mega_init(int max_pages, const std::vector<MegaLayer>& layers, const bf16* head_f, int head_items, MegaState* out);
+void t3_mega_free(MegaState* ms);
 size_t t3_mega_ll_words(int which);   // 0 qkv, 1 attention partials, 2 y, 3 act, 4 z, 5 arrival counters
-void launch_t3_mega(const MegaParams& p, cudaStream_t st);
+void launch_t3_mega(const MegaParams& p, const MegaState& ms, cudaStream_t st);

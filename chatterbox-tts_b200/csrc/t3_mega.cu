@@ -749,9 +749,7 @@ template <int NT, int RA> size_t mega_smem(int max_pages) {
 
 }  // namespace
 
-int t3_mega_grid = 0;
 
-static int g_mega_max_pages = 0;
 
 // host mirror of the kernel's Deal walk: the slot addresses of every CTA in consumption order
 static void build_schedule(int G, const std::vector<MegaLayer>& layers, const bf16* head_f, int head_items, std::vector<unsigned long long>& sched, std::vector<int>& count) {
@@ -782,17 +780,17 @@ static void build_schedule(int G, const std::vector<MegaLayer>& layers, const bf
     }
 }
 
-static unsigned long long* g_sched_d = nullptr;
-static int* g_sched_count_d = nullptr;
 
-bool t3_mega_init(int max_pages, const std::vector<MegaLayer>& layers, const bf16* head_f, int head_items) {
+// Per-ENGINE state (the schedule holds that engine's weight addresses): returned to the caller, never kept in globals.
+bool t3_mega_init(int max_pages, const std::vector<MegaLayer>& layers, const bf16* head_f, int head_items, MegaState* out) {
+    *out = MegaState{};
     int dev = 0, sms = 0, coop = 0;
     CBX_CHECK(cudaGetDevice(&dev));
     CBX_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CBX_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return false;
     if (mega_smem<2, 16>(max_pages) > 227 * 1024 || mega_smem<1, 2>(max_pages) > 227 * 1024 || mega_smem<1, 8>(max_pages) > 227 * 1024) return false;
-    g_mega_max_pages = max_pages;
+    out->max_pages = max_pages;
     CBX_CHECK(cudaFuncSetAttribute(t3_mega_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem<1, 2>(max_pages)));
     CBX_CHECK(cudaFuncSetAttribute(t3_mega_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem<1, 8>(max_pages)));
     CBX_CHECK(cudaFuncSetAttribute(t3_mega_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega_smem<2, 16>(max_pages)));
@@ -801,13 +799,13 @@ bool t3_mega_init(int max_pages, const std::vector<MegaLayer>& layers, const bf1
     CBX_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, t3_mega_kernel<1, 8>, THREADS, mega_smem<1, 8>(max_pages)));
     CBX_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, t3_mega_kernel<2, 16>, THREADS, mega_smem<2, 16>(max_pages)));
     if (occ0 < 1 || occ1 < 1 || occ2 < 1) return false;
-    t3_mega_grid = sms;
+    out->grid = sms;
     std::vector<unsigned long long> sched; std::vector<int> count;
     build_schedule(sms, layers, head_f, head_items, sched, count);
-    CBX_CHECK(cudaMalloc(&g_sched_d, sched.size() * 8));
-    CBX_CHECK(cudaMalloc(&g_sched_count_d, count.size() * 4));
-    CBX_CHECK(cudaMemcpy(g_sched_d, sched.data(), sched.size() * 8, cudaMemcpyHostToDevice));
-    CBX_CHECK(cudaMemcpy(g_sched_count_d, count.data(), count.size() * 4, cudaMemcpyHostToDevice));
+    CBX_CHECK(cudaMalloc(&out->sched, sched.size() * 8));
+    CBX_CHECK(cudaMalloc(&out->sched_count, count.size() * 4));
+    CBX_CHECK(cudaMemcpy(out->sched, sched.data(), sched.size() * 8, cudaMemcpyHostToDevice));
+    CBX_CHECK(cudaMemcpy(out->sched_count, count.data(), count.size() * 4, cudaMemcpyHostToDevice));
     return true;
 }
 
@@ -822,22 +820,28 @@ size_t t3_mega_ll_words(int which) {   // sizes (in 8-byte words) of the double-
     }
 }
 
-void launch_t3_mega(const MegaParams& p_in, cudaStream_t st) {
+void t3_mega_free(MegaState* ms) {
+    if (ms->sched) cudaFree(ms->sched);
+    if (ms->sched_count) cudaFree(ms->sched_count);
+    *ms = MegaState{};
+}
+
+void launch_t3_mega(const MegaParams& p_in, const MegaState& ms, cudaStream_t st) {
     MegaParams p = p_in;
-    p.sched = g_sched_d; p.sched_count = g_sched_count_d;
+    p.sched = ms.sched; p.sched_count = ms.sched_count;
     static const int l2_ahead = [] { const char* e = getenv("CBX_T3_L2_AHEAD"); return e ? atoi(e) : 0; }();
     p.l2_ahead = l2_ahead;
-    CBX_REQUIRE(t3_mega_grid > 0, "t3 megakernel not initialised");
+    CBX_REQUIRE(ms.grid > 0, "t3 megakernel not initialised");
     CBX_REQUIRE(p.rows >= 1 && p.rows <= 16, "t3 megakernel: rows must be in [1,16]");
     CBX_REQUIRE(p.n_layers <= MAX_LAYERS, "t3 megakernel: too many layers");
-    CBX_REQUIRE(p.max_pages == g_mega_max_pages, "t3 megakernel: page-table width changed after init");
+    CBX_REQUIRE(p.max_pages == ms.max_pages, "t3 megakernel: page-table width changed after init");
     ProfScope ps(PC_GEMV, 2.0 * (p.n_layers * 16777216.0 + (double)p.head_items * 16 * D), st);
     CBX_CHECK(cudaMemsetAsync(p.cnt, 0, (size_t)MAX_LAYERS * CNT_STRIDE * 4, st));
     void* args[] = {(void*)&p};
     // cooperative launch: the flagged-word exchange needs every CTA of the grid to be resident
-    if (p.rows <= 2) CBX_CHECK(cudaLaunchCooperativeKernel((void*)t3_mega_kernel<1, 2>, dim3(t3_mega_grid), dim3(THREADS), args, mega_smem<1, 2>(g_mega_max_pages), st));
-    else if (p.rows <= 8) CBX_CHECK(cudaLaunchCooperativeKernel((void*)t3_mega_kernel<1, 8>, dim3(t3_mega_grid), dim3(THREADS), args, mega_smem<1, 8>(g_mega_max_pages), st));
-    else CBX_CHECK(cudaLaunchCooperativeKernel((void*)t3_mega_kernel<2, 16>, dim3(t3_mega_grid), dim3(THREADS), args, mega_smem<2, 16>(g_mega_max_pages), st));
+    if (p.rows <= 2) CBX_CHECK(cudaLaunchCooperativeKernel((void*)t3_mega_kernel<1, 2>, dim3(ms.grid), dim3(THREADS), args, mega_smem<1, 2>(ms.max_pages), st));
+    else if (p.rows <= 8) CBX_CHECK(cudaLaunchCooperativeKernel((void*)t3_mega_kernel<1, 8>, dim3(ms.grid), dim3(THREADS), args, mega_smem<1, 8>(ms.max_pages), st));
+    else CBX_CHECK(cudaLaunchCooperativeKernel((void*)t3_mega_kernel<2, 16>, dim3(ms.grid), dim3(THREADS), args, mega_smem<2, 16>(ms.max_pages), st));
 }
 
 extern "C" int cbx_t3_mega_prof(long long* out_h) { return cudaMemcpyFromSymbol(out_h, g_mega_prof, sizeof(long long) * 256 * 4) == cudaSuccess ? 0 : 1; }

@@ -179,6 +179,37 @@ def test_t3_megakernel_matches_gemv_path(tiny, tiny_cfg, dev):
         eng.t3_set_persistent(False)
 
 
+def test_t3_persistent_kernel_state_is_per_engine(tiny, tiny_cfg, dev):
+    """The persistent kernel's weight schedule holds device addresses of ONE engine's weights: a second engine created
+    afterwards (different weights) must not change what the first one computes."""
+    from conftest import bf16_round
+    from cbx_b200.native import NativeEngine
+    from cbx_b200.weights import random_state_dict
+    eng, sd_dev, conds, voice = tiny
+    text = _text(9, seed=5)[0].numpy()
+
+    def run(e, v, persistent):
+        e.t3_set_persistent(persistent)
+        s = e.t3_open(v, text, seed=3, max_new=6)
+        e.t3_step([s], 1)
+        lg = torch.from_numpy(e.t3_logits(s)).clone()
+        e.t3_close(s)
+        e.t3_set_persistent(False)
+        return lg
+
+    before = run(eng, voice, True)
+    other = NativeEngine(tiny_cfg, max_streams=2, max_s3_tokens=64)
+    try:
+        other.load_state_dict(bf16_round(random_state_dict(tiny_cfg, 1)))
+        ov = other.voice_put("v", conds["t3"], conds["gen"])
+        lo_p, lo_g = run(other, ov, True), run(other, ov, False)
+        after = run(eng, voice, True)
+        assert torch.equal(before, after), "creating another engine changed this engine's persistent-kernel results"
+        assert _rel(lo_p, lo_g) < 5e-3 and _rel(lo_p, before) > 1e-2   # the other engine computes with ITS weights
+    finally:
+        other.close()
+
+
 def test_flow_tiny_mel(tiny, tiny_cfg, dev):
     from oracle import flow as F
     eng, sd_dev, conds, voice = tiny

@@ -103,7 +103,13 @@ int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
         v.spks = e->scratch<float>(MEL);
     }
     for (int i = 0; i < cfg->n_lanes; i++) { Lane* L = new Lane(); lane_alloc(e, *L, 1); e->lanes.push_back(L); }
-    for (int i = 0; i < 2; i++) { Lane* L = new Lane(); lane_alloc(e, *L, FLOW_MAXB); e->batch_lanes.push_back(L); }
+    for (int i = 0; i < 2; i++) {
+        Lane* L = new Lane(); lane_alloc(e, *L, FLOW_MAXB); e->batch_lanes.push_back(L);
+        for (int k = 0; k < 4; k++) { Lane* S = new Lane(); lane_alloc(e, *S, 0); L->sub.push_back(S); }
+        CBX_CHECK(cudaEventCreateWithFlags(&L->ev_flow, cudaEventDisableTiming));
+        L->ev_call.resize(FLOW_MAXB);
+        for (auto& ev : L->ev_call) CBX_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     CBX_CHECK(cudaDeviceSynchronize());
     *out = e;
     CBX_API_END
@@ -128,7 +134,12 @@ void cbx_engine_destroy(cbx_engine* e) {
     t3_mega_free(&e->t3.mega_state);
     for (auto& t : e->tensors) cudaFree(t.ptr);
     for (void* p : e->scratch_allocs) cudaFree(p);
-    for (Lane* L : e->batch_lanes) e->lanes.push_back(L);
+    for (Lane* L : e->batch_lanes) {
+        e->lanes.push_back(L);
+        for (Lane* S : L->sub) e->lanes.push_back(S);
+        if (L->ev_flow) cudaEventDestroy(L->ev_flow);
+        for (auto& ev : L->ev_call) cudaEventDestroy(ev);
+    }
     for (Lane* L : e->lanes) { for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second); cudaFreeHost(L->g_dyn_h); cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
     cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
     delete e;
@@ -427,13 +438,27 @@ int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_call
     // norm / attention launch covers all calls, so the per-launch latency that bounds a single call is shared
     flow_run(e, L, L.st);
     const long mel_bs = 2L * e->cfg.max_s3_tokens * MEL;
-    for (int b = 0; b < n_calls; b++) {   // the vocoder runs per call (different lengths, source caches and seeds)
+    // the vocoder runs per call (different lengths, source caches and seeds) on the lane's vocoder streams: calls are dealt
+    // round-robin over them, a call whose cache_source is an earlier call's source output waits for that call
+    CBX_CHECK(cudaEventRecord(L.ev_flow, L.st));
+    const int nsub = prof_enabled() ? 1 : (int)L.sub.size();   // per-launch profiling brackets launches with events on ONE stream
+    for (int b = 0; b < n_calls; b++) {
         const cbx_s3gen_call& c = calls[b];
         const long Ls = 960L * c.n;
-        CBX_CHECK(cudaMemcpyAsync(L.mel, L.melb + b * mel_bs, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
-        hift_infer(e, L, 2 * c.n, c.cache_source_d, c.m > Ls ? Ls : c.m, c.wav_out_d, c.source_out_d, nullptr, nullptr, c.seed, L.st);
-        if (c.mel_out_d) CBX_CHECK(cudaMemcpyAsync(c.mel_out_d, L.mel, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+        Lane& S = *L.sub[b % nsub];
+        cudaStream_t hs = prof_enabled() ? L.st : S.st;
+        if (!prof_enabled()) {
+            CBX_CHECK(cudaStreamWaitEvent(hs, L.ev_flow, 0));
+            for (int a = 0; a < b; a++)
+                if (c.cache_source_d && c.cache_source_d == calls[a].source_out_d) CBX_CHECK(cudaStreamWaitEvent(hs, L.ev_call[a], 0));
+        }
+        CBX_CHECK(cudaMemcpyAsync(S.mel, L.melb + b * mel_bs, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, hs));
+        hift_infer(e, S, 2 * c.n, c.cache_source_d, c.m > Ls ? Ls : c.m, c.wav_out_d, c.source_out_d, nullptr, nullptr, c.seed, hs);
+        if (c.mel_out_d) CBX_CHECK(cudaMemcpyAsync(c.mel_out_d, S.mel, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, hs));
+        if (!prof_enabled()) CBX_CHECK(cudaEventRecord(L.ev_call[b], hs));
     }
+    if (!prof_enabled())
+        for (int b = 0; b < n_calls; b++) CBX_CHECK(cudaStreamWaitEvent(L.st, L.ev_call[b], 0));
     br.finish();
     CBX_API_END
 }

@@ -82,6 +82,8 @@ struct Lane {   // S3Gen workspace: one batch of up to `bmax` calls at a time
     std::mutex lock; cudaStream_t st; cudaEvent_t ev_in, ev_out;
     int bmax = 1, nb = 1, Ttm = 0; FlowCall call[FLOW_MAXB];   // current batch; sequences are right-padded to Ttm tokens
     float* melb = nullptr;   // [bmax][2*max_s3_tokens][80] CFM output per call
+    std::vector<Lane*> sub;  // batch lanes: vocoder-only workspaces with their own streams (the calls' HiFT passes run in parallel)
+    cudaEvent_t ev_flow = nullptr; std::vector<cudaEvent_t> ev_call;
     // encoder
     int* tok; bf16 *e_in, *e_xb, *e_y1, *e_xn, *e_qkv, *e_pos, *e_p, *e_o, *e_ff, *e_up, *e_upc; float *e_tmp, *e_x, *e_bd;
     // cfm

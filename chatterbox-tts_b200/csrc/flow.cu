@@ -119,18 +119,20 @@ void lane_alloc(cbx_engine* e, Lane& L, int bmax) {
     CBX_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
     CBX_CHECK(cudaEventCreateWithFlags(&L.ev_in, cudaEventDisableTiming));
     CBX_CHECK(cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
-    L.tok = e->scratch<int>(B * Tt);
-    L.e_in = e->scratch<bf16>(B * T * F_D); L.e_xb = e->scratch<bf16>(B * (T + EP) * F_D); L.e_y1 = e->scratch<bf16>(B * (T + EP) * F_D);
-    L.e_xn = e->scratch<bf16>(B * T * F_D); L.e_qkv = e->scratch<bf16>(B * T * 4 * F_D); L.e_pos = e->scratch<bf16>(2 * T * F_D); L.e_p = e->scratch<bf16>(2 * T * F_D);
-    L.e_o = e->scratch<bf16>(B * T * F_D); L.e_ff = e->scratch<bf16>(B * T * F_FFN); L.e_up = e->scratch<bf16>(B * (T + EP) * F_D); L.e_upc = e->scratch<bf16>(B * T * F_D);
-    L.e_tmp = e->scratch<float>(B * T * F_D); L.e_x = e->scratch<float>(B * T * F_D); L.e_bd = e->scratch<float>(B * F_H * T * 2 * T);
-    L.mu = e->scratch<float>(B * T * MEL); L.cond = e->scratch<float>(B * T * MEL); L.x = e->scratch<float>(B * T * MEL); L.v = e->scratch<float>(2 * B * T * MEL);
-    const long TH = T + CH;
-    L.c_in = e->scratch<bf16>(2 * B * TH * C_IN); L.c_hb = e->scratch<bf16>(2 * B * TH * C_CH); L.c_inb = e->scratch<bf16>(2 * B * TH * C_CH);
-    L.c_upin = e->scratch<bf16>(2 * B * TH * 2 * C_CH); L.c_xn = e->scratch<bf16>(2 * B * T * C_CH); L.c_qkv = e->scratch<bf16>(2 * B * T * 3 * C_INNER);
-    L.c_o = e->scratch<bf16>(2 * B * T * C_INNER); L.c_ff = e->scratch<bf16>(2 * B * T * C_FF); L.c_fb = e->scratch<bf16>(2 * B * T * C_CH);
-    L.c_tmp = e->scratch<float>(2 * B * T * C_CH); L.c_tmp2 = e->scratch<float>(2 * B * T * C_CH); L.c_h = e->scratch<float>(2 * B * T * C_CH);
-    L.melb = e->scratch<float>(B * Tg * MEL);
+    if (bmax > 0) {   // bmax == 0: a vocoder-only workspace (parallel HiFT streams of a batch lane)
+        L.tok = e->scratch<int>(B * Tt);
+        L.e_in = e->scratch<bf16>(B * T * F_D); L.e_xb = e->scratch<bf16>(B * (T + EP) * F_D); L.e_y1 = e->scratch<bf16>(B * (T + EP) * F_D);
+        L.e_xn = e->scratch<bf16>(B * T * F_D); L.e_qkv = e->scratch<bf16>(B * T * 4 * F_D); L.e_pos = e->scratch<bf16>(2 * T * F_D); L.e_p = e->scratch<bf16>(2 * T * F_D);
+        L.e_o = e->scratch<bf16>(B * T * F_D); L.e_ff = e->scratch<bf16>(B * T * F_FFN); L.e_up = e->scratch<bf16>(B * (T + EP) * F_D); L.e_upc = e->scratch<bf16>(B * T * F_D);
+        L.e_tmp = e->scratch<float>(B * T * F_D); L.e_x = e->scratch<float>(B * T * F_D); L.e_bd = e->scratch<float>(B * F_H * T * 2 * T);
+        L.mu = e->scratch<float>(B * T * MEL); L.cond = e->scratch<float>(B * T * MEL); L.x = e->scratch<float>(B * T * MEL); L.v = e->scratch<float>(2 * B * T * MEL);
+        const long TH = T + CH;
+        L.c_in = e->scratch<bf16>(2 * B * TH * C_IN); L.c_hb = e->scratch<bf16>(2 * B * TH * C_CH); L.c_inb = e->scratch<bf16>(2 * B * TH * C_CH);
+        L.c_upin = e->scratch<bf16>(2 * B * TH * 2 * C_CH); L.c_xn = e->scratch<bf16>(2 * B * T * C_CH); L.c_qkv = e->scratch<bf16>(2 * B * T * 3 * C_INNER);
+        L.c_o = e->scratch<bf16>(2 * B * T * C_INNER); L.c_ff = e->scratch<bf16>(2 * B * T * C_FF); L.c_fb = e->scratch<bf16>(2 * B * T * C_CH);
+        L.c_tmp = e->scratch<float>(2 * B * T * C_CH); L.c_tmp2 = e->scratch<float>(2 * B * T * C_CH); L.c_h = e->scratch<float>(2 * B * T * C_CH);
+        L.melb = e->scratch<float>(B * Tg * MEL);
+    }
     // hift (one call at a time)
     const long HH = H_HALO;
     L.mel = e->scratch<float>(Tg * MEL); L.h_mel = e->scratch<bf16>((Tg + 2 * HH) * MEL);

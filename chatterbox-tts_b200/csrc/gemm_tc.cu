@@ -164,9 +164,138 @@ __global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent variant for multi-wave launches (batched S3Gen: M = calls x 2 x T rows).  One CTA per SM walks a static
+// list of output tiles; the TMA warp keeps the operand ring full ACROSS tiles, the MMA warp alternates between two TMEM
+// accumulators, and eight dedicated epilogue warps drain accumulator i while the tensor core fills accumulator i^1 --
+// the per-tile prologue / epilogue latency that bounds the one-tile kernel above disappears from the critical path.
+template <int BN> struct TcPCfg {
+    static constexpr int STAGES = 4;
+    static constexpr int B_BYTES = BN * TK * 2;
+    static constexpr int RING = STAGES * (A_BYTES + B_BYTES);
+    static constexpr int LDT = BN + 4;
+    static constexpr int TILE_BYTES = TM * LDT * 4;
+    static constexpr int SMEM = RING + TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+template <int BN, int ACT, int ACT2>
+__global__ void __launch_bounds__(320, 1) gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                                    const GemmParams p, int kc_blocks, int w_batched, int tiles_m, int tiles_n, int n_tiles) {
+    using C = TcPCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + C::STAGES * A_BYTES;
+    const uint32_t stile = base + C::RING;
+    const uint32_t bars = stile + C::TILE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * C::STAGES, tfull0 = bars + 16 * C::STAGES, tempty0 = tfull0 + 16, tmem_slot = tempty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = p.K / TK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_launch_dependents();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pdl_wait();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // tile t -> (n tile fastest: neighbouring CTAs share the A rows in L2, m tile, batch)
+    auto tile_coords = [&](int t, int& m0, int& n0, int& b) { n0 = (t % tiles_n) * BN; m0 = ((t / tiles_n) % tiles_m) * TM; b = t / (tiles_n * tiles_m); };
+
+    if (warp == 0) {
+        if (lane == 0) {   // TMA producer: the ring runs ahead into the next tile
+            int g = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                int m0, n0, b;
+                tile_coords(t, m0, n0, b);
+                for (int kb = 0; kb < KB; kb++, g++) {
+                    const int s = g % C::STAGES, ph = (g / C::STAGES) & 1;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    mbar_expect_tx(full0 + 8 * s, A_BYTES + C::B_BYTES);
+                    const int tap = kb / kc_blocks, ci = (kb % kc_blocks) * TK;
+                    tma_load_4d(sA + s * A_BYTES, &tmA, full0 + 8 * s, ci, m0, tap, b);
+                    tma_load_3d(sB + s * C::B_BYTES, &tmW, full0 + 8 * s, kb * TK, n0, w_batched ? b : 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // MMA issuer: accumulator it & 1
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+                const int acc = it & 1;
+                mbar_wait(tempty0 + 8 * acc, ((it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < KB; kb++, g++) {
+                    const int s = g % C::STAGES, ph = (g / C::STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t ad = umma_desc(sA + s * A_BYTES), bd = umma_desc(sB + s * C::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TK / 16; k++) umma_bf16(tmem_base + acc * BN, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(empty0 + 8 * s);
+                }
+                umma_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else {               // epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+        const int q = warp & 3, half = (warp - 2) >> 2, et = threadIdx.x - 64;
+        constexpr int LDT = C::LDT, CPR = BN / 8, RSTEP = 256 / CPR;
+        const int cc = (et % CPR) * 8;
+        float* tile = reinterpret_cast<float*>(smem_raw + (stile - smem_u32(smem_raw)));
+        int it = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int acc = it & 1;
+            int m0, n0, b;
+            tile_coords(t, m0, n0, b);
+            ColOps co;
+            load_colops(p, b, n0 + cc, co);
+            mbar_wait(tfull0 + 8 * acc, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                float* trow = tile + (q * 32 + lane) * LDT + half * (BN / 2);
+#pragma unroll
+                for (int gq = 0; gq < BN / 64; gq++) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2) + gq * 32;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 8; c++)
+                        *reinterpret_cast<uint4*>(trow + gq * 32 + 4 * c) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                }
+            }
+            // this thread's part of the accumulator is in shared memory: hand it back to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // the staged tile is complete
+            epilogue_rows<ACT, ACT2>(p, b, m0, et / CPR, RSTEP, TM, tile, LDT, cc, co);
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone is done reading it: the next tile may overwrite
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn g_encode = nullptr;
+int g_sms = 148, g_persistent_min = 0;   // tiles from which the persistent kernel is used (0 = never)
 bool g_tc_ok = false;
 long g_tc_launches = 0;
 
@@ -192,6 +321,13 @@ bool launch_tc(const GemmParams& p, cudaStream_t st) {
     }
     dim3 grid(cdiv(p.M, TM), cdiv(p.N, BN), p.batch);
     bool done = false;
+    const int n_tiles = (int)grid.x * (int)grid.y * (int)grid.z;
+    if (g_persistent_min > 0 && n_tiles >= g_persistent_min) {
+        const int ctas = n_tiles < g_sms ? n_tiles : g_sms;
+#define CBX_LAUNCHP(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { launch_pdl(gemm_tc_persistent_kernel<BN, A1, A2>, dim3(ctas), dim3(320), TcPCfg<BN>::SMEM, st, tmA, tmW, p, p.kc / TK, w_batched, (int)grid.x, (int)grid.y, n_tiles); done = true; }
+        CBX_FOR_ACT_PAIRS(CBX_LAUNCHP)
+#undef CBX_LAUNCHP
+    }
 #define CBX_LAUNCH(A1, A2) if (!done && p.act == A1 && p.act2 == A2) { launch_pdl(gemm_tc_kernel<BN, A1, A2>, grid, dim3(256), C::SMEM, st, tmA, tmW, p, p.kc / TK, w_batched); done = true; }
     CBX_FOR_ACT_PAIRS(CBX_LAUNCH)
 #undef CBX_LAUNCH
@@ -215,6 +351,19 @@ void gemm_tc_init() {
     CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
     CBX_FOR_ACT_PAIRS(CBX_ATTR)
 #undef CBX_ATTR
+#define CBX_ATTRP(A1, A2) \
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<64, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPCfg<64>::SMEM)); \
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<128, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPCfg<128>::SMEM));
+    CBX_FOR_ACT_PAIRS(CBX_ATTRP)
+#undef CBX_ATTRP
+    {
+        int dev = 0;
+        CBX_CHECK(cudaGetDevice(&dev));
+        CBX_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+        // more than two waves of the two-CTAs-per-SM kernel: the persistent one wins (CBX_GEMM_PERSISTENT_MIN overrides, 0 = off)
+        const char* e = getenv("CBX_GEMM_PERSISTENT_MIN");
+        g_persistent_min = e ? atoi(e) : 2 * 2 * g_sms;
+    }
     g_tc_ok = true;
 }
 

@@ -40,7 +40,8 @@ def tiny(dev, tiny_cfg):
     eng.close()
 
 
-@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (100, 72, 200), (513, 256, 768), (1, 1024, 256), (300, 18, 448), (2000, 1536, 256)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (100, 72, 200), (513, 256, 768), (1, 1024, 256), (300, 18, 448), (2000, 1536, 256),
+                                   (16000, 1024, 256), (9001, 1536, 512), (40000, 192, 1024)])   # the last three: persistent kernel (>= 592 tiles)
 def test_gemm_op(dev, M, N, K):
     import ctypes as C
     from cbx_b200 import lib as L

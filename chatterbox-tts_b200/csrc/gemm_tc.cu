@@ -375,7 +375,8 @@ bool launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
     if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15)) return false;
     // wide tiles only when they still leave enough CTAs in flight
     const long ctas128 = (long)cdiv(p.M, TM) * cdiv(p.N, 128) * p.batch;
-    if (p.N >= 128 && ctas128 >= 96) return launch_tc<128>(p, st);
+    static const long wide_min = [] { const char* e = getenv("CBX_GEMM_WIDE_MIN"); return e ? atol(e) : 149L; }();
+    if (p.N >= 128 && ctas128 >= wide_min) return launch_tc<128>(p, st);
     return launch_tc<64>(p, st);
 }
 

@@ -152,7 +152,9 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 
 // ---------------------------------------------------------------- per-launch profiler (bench.py roofline pass)
 enum ProfClass { PC_GEMM = 0, PC_ATTN = 1, PC_GEMV = 2, PC_DECODE_ATTN = 3, PC_SAMPLER = 4, PC_NORM = 5, PC_ELEMWISE = 6, PC_HIFT_MISC = 7, PC_COUNT = 8 };
-bool prof_enabled();
+bool prof_enabled();   // per-launch bracketing is on for this thread
+bool prof_active();    // a profiling pass is running (even if this thread has suspended per-launch bracketing)
+void prof_suspend(int delta);   // +1 / -1: units that are timed as a whole (a graph-replayed T3 decode step)
 void prof_begin_launch(int cls, double work, cudaStream_t st);   // work: FLOPs (GEMM/ATTN) or bytes (everything else)
 void prof_end_launch(cudaStream_t st);
 struct ProfScope {

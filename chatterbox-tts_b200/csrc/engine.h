@@ -43,7 +43,7 @@ struct T3Model {
     // prefill workspace
     float* pf_x; bf16 *pf_xn, *pf_qkv, *pf_att, *pf_act; int* pf_text; int pf_max = 0;
     // host side
-    std::vector<int> free_pages; std::vector<int> slot_used; std::vector<std::vector<int>> slot_pages; std::vector<int> slot_maxnew;
+    std::vector<int> free_pages; std::vector<int> slot_used; std::vector<std::vector<int>> slot_pages; std::vector<int> slot_maxnew; std::vector<long> slot_pos_h;
     std::vector<int> h_active;   // last active set uploaded
     std::unordered_map<int, cudaGraphExec_t> step_graphs;   // keyed by n_streams
 };

@@ -12,13 +12,16 @@ std::mutex g_mu;
 std::vector<Rec> g_recs;
 bool g_on = false;
 thread_local Rec t_cur;
+thread_local int t_suspend = 0;
 }  // namespace
 
-bool prof_enabled() { return g_on; }
+bool prof_enabled() { return g_on && t_suspend == 0; }
+bool prof_active() { return g_on; }
+void prof_suspend(int d) { t_suspend += d; }
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* d = getenv("CBX_DISABLE_PDL"); v = (d && d[0] == '1') ? 0 : 1; }
-    return v == 1 && !g_on;   // per-launch event timing needs plain stream order
+    return v == 1 && !prof_enabled();   // per-launch event timing needs plain stream order
 }
 void prof_begin_launch(int cls, double work, cudaStream_t st) {
     t_cur.cls = cls; t_cur.work = work;

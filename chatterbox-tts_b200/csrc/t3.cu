@@ -82,6 +82,7 @@ void t3_alloc(cbx_engine* e) {
     m.slot_used.assign(S, 0);
     m.slot_pages.assign(S, {});
     m.slot_maxnew.assign(S, 0);
+    m.slot_pos_h.assign(S, 0);
     t3_kernels_init();
     for (int i = 0; i < 6; i++) m.ll[i] = e->scratch<unsigned long long>((long)t3_mega_ll_words(i));
     m.epoch = e->scratch<unsigned int>(4);
@@ -178,7 +179,7 @@ int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w,
             int pg = m.free_pages.back(); m.free_pages.pop_back();
             pt[r * m.max_pages + i] = pg; m.slot_pages[slot].push_back(pg);
         }
-    m.slot_used[slot] = 1; m.slot_maxnew[slot] = max_new;
+    m.slot_used[slot] = 1; m.slot_maxnew[slot] = max_new; m.slot_pos_h[slot] = Lp;
     CBX_CHECK(cudaMemcpyAsync(m.page_table + (long)slot * 2 * m.max_pages, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, st));
     CBX_CHECK(cudaMemcpyAsync(m.pf_text, text_ids_h, L * 4, cudaMemcpyHostToDevice, st));
     CBX_CHECK(cudaStreamSynchronize(st));   // pt / text staging are host stack buffers
@@ -276,22 +277,35 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
         m.h_active = act;
     }
     const long per_step = m.mega ? 2 : 5L * e->cfg.t3_layers + 2;
-    if (noise_dev || prof_enabled()) {
+    // algorithmic bytes of one step: every weight once for all rows + the KV cache of every row (host-side position estimate)
+    double kv_pos = 0;
+    for (int s : act) { kv_pos += 2.0 * m.slot_pos_h[s]; m.slot_pos_h[s] += n_steps; }
+    const double step_bytes = (double)e->cfg.t3_layers * 16779264.0 * 2 + (double)T3_VPAD * T3_D * 2 + 122880.0 * kv_pos;
+    if (noise_dev) {
         for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev ? noise_dev + (long)i * n * T3_V : nullptr, st);
     } else {
         const int gkey = n + (m.mega ? 1000 : 0);
         auto it = m.step_graphs.find(gkey);
         if (it == m.step_graphs.end()) {
             cudaGraph_t graph;
+            prof_suspend(+1);
             CBX_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            enqueue_step(e, n, nullptr, st);
+            try { enqueue_step(e, n, nullptr, st); } catch (...) { prof_suspend(-1); cudaGraph_t junk; cudaStreamEndCapture(st, &junk); throw; }
             CBX_CHECK(cudaStreamEndCapture(st, &graph));
+            prof_suspend(-1);
             cudaGraphExec_t exec;
             CBX_CHECK(cudaGraphInstantiate(&exec, graph, 0));
             CBX_CHECK(cudaGraphDestroy(graph));
             it = m.step_graphs.emplace(gkey, exec).first;
         }
-        for (int i = 0; i < n_steps; i++) CBX_CHECK(cudaGraphLaunch(it->second, st));
+        // a profiling pass times the replayed step as ONE unit (class: T3 decode step): bracketing its ~150 launches one by
+        // one would break the graph / PDL overlap the step is built on and measure something else
+        const bool prof = prof_active();
+        for (int i = 0; i < n_steps; i++) {
+            if (prof) prof_begin_launch(PC_GEMV, step_bytes + 122880.0 * 2 * n * i, st);
+            CBX_CHECK(cudaGraphLaunch(it->second, st));
+            if (prof) prof_end_launch(st);
+        }
     }
     e->gpu_launches += per_step * n_steps;
 }

@@ -382,7 +382,7 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
         const unsigned long long key = ((unsigned long long)voice << 48) | ((unsigned long long)(v.version & 0xFFFF) << 32) | ((unsigned long long)v.n_prompt << 16) | (unsigned long long)n;
         auto it = L.graphs.find(key);
         if (it == L.graphs.end()) {
-            const long before = e->gpu_launches;
+            const long before = e->gpu_launches.load();
             cudaGraph_t graph;
             CBX_CHECK(cudaStreamBeginCapture(L.st, cudaStreamCaptureModeThreadLocal));
             try {
@@ -399,7 +399,7 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
             CBX_CHECK(cudaGraphDestroy(graph));
             if (L.graphs.size() >= 64) { for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second); L.graphs.clear(); }
             it = L.graphs.emplace(key, exec).first;
-            L.launches_per_graph[key] = e->gpu_launches - before;
+            L.launches_per_graph[key] = e->gpu_launches.load() - before;
             e->gpu_launches = before;
         }
         CBX_CHECK(cudaGraphLaunch(it->second, L.st));
@@ -475,7 +475,7 @@ int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const fl
     CBX_API_END
 }
 
-int64_t cbx_gpu_launches(cbx_engine* e) { return e ? e->gpu_launches : -1; }
+int64_t cbx_gpu_launches(cbx_engine* e) { return e ? (int64_t)e->gpu_launches.load() : (int64_t)-1; }
 
 static void ops_init_once() {
     static std::once_flag once;

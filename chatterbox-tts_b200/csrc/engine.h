@@ -1,5 +1,6 @@
 // Internal engine structures: weight registry, T3 / flow / HiFT models and per-lane workspaces.
 #pragma once
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -108,7 +109,7 @@ struct cbx_engine {
     std::mutex t3_mu; cudaStream_t t3_st; cudaEvent_t t3_ev_in, t3_ev_out;
     std::vector<Lane*> lanes; std::mutex lane_pick_mu; int lane_rr = 0;
     std::vector<Lane*> batch_lanes;   // workspaces of cbx_s3gen_infer_batch (FLOW_MAXB calls each): two batches can be in flight
-    long gpu_launches = 0;
+    std::atomic<long> gpu_launches{0};   // statistics only, bumped from the T3, S3Gen and request threads
 
     template <typename T> T* reg(const std::string& name, int dtype, long numel);
     template <typename T> T* scratch(long numel);

@@ -1,0 +1,138 @@
+"""Host logic of the S3Gen batcher and the T3 slot semaphore (no GPU): dependency chaining inside a batch, finished
+dependencies passed as tensors, dropped jobs, submission order, priority order."""
+import os
+import sys
+import threading
+import time
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "chatterbox-tts_b200"), os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from cbx_b200.engine import PrioritySlots, S3GenBatcher, _Cancelled  # noqa: E402
+from fake_backend import FakeModel  # noqa: E402
+
+
+class BatchNative:
+    """FakeNative's S3Gen with the batch entry point; records how every batch was composed."""
+    is_fake = True
+    device = 0
+
+    def __init__(self, gate: threading.Event = None):
+        self.batches, self.gate = [], gate
+
+    def s3gen_infer(self, voice, tokens, cache_source=None, seed=0, **kw):
+        return FakeModel.s3gen(tokens, cache_source)
+
+    def s3gen_infer_batch(self, calls):
+        if self.gate is not None:
+            self.gate.wait(5)
+        self.batches.append([(len(t), ("chain", c) if isinstance(c, int) else ("tensor" if c is not None else None)) for _, t, c, _ in calls])
+        outs = []
+        for voice, toks, cache, seed in calls:
+            if isinstance(cache, int):
+                cache = outs[cache][1]            # the vocoder of a batch runs in call order: the earlier source exists
+            outs.append(FakeModel.s3gen(toks, cache))
+        return outs
+
+
+def _toks(n, k=0):
+    return [(7 * i + k) % 6561 for i in range(n)]
+
+
+def test_chained_slices_share_a_batch_and_match_sequential():
+    gate = threading.Event()
+    nat = BatchNative(gate)
+    b = S3GenBatcher(nat, max_batch=8, workers=1)
+    try:
+        first = b.submit(0, _toks(35), None, 1)           # occupies the worker (blocked on the gate) ...
+        time.sleep(0.1)
+        j1 = b.submit(0, _toks(70), first, 2)             # ... while three dependent slices and one unrelated call pile up
+        j2 = b.submit(0, _toks(105), j1, 3)
+        other = b.submit(0, _toks(20, 5), None, 4)
+        j3 = b.submit(0, _toks(140), j2, 5)
+        gate.set()
+        outs = [j.wait() for j in (first, j1, j2, other, j3)]
+    finally:
+        b.stop()
+    # the reference order: every slice synthesised with the previous slice's source as cache_source
+    src, ref = None, []
+    for n in (35, 70, 105):
+        w, src = FakeModel.s3gen(_toks(n), src)
+        ref.append((w, src))
+    w4, s4 = FakeModel.s3gen(_toks(140), src)
+    for got, want in zip((outs[0], outs[1], outs[2]), ref):
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    assert torch.equal(outs[4][0], w4)
+    assert torch.equal(outs[3][0], FakeModel.s3gen(_toks(20, 5), None)[0])
+    # first ran alone; the second batch holds j1 (finished dependency -> tensor), j2 and j3 chained to earlier members
+    assert nat.batches[0] == [(35, None)]
+    assert nat.batches[1] == [(70, "tensor"), (105, ("chain", 0)), (20, None), (140, ("chain", 1))]
+
+
+def test_dropped_job_and_its_dependents_are_cancelled():
+    gate = threading.Event()
+    nat = BatchNative(gate)
+    b = S3GenBatcher(nat, max_batch=8, workers=1)
+    try:
+        first = b.submit(0, _toks(35), None, 1)
+        time.sleep(0.1)
+        j1 = b.submit(0, _toks(70), first, 2)
+        j2 = b.submit(0, _toks(105), j1, 3)
+        keep = b.submit(0, _toks(12), None, 4)
+        j1.dropped = True                                  # what a cancelled request does to its pending jobs
+        gate.set()
+        first.wait()
+        with pytest.raises(_Cancelled):
+            j1.wait()
+        with pytest.raises(_Cancelled):
+            j2.wait()
+        assert torch.equal(keep.wait()[0], FakeModel.s3gen(_toks(12), None)[0])
+    finally:
+        b.stop()
+
+
+def test_batch_size_is_bounded_and_order_is_kept():
+    gate = threading.Event()
+    nat = BatchNative(gate)
+    b = S3GenBatcher(nat, max_batch=4, workers=1)
+    try:
+        head = b.submit(0, _toks(3), None, 0)
+        time.sleep(0.1)
+        jobs = [b.submit(0, _toks(4 + i), None, i) for i in range(9)]
+        gate.set()
+        head.wait()
+        for j in jobs:
+            j.wait()
+    finally:
+        b.stop()
+    sizes = [len(x) for x in nat.batches]
+    assert sizes[0] == 1 and max(sizes) <= 4 and sum(sizes) == 10
+    assert [n for batch in nat.batches[1:] for n, _ in batch] == [4 + i for i in range(9)]
+
+
+def test_priority_slots_serve_lowest_priority_first():
+    slots = PrioritySlots(1)
+    assert slots.acquire(0)
+    order, ths = [], []
+
+    def waiter(prio):
+        if slots.acquire(prio):
+            order.append(prio)
+            slots.release()
+
+    for prio in (5, 1, 3):                                 # arrive in this order while the slot is taken
+        t = threading.Thread(target=waiter, args=(prio,))
+        t.start()
+        ths.append(t)
+        time.sleep(0.05)
+    slots.release()
+    for t in ths:
+        t.join(5)
+    assert order == [1, 3, 5]
+    assert slots.acquire(9, cancelled=lambda: False)       # free again
+    assert not slots.acquire(0, cancelled=lambda: True)    # a cancelled waiter gives up instead of blocking

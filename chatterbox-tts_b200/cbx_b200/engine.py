@@ -409,7 +409,9 @@ class TextToSpeechEngine:
         self.voice_conditioning_executor = concurrent.futures.ThreadPoolExecutor(max_workers=n, thread_name_prefix="cbx-voice")
         # two S3Gen lanes: measured on B200, more lanes do not raise aggregate throughput (the per-call kernels are
         # latency-bound and already span the SMs) and cost workspace + graph captures per lane
-        self.native_kwargs = dict(max_streams=max(8, n), n_lanes=2)
+        # T3 stream slots: more than one decode batch (8 streams = 16 rows) may be open; the scheduler rotates batches, so the
+        # ninth text chunk of a paragraph does not have to wait for a whole chunk to finish decoding
+        self.native_kwargs = dict(max_streams=max(int(os.environ.get("CBX_MAX_STREAMS", "16")), n), n_lanes=2)
         # text chunks of one request that may be in flight at once (T3 decoding + S3Gen), ahead of the chunk being emitted
         self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "8"))
         self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=4 * max(8, n), thread_name_prefix="cbx-chunk")

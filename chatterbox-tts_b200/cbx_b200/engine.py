@@ -414,6 +414,9 @@ class TextToSpeechEngine:
         self.native_kwargs = dict(max_streams=max(int(os.environ.get("CBX_MAX_STREAMS", "16")), n), n_lanes=2)
         # text chunks of one request that may be in flight at once (T3 decoding + S3Gen), ahead of the chunk being emitted
         self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "8"))
+        # later chunks of a request start when chunk 0's first slice is on its way: "audio" = its PCM has been sent (lowest
+        # first-chunk latency), "tokens" = its tokens are decoded (their prefills overlap the first S3Gen call: +throughput)
+        self.hold_until = os.environ.get("CBX_HOLD_UNTIL", "audio")
         self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=4 * max(8, n), thread_name_prefix="cbx-chunk")
         self.s3gen: Optional[S3GenBatcher] = None
         self._pinned_pool: queue.Queue = queue.Queue()
@@ -650,6 +653,8 @@ class TextToSpeechEngine:
                         # consecutive slices of this chunk can ride in the same batch when T3 runs ahead of S3Gen
                         if ci == 0 and first_slice:
                             trace("slice1_tokens")
+                            if self.hold_until == "tokens":
+                                first_slice_ready.set()
                         job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx)
                         prev_job = job
                         jobs.append(job)

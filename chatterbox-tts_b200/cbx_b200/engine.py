@@ -229,6 +229,7 @@ class S3GenBatcher:
     def __init__(self, native, max_batch: int = None, workers: int = None):
         self.native = native
         self.max_batch = max_batch or int(os.environ.get("CBX_S3GEN_MAX_BATCH", "8"))
+        self.max_batch_deep = max(self.max_batch, int(os.environ.get("CBX_S3GEN_MAX_BATCH_DEEP", "16"))) if max_batch is None else max_batch
         self.on_gpu = not getattr(native, "is_fake", False)
         self.can_batch = hasattr(native, "s3gen_infer_batch")
         self.jobs = collections.deque()
@@ -262,7 +263,9 @@ class S3GenBatcher:
     def _take(self):
         """Under self.cv: the longest prefix-ordered set of runnable jobs, at most max_batch."""
         batch, members, keep = [], set(), collections.deque()
-        limit = self.max_batch if self.can_batch else 1
+        # deep queue (many concurrent requests): the native capacity of 16 calls per batch pays; otherwise smaller batches keep
+        # the slice-to-slice latency chain of a single request short
+        limit = (self.max_batch_deep if len(self.jobs) >= self.max_batch_deep else self.max_batch) if self.can_batch else 1
         while self.jobs:
             j = self.jobs.popleft()
             ready = j.dep is None or j.dep.done.is_set() or id(j.dep) in members

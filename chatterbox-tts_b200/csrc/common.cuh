@@ -179,6 +179,9 @@ struct GemmParams {
     float out_scale = 1.f; int accumulate = 0;                   // outF = (accumulate? outF : 0) + scale*v
     float* outF = nullptr; bf16* outB = nullptr; long ldc = 0; long c_bs = 0;
     bf16* outB2 = nullptr; int act2 = ACT_NONE; float act2_param = 0.f; const float* act2_alpha = nullptr; long ldc2 = 0; long c2_bs = 0;
+    // LayerNorm of the finished row fused into the epilogue (tcgen05 kernel only; N must be 1..4 tiles wide): outF = acc + bias +
+    // res (fp32), outB2 = LayerNorm(outF row) * ln_gamma + ln_beta (bf16)
+    const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 1e-5f;
     // transposed-conv scatter mask: column n belongs to phase n/ct_cout; output time = m*ct_u + phase - ct_pad must be in [0, ct_len)
     int ct_u = 0, ct_cout = 0, ct_pad = 0, ct_len = 0;
 };

@@ -3,6 +3,7 @@
 // zero-haloed bf16 buffers; residual streams stay fp32.  Host orchestration only.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "engine.h"
 
 using namespace dims;
@@ -230,22 +231,43 @@ static void encoder(cbx_engine* e, Lane& L, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------- estimator
 // all estimator tensors are [2*nb][T(+halo)][C] (rows 2b, 2b+1 = conditional / unconditional pass of call b)
-static void tfm_block(cbx_engine* e, Lane& L, const TfmP& t, int T, cudaStream_t st) {
+// The two LayerNorms of a block CAN ride in the epilogue of the GEMM that produces their input (cluster-fused LN of
+// gemm_tc.cu): `pre_normed` = c_xn already holds LN1(c_h) (written by the previous block's ff2), `next_ln` = the LN1 of
+// the following block, applied by this block's ff2.  Measured on B200 it does not pay -- one call 37.1 ms fused vs 35.4 ms
+// with the separate norm kernels, 8 x 140 tokens 127.6 vs 124.9 ms: under PDL the norm launches overlap their neighbours,
+// while two cluster barriers and a second epilogue pass lengthen every residual GEMM -- so it is opt-in (CBX_FUSE_LN=1).
+static bool fuse_ln() {
+    const char* v = getenv("CBX_FUSE_LN");
+    const char* tc = getenv("CBX_DISABLE_TC");
+    return v && v[0] == '1' && !(tc && tc[0] == '1');   // the fused epilogue lives in the tcgen05 kernel
+}
+static void tfm_block(cbx_engine* e, Lane& L, const TfmP& t, int T, bool pre_normed, const LNp* next_ln, cudaStream_t st) {
     const int NB = 2 * L.nb;
     const long bs = (long)T * C_CH;
     NormParams n; n.in = L.c_h; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = NB; n.C = C_CH; n.gain = t.n1.g; n.bias = t.n1.b; n.eps = 1e-5f;
     n.outB = L.c_xn; n.ld_outB = C_CH; n.outB_bs = bs;
-    launch_norm(n, st);
+    if (!pre_normed) { launch_norm(n, st); e->gpu_launches += 1; }
     GemmParams g = mk(t.qkv, L.c_xn, C_CH, NB * T, C_CH, 0); g.outB = L.c_qkv; g.ldc = 3 * C_INNER; launch_gemm(g, st);
     AttnParams a; a.q = L.c_qkv; a.k = L.c_qkv + C_INNER; a.v = L.c_qkv + 2 * C_INNER; a.ldq = a.ldk = a.ldv = 3 * C_INNER;
     a.q_bs = a.k_bs = a.v_bs = (long)T * 3 * C_INNER; a.o = L.c_o; a.ldo = C_INNER; a.o_bs = (long)T * C_INNER; a.T = T; a.H = 8; a.batch = NB; a.scale = 0.125f;
     set_kv_len(a, L, 2, 2);
     launch_attention(a, st);
-    g = mk(t.out, L.c_o, C_INNER, NB * T, C_INNER, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
-    n.gain = t.n3.g; n.bias = t.n3.b; launch_norm(n, st);
+    g = mk(t.out, L.c_o, C_INNER, NB * T, C_INNER, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH;
+    if (fuse_ln()) { g.ln_gamma = t.n3.g; g.ln_beta = t.n3.b; g.ln_eps = 1e-5f; g.outB2 = L.c_xn; g.ldc2 = C_CH; }
+    launch_gemm(g, st);
+    if (!fuse_ln()) { n.gain = t.n3.g; n.bias = t.n3.b; launch_norm(n, st); e->gpu_launches += 1; }
     g = mk(t.ff0, L.c_xn, C_CH, NB * T, C_CH, 0); g.act = ACT_GELU; g.outB = L.c_ff; g.ldc = C_FF; launch_gemm(g, st);
-    g = mk(t.ff2, L.c_ff, C_FF, NB * T, C_FF, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH; launch_gemm(g, st);
-    e->gpu_launches += 7;
+    g = mk(t.ff2, L.c_ff, C_FF, NB * T, C_FF, 0); g.res = L.c_h; g.ldr = C_CH; g.outF = L.c_h; g.ldc = C_CH;
+    if (next_ln) { g.ln_gamma = next_ln->g; g.ln_beta = next_ln->b; g.ln_eps = 1e-5f; g.outB2 = L.c_xn; g.ldc2 = C_CH; }
+    launch_gemm(g, st);
+    e->gpu_launches += 5;
+}
+
+// the transformer blocks [j0, j0 + nb) of one estimator stage
+static void tfm_stage(cbx_engine* e, Lane& L, int j0, int nb, int T, cudaStream_t st) {
+    FlowModel& f = e->flow;
+    for (int j = 0; j < nb; j++)
+        tfm_block(e, L, f.tfms[j0 + j], T, fuse_ln() && j > 0, (fuse_ln() && j + 1 < nb) ? &f.tfms[j0 + j + 1].n1 : nullptr, st);
 }
 
 // resnet: in = haloed bf16 [2nb][CH+T][cin] -> L.c_h fp32 [2nb][T][256]
@@ -279,19 +301,19 @@ static void estimator(cbx_engine* e, Lane& L, int T, int step, cudaStream_t st) 
     auto tp = [&](int r) { return f.tproj + ((long)r * nsteps + step) * C_CH; };
     // down stage
     resnet(e, L, f.resnets[0], tp(0), L.c_in, T, st);
-    for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[j], T, st);
+    tfm_stage(e, L, 0, nb, T, st);
     to_bf16_haloed(e, L, L.c_upin, 2 * C_CH, C_CH, T, st);          // skip connection -> channels [256,512) of the up-stage input
     to_bf16_haloed(e, L, L.c_hb, C_CH, 0, T, st);
     GemmParams g = mk(f.down_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
     launch_gemm(g, st);
     for (int i = 0; i < nmid; i++) {
         resnet(e, L, f.resnets[1 + i], tp(1 + i), L.c_inb, T, st);
-        for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[(1 + i) * nb + j], T, st);
+        tfm_stage(e, L, (1 + i) * nb, nb, T, st);
         if (i + 1 < nmid) to_bf16_haloed(e, L, L.c_inb, C_CH, 0, T, st);
         else to_bf16_haloed(e, L, L.c_upin, 2 * C_CH, 0, T, st);
     }
     resnet(e, L, f.resnets[nres - 1], tp(nres - 1), L.c_upin, T, st);
-    for (int j = 0; j < nb; j++) tfm_block(e, L, f.tfms[(nres - 1) * nb + j], T, st);
+    tfm_stage(e, L, (nres - 1) * nb, nb, T, st);
     to_bf16_haloed(e, L, L.c_hb, C_CH, 0, T, st);
     g = mk(f.up_conv, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outB = L.c_inb + CH * C_CH; g.ldc = C_CH; g.c_bs = TH * C_CH;
     launch_gemm(g, st);

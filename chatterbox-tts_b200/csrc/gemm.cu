@@ -189,6 +189,7 @@ void launch_gemm(const GemmParams& p, cudaStream_t st) {
     // pick the tile so the grid covers the 148 SMs: big tiles only when they still give >= ~2 waves
     ProfScope ps(PC_GEMM, 2.0 * p.M * p.N * p.K * p.batch, st);
     if (launch_gemm_tc(p, st)) return;
+    CBX_REQUIRE(!p.ln_gamma, "gemm: the fused LayerNorm epilogue exists only on the tcgen05 path (N must be 1..4 tiles, no activation)");
     long big = (long)cdiv(p.M, 128) * cdiv(p.N, 128) * p.batch;
     if (big >= 296) launch_cfg<128, 128, 4, 4>(p, st);
     else launch_cfg<64, 64, 2, 4>(p, st);

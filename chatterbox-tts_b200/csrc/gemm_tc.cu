@@ -58,7 +58,24 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, int ACT, int ACT2>
+// LayerNorm of the finished row fused into the epilogue (LN = true; N == cluster size x BN, the CTAs of a row's tiles form
+// one thread-block cluster along N): every CTA writes its part of the fp32 row (bias + residual), computes {mean, M2}
+// of its BN columns, the cluster exchanges them through distributed shared memory, and every CTA writes its part of
+// LayerNorm(row) * gamma + beta as bf16 -- the separate norm kernel between a residual GEMM and the next projection
+// (two per CFM transformer block, a fifth of all S3Gen launches) disappears.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_cluster_f2(const float* local_smem_ptr, uint32_t cta_rank) {
+    uint32_t la = smem_u32(local_smem_ptr), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta_rank));
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(ra) : "memory");
+    return v;
+}
+
+template <int BN, int ACT, int ACT2, bool LN = false>
 __global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                          const GemmParams p, int kc_blocks, int w_batched) {
     using C = TcCfg<BN>;
@@ -155,7 +172,79 @@ __global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__
         if (threadIdx.x == 64) TC_TRACE(7);
         __syncthreads();
         if (threadIdx.x == 64) TC_TRACE(8);
-        epilogue_rows<ACT, ACT2>(p, b, m0, et / CPR, RSTEP, TM, tile, LDT, cc, co);
+        if constexpr (!LN) {
+            epilogue_rows<ACT, ACT2>(p, b, m0, et / CPR, RSTEP, TM, tile, LDT, cc, co);
+        } else {
+            float* stats = tile + TM * LDT;                       // [TM][2]: {mean, M2} of this CTA's BN columns per row
+            const int n = n0 + cc, sub = et % CPR;
+            uint32_t cs, rank;
+            asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+            (void)rank;
+            float gam[8], bet[8];
+            ld8(p.ln_gamma + n, 8, gam);
+            ld8(p.ln_beta + n, 8, bet);
+            // pass 1: v = acc + bias + residual -> fp32 row (global) and back into the staged tile; per-row {mean, M2}.
+            // All residual rows of this thread are requested first: one L2 round trip instead of one per row.
+            constexpr int NR = TM / RSTEP;
+            float rr[NR][8];
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                const int m = m0 + et / CPR + k * RSTEP;
+                if (m < p.M && p.res) ld8(p.res + (long)b * p.r_bs + (long)m * p.ldr + n, 8, rr[k]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) rr[k][i] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                const int r = et / CPR + k * RSTEP, m = m0 + r;
+                const bool valid = m < p.M;
+                float v[8];
+                const float4 x0 = *reinterpret_cast<const float4*>(tile + r * LDT + cc), x1 = *reinterpret_cast<const float4*>(tile + r * LDT + cc + 4);
+                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { v[i] = v[i] + co.t0[i] + rr[k][i]; s += v[i]; }
+                if (valid && p.outF) st8(p.outF + (long)b * p.c_bs + (long)m * p.ldc + n, 8, v);
+                *reinterpret_cast<float4*>(tile + r * LDT + cc) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(tile + r * LDT + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int o = CPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float mean_c = s * (1.f / BN);
+                float d2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { const float d = v[i] - mean_c; d2 += d * d; }
+#pragma unroll
+                for (int o = CPR / 2; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                if (sub == 0) *reinterpret_cast<float2*>(stats + r * 2) = make_float2(mean_c, d2);
+            }
+            cluster_sync_all();
+            // pass 2: merge the cluster's partial statistics (equal counts: Chan's formula), normalise this CTA's columns
+            for (int r = et / CPR; r < TM; r += RSTEP) {
+                const int m = m0 + r;
+                float mc[4], dc[4], mean = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (c < (int)cs) { const float2 t = ld_cluster_f2(stats + r * 2, (uint32_t)c); mc[c] = t.x; dc[c] = t.y; mean += t.x; }
+                }
+                mean /= (float)cs;
+                float m2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c < (int)cs) { const float d = mc[c] - mean; m2 += dc[c] + (float)BN * d * d; }
+                const float rstd = rsqrtf(m2 / (float)(BN * cs) + p.ln_eps);
+                if (m < p.M) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(tile + r * LDT + cc), x1 = *reinterpret_cast<const float4*>(tile + r * LDT + cc + 4);
+                    float y[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) y[i] = (y[i] - mean) * rstd * gam[i] + bet[i];
+                    st8b(p.outB2 + (long)b * p.c2_bs + (long)m * p.ldc2 + n, 8, y);
+                }
+            }
+            cluster_sync_all();   // nobody leaves while a peer may still read its statistics
+        }
     }
     if (threadIdx.x == 64) TC_TRACE(5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -321,6 +410,22 @@ bool launch_tc(const GemmParams& p, cudaStream_t st) {
     }
     dim3 grid(cdiv(p.M, TM), cdiv(p.N, BN), p.batch);
     bool done = false;
+    if (p.ln_gamma) {   // LayerNorm fused into the epilogue: the N tiles of a row form one cluster
+        if (p.act != ACT_NONE || p.act2 != ACT_NONE || p.N % BN != 0 || grid.y > 4 || !p.outB2 || !p.ln_beta || p.glu || p.ct_u || p.accumulate ||
+            p.out_scale != 1.f || p.bias2 || p.outB) return false;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = grid.y; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        CBX_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, ACT_NONE, ACT_NONE, true>, tmA, tmW, p, p.kc / TK, w_batched));
+        CBX_CHECK(cudaGetLastError());
+        g_tc_launches++;
+        return true;
+    }
     const int n_tiles = (int)grid.x * (int)grid.y * (int)grid.z;
     if (g_persistent_min > 0 && n_tiles >= g_persistent_min) {
         const int ctas = n_tiles < g_sms ? n_tiles : g_sms;
@@ -351,6 +456,8 @@ void gemm_tc_init() {
     CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
     CBX_FOR_ACT_PAIRS(CBX_ATTR)
 #undef CBX_ATTR
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<64, ACT_NONE, ACT_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM));
+    CBX_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<128, ACT_NONE, ACT_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM));
 #define CBX_ATTRP(A1, A2) \
     CBX_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<64, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPCfg<64>::SMEM)); \
     CBX_CHECK(cudaFuncSetAttribute(gemm_tc_persistent_kernel<128, A1, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPCfg<128>::SMEM));

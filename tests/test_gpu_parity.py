@@ -225,6 +225,22 @@ def test_flow_tiny_mel(tiny, tiny_cfg, dev):
     assert r < 2e-2, f"mel relative error {r}"
 
 
+def test_flow_fused_layernorm_epilogue_matches(tiny, tiny_cfg, dev, monkeypatch):
+    """CBX_FUSE_LN=1 moves the LayerNorms of the CFM transformer blocks into the epilogue of the producing GEMM (2-/4-CTA
+    clusters exchanging row statistics through distributed shared memory): same mel as with the separate norm kernels."""
+    eng, sd_dev, conds, voice = tiny
+    g = torch.Generator().manual_seed(12)
+    toks = torch.randint(0, 6561, (29,), generator=g).numpy()
+    monkeypatch.delenv("CBX_FUSE_LN", raising=False)
+    plain = eng.flow_infer(voice, toks).clone()
+    monkeypatch.setenv("CBX_FUSE_LN", "1")
+    fused = eng.flow_infer(voice, toks).clone()
+    monkeypatch.delenv("CBX_FUSE_LN")
+    torch.cuda.synchronize()
+    r = _rel(fused, plain)
+    assert 0 < r < 1e-2, f"fused vs separate LayerNorm: {r}"      # > 0: the fused path really ran; bf16 rounding points move, 10 Euler steps amplify
+
+
 def test_hift_stages(tiny, tiny_cfg, dev):
     """HiFT parity stage by stage.  The source is a chaotic function of f0 (phase = running sum of f0),
     so it is compared with the oracle's f0 teacher-forced, and the waveform with the oracle's source

@@ -317,7 +317,7 @@ def run_b200(args):
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as fh:
                 tr = json.load(fh)
-            key = "gemm_tc_kernel" if dom == 0 else ("attn_tc_kernel" if dom == 1 else None)
+            key = "gemm_tc_kernel" if dom == 0 else ("attn_tc_kernel" if dom == 1 else ("t3_decode_step" if dom == 2 else None))
             if key in tr:
                 roof["traffic"] = tr[key]["dram_bytes_per_launch"]
                 roof["traffic_note"] = tr[key].get("note", "")

@@ -345,6 +345,7 @@ def run_b200(args):
         if world == 1 and not args.no_concurrent:
             line["concurrent8"] = await concurrent_leg()
         line["s3gen_batch_sizes"] = {str(k): int(v) for k, v in sorted(eng.s3gen.batches.items())}
+        line["s3gen_padding"] = {"tokens_requested": int(eng.s3gen.pad_stats[0]), "tokens_after_padding": int(eng.s3gen.pad_stats[1])}
         print(json.dumps(line), flush=True)
 
     asyncio.run(main())

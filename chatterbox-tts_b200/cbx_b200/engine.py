@@ -236,6 +236,7 @@ class S3GenBatcher:
         self.cv = threading.Condition()
         self.running = True
         self.batches = collections.Counter()   # batch size -> count (bench / tests)
+        self.pad_stats = [0, 0]                # new tokens requested, new tokens computed after padding to the batch maximum
         n = workers or int(os.environ.get("CBX_S3GEN_WORKERS", "1"))
         # after the first pending job shows up, wait this long for companions (slices of concurrent requests become ready
         # within a decode round of each other): one batch of 8 beats a single call followed by a batch of 7
@@ -330,6 +331,9 @@ class S3GenBatcher:
                             st.synchronize()
                     with self.cv:
                         self.batches[len(live)] += 1
+                        lens = [len(j.toks) for j in live]
+                        self.pad_stats[0] += sum(lens)
+                        self.pad_stats[1] += max(lens) * len(lens)
                     for j, o in zip(live, outs):
                         j.out = o
                 except BaseException as ex:

@@ -424,7 +424,9 @@ class TextToSpeechEngine:
         # later chunks of a request start when chunk 0's first slice is on its way: "audio" = its PCM has been sent (lowest
         # first-chunk latency), "tokens" = its tokens are decoded (their prefills overlap the first S3Gen call: +throughput)
         self.hold_until = os.environ.get("CBX_HOLD_UNTIL", "audio")
-        self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=4 * max(8, n), thread_name_prefix="cbx-chunk")
+        # one worker thread per text chunk in flight: every request can have chunk_parallelism of them (most just wait for a T3
+        # slot or for tokens), so the pool is sized for that product and a new request never queues behind waiting chunks
+        self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=max(32, n * (self.chunk_parallelism + 1)), thread_name_prefix="cbx-chunk")
         self.s3gen: Optional[S3GenBatcher] = None
         self._pinned_pool: queue.Queue = queue.Queue()
         self.t3_slots: Optional[PrioritySlots] = None

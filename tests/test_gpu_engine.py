@@ -66,6 +66,10 @@ def test_concurrent_streams_match_sequential(engine):
     conc = asyncio.run(both())
     for a, b in zip(seq, conc):
         assert a.shape == b.shape
+        # T3 is batch invariant (same tokens) and a batched S3Gen pass reproduces the single call to float rounding, so the
+        # audio of a request must not depend on what else is running: int16 PCM within a few LSB
+        d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+        assert d.max() <= 64 and d.mean() < 1.0, f"concurrent vs sequential PCM: max {d.max()} mean {d.mean():.3f}"
 
 
 def test_zero_overlap_and_wav(engine):

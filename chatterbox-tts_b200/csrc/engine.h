@@ -42,6 +42,7 @@ struct T3Model {
     // megakernel state
     bool mega = false, mega_ok = false; MegaState mega_state; MegaLayer* d_layers = nullptr; unsigned long long* ll[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; unsigned int* epoch = nullptr;
     // prefill workspace
+    bf16 *xb = nullptr, *attn_b = nullptr, *act_b = nullptr; float* ss = nullptr;   // bf16 hand-over buffers of the decode step
     float* pf_x; bf16 *pf_xn, *pf_qkv, *pf_att, *pf_act; int* pf_text; int pf_max = 0;
     // host side
     std::vector<int> free_pages; std::vector<int> slot_used; std::vector<std::vector<int>> slot_pages; std::vector<int> slot_maxnew; std::vector<long> slot_pos_h;

@@ -66,6 +66,12 @@ void t3_alloc(cbx_engine* e) {
     m.qkv = e->scratch<float>((long)R * 3 * T3_D);
     m.attn = e->scratch<float>((long)R * T3_D);
     m.act = e->scratch<float>((long)R * T3_FFN);
+    // bf16 hand-over buffers of the decode step: residual row x gain of the consuming norm (+ per-strip sums of squares),
+    // attention output, SwiGLU activations
+    m.xb = e->scratch<bf16>((long)R * T3_D);
+    m.ss = e->scratch<float>((long)R * (T3_D / 16));
+    m.attn_b = e->scratch<bf16>((long)R * T3_D);
+    m.act_b = e->scratch<bf16>((long)R * T3_FFN);
     m.logits = e->scratch<float>((long)R * T3_VPAD);
     m.d_slots = e->scratch<int>(S);
     m.d_rowmap = e->scratch<int>(R);
@@ -239,26 +245,38 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         enqueue_sampler(e, n, noise, st);
         return;
     }
-    for (int li = 0; li < e->cfg.t3_layers; li++) {
+    // The residual stream stays fp32 in m.x; what the kernels hand to each other is bf16 (the input staging of every CTA is
+    // the dominant L2 traffic at 16 rows): a residual GEMV also writes bf16(x * gain of the next norm) and per-strip sums
+    // of squares, the consuming projection scales its outputs by the row's RMS factor.  Layer 0 reads the fp32 row the
+    // sampler wrote.
+    static const int gu_strips = [] { const char* v = getenv("CBX_T3_GU_STRIPS"); return v ? atoi(v) : 2; }();
+    const int n_layers = e->cfg.t3_layers;
+    for (int li = 0; li < n_layers; li++) {
         const T3Layer& l = m.layers[li];
-        GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1; q.x = m.x; q.ldx_in = T3_D;
-        q.row_map = m.d_rowmap; q.rows = rows; q.gain = l.ln1; q.eps = 1e-5f; q.out = m.qkv; q.ld_out = 3 * T3_D; q.epi = GEMV_STORE;
+        GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1;
+        q.row_map = m.d_rowmap; q.rows = rows; q.eps = 1e-5f; q.out = m.qkv; q.ld_out = 3 * T3_D; q.epi = GEMV_STORE;
+        if (li == 0) { q.x = m.x; q.ldx_in = T3_D; q.gain = l.ln1; }
+        else { q.xb = m.xb; q.ldxb = T3_D; q.ss_in = m.ss; q.n_ss = T3_D / 16; }
         launch_gemv(q, 8, st);
-        DecodeAttnParams a; a.qkv = m.qkv; a.out = m.attn; a.kv = m.kv + li * m.kv_layer_stride; a.kv_half = m.kv_half; a.page_table = m.page_table;
+        DecodeAttnParams a; a.qkv = m.qkv; a.out_b = m.attn_b; a.kv = m.kv + li * m.kv_layer_stride; a.kv_half = m.kv_half; a.page_table = m.page_table;
         a.max_pages = m.max_pages; a.slot_pos = m.slot_pos; a.row_map = m.d_rowmap; a.inv_freq = m.inv_freq; a.H = T3_H;
         launch_decode_attn(a, rows, e->cfg.max_seq, st);
-        GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.x = m.attn; o.ldx_in = T3_D;
+        GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.xb = m.attn_b; o.ldxb = T3_D;
         o.row_map = m.d_rowmap; o.rows = rows; o.out = m.x; o.ld_out = T3_D; o.epi = GEMV_RESID;
+        o.out_b = m.xb; o.ld_out_b = T3_D; o.next_gain = l.ln2; o.ss_out = m.ss;
         launch_gemv(o, 16, st);
-        GemvParams gu; gu.Wf = l.wgu_f; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.n_strips = 2 * T3_FFN / 16; gu.strips_per_cta = 2; gu.x = m.x; gu.ldx_in = T3_D;
-        gu.row_map = m.d_rowmap; gu.rows = rows; gu.gain = l.ln2; gu.eps = 1e-5f; gu.out = m.act; gu.ld_out = T3_FFN; gu.epi = GEMV_GLU;
+        GemvParams gu; gu.Wf = l.wgu_f; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.n_strips = 2 * T3_FFN / 16; gu.strips_per_cta = gu_strips;
+        gu.xb = m.xb; gu.ldxb = T3_D; gu.ss_in = m.ss; gu.n_ss = T3_D / 16;
+        gu.row_map = m.d_rowmap; gu.rows = rows; gu.eps = 1e-5f; gu.out_b = m.act_b; gu.ld_out_b = T3_FFN; gu.epi = GEMV_GLU;
         launch_gemv(gu, 8, st);
-        GemvParams d; d.Wf = l.wd_f; d.N = T3_D; d.K = T3_FFN; d.n_strips = T3_D / 16; d.strips_per_cta = 1; d.x = m.act; d.ldx_in = T3_FFN;
+        GemvParams d; d.Wf = l.wd_f; d.N = T3_D; d.K = T3_FFN; d.n_strips = T3_D / 16; d.strips_per_cta = 1; d.xb = m.act_b; d.ldxb = T3_FFN;
         d.row_map = m.d_rowmap; d.rows = rows; d.out = m.x; d.ld_out = T3_D; d.epi = GEMV_RESID;
+        d.out_b = m.xb; d.ld_out_b = T3_D; d.next_gain = li + 1 < n_layers ? m.layers[li + 1].ln1 : m.final_norm; d.ss_out = m.ss;
         launch_gemv(d, 16, st);
     }
-    GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = 1; h.x = m.x; h.ldx_in = T3_D;
-    h.row_map = m.d_rowmap; h.rows = rows; h.gain = m.final_norm; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
+    GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = 1;
+    h.xb = m.xb; h.ldxb = T3_D; h.ss_in = m.ss; h.n_ss = T3_D / 16;
+    h.row_map = m.d_rowmap; h.rows = rows; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
     launch_gemv(h, 8, st);
     enqueue_sampler(e, n, noise, st);
 }

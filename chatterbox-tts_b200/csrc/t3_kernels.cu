@@ -21,8 +21,13 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
     const int ldx = p.K + 8;  // bf16 elements per staged row (+8 pad: conflict-free fragment reads)
     bf16* xs = reinterpret_cast<bf16*>(smem);                                   // [8*NT][ldx]
     float* part = reinterpret_cast<float*>(smem + (size_t)8 * NT * ldx * 2);    // [nwarps][S][16][8*NT]
+    float* sq = part + (size_t)nwarps * p.strips_per_cta * 16 * 8 * NT;         // [S][16][8*NT] squares of the new residual values
+    float* scl = sq + (size_t)p.strips_per_cta * 16 * 8 * NT;                   // [8*NT] RMS scale per row (ss_in)
+    int* rmap = reinterpret_cast<int*>(scl + 8 * NT);                           // [8*NT] compact row -> global row
+    constexpr int R = 8 * NT;
 
-    // weights do not depend on the previous kernel: fetch this warp's first batch of fragments before waiting for it
+    // weights and the row map do not depend on the previous kernel: fetch this warp's first batch of fragments and the
+    // map before waiting for it
     pdl_launch_dependents();
     uint4 wpre[8];
     {
@@ -31,19 +36,47 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
 #pragma unroll
         for (int u = 0; u < 8; u++) wpre[u] = (strip0 < p.n_strips && u < perp) ? __ldg(wp0 + (size_t)u * 32) : make_uint4(0u, 0u, 0u, 0u);
     }
+    if (tid < R) rmap[tid] = tid < p.rows ? p.row_map[tid] : 0;
+    __syncthreads();
     pdl_wait();
-    // ---- stage input rows (optionally RMS-normalised) as bf16: every thread owns float4 columns of all rows, so the
+    if (p.xb) {
+        // ---- bf16 rows written by the producing kernel: 16-byte chunks, eight in flight per thread
+        const int nch = p.K >> 3, sh = 31 - __clz(nch), total = R * nch;
+        for (int c0 = 0; c0 < total; c0 += blockDim.x * 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = c0 + u * blockDim.x + tid, r = c >> sh, ch = c & (nch - 1);
+                v[u] = (c < total && r < p.rows) ? *reinterpret_cast<const uint4*>(p.xb + (long)rmap[r] * p.ldxb + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int c = c0 + u * blockDim.x + tid, r = c >> sh, ch = c & (nch - 1);
+                if (c < total) *reinterpret_cast<uint4*>(xs + (size_t)r * ldx + ch * 8) = v[u];
+            }
+        }
+        if (tid < R) {
+            float sc = 1.f;
+            if (p.ss_in && tid < p.rows) {
+                const float4* sp = reinterpret_cast<const float4*>(p.ss_in + (long)rmap[tid] * p.n_ss);
+                float ss = 0.f;
+                for (int i = 0; i < p.n_ss / 4; i++) { const float4 t = sp[i]; ss += (t.x + t.y) + (t.z + t.w); }
+                sc = rsqrtf(ss / p.K + p.eps);
+            }
+            scl[tid] = sc;
+        }
+    } else {
+    // ---- stage fp32 input rows (optionally RMS-normalised) as bf16: every thread owns float4 columns of all rows, so the
     // whole staging is one global round trip; per-row sums of squares are reduced through shared memory
-    {
+        if (tid < R) scl[tid] = 1.f;
         float* red = part;   // [8*NT][nwarps] scratch inside the partial-sum area (free until the main loop ends)
-        constexpr int R = 8 * NT;
         const int nvec = p.K >> 2;
         for (int c0 = 0; c0 < nvec; c0 += blockDim.x) {
             const int c = c0 + tid;
             float4 v[R];
 #pragma unroll
             for (int r = 0; r < R; r++)
-                v[r] = (r < p.rows && c < nvec) ? *reinterpret_cast<const float4*>(p.x + (long)p.row_map[r] * p.ldx_in + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[r] = (r < p.rows && c < nvec) ? *reinterpret_cast<const float4*>(p.x + (long)rmap[r] * p.ldx_in + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.gain) {   // K == blockDim.x * 4 is not required: accumulate partial sums over the column passes
 #pragma unroll
                 for (int r = 0; r < R; r++) {
@@ -68,7 +101,7 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
                         float ss = 0.f;
                         for (int w = 0; w < nwarps; w++) ss += red[r * nwarps + w];
                         const float scale = rsqrtf(ss / p.K + p.eps);
-                        const float4 a = *reinterpret_cast<const float4*>(p.x + (long)p.row_map[r] * p.ldx_in + c * 4);   // L1 hit
+                        const float4 a = *reinterpret_cast<const float4*>(p.x + (long)rmap[r] * p.ldx_in + c * 4);   // L1 hit
                         o = make_uint2(pack_bf16(a.x * scale * gg.x, a.y * scale * gg.y), pack_bf16(a.z * scale * gg.z, a.w * scale * gg.w));
                     }
                     *reinterpret_cast<uint2*>(xs + (size_t)r * ldx + c * 4) = o;
@@ -136,9 +169,13 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
                 gsum += part[((size_t)(w * S + 2 * pr) * 16 + f) * (8 * NT) + r];
                 usum += part[((size_t)(w * S + 2 * pr + 1) * 16 + f) * (8 * NT) + r];
             }
+            gsum *= scl[r]; usum *= scl[r];
             int pair = (blockIdx.x * S) / 2 + pr;
-            if (pair * 2 + 1 < p.n_strips)
-                p.out[(long)p.row_map[r] * p.ld_out + pair * 16 + f] = gsum / (1.f + expf(-gsum)) * usum;
+            if (pair * 2 + 1 < p.n_strips) {
+                const float a = gsum / (1.f + expf(-gsum)) * usum;
+                if (p.out_b) p.out_b[(long)rmap[r] * p.ld_out_b + pair * 16 + f] = __float2bfloat16(a);
+                else p.out[(long)rmap[r] * p.ld_out + pair * 16 + f] = a;
+            }
         }
     } else {
         for (int i = tid; i < S * per_strip; i += blockDim.x) {
@@ -147,10 +184,27 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
             if (r >= p.rows || strip >= p.n_strips) continue;
             float s = 0.f;
             for (int w = 0; w < nwarps; w++) s += part[((size_t)(w * S + sl) * 16 + f) * (8 * NT) + r];
+            s *= scl[r];
             int col = strip * 16 + f;
             if (col >= p.N) continue;
-            float* o = p.out + (long)p.row_map[r] * p.ld_out + col;
-            if (p.epi == GEMV_RESID) *o += s; else *o = s;
+            float* o = p.out + (long)rmap[r] * p.ld_out + col;
+            if (p.epi == GEMV_RESID) {
+                const float v = *o + s;
+                *o = v;
+                if (p.out_b) p.out_b[(long)rmap[r] * p.ld_out_b + col] = __float2bfloat16(v * p.next_gain[col]);
+                if (p.ss_out) sq[(sl * 16 + f) * (8 * NT) + r] = v * v;
+            } else *o = s;
+        }
+        if (p.epi == GEMV_RESID && p.ss_out) {   // sum of squares of this strip's 16 new values per row, fixed order
+            __syncthreads();
+            for (int i = tid; i < S * 8 * NT; i += blockDim.x) {
+                const int sl = i / (8 * NT), r = i % (8 * NT), strip = blockIdx.x * S + sl;
+                if (r >= p.rows || strip >= p.n_strips) continue;
+                float ss = 0.f;
+#pragma unroll
+                for (int f = 0; f < 16; f++) ss += sq[(sl * 16 + f) * (8 * NT) + r];
+                p.ss_out[(long)rmap[r] * p.n_strips + strip] = ss;
+            }
         }
     }
 }
@@ -169,11 +223,14 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
     __shared__ float wm[8], wl[8];
     __shared__ float wo[8 * HD];
     const int h = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_prologue();
+    // the row map and the page table are written by the host between steps only: read them before waiting for the QKV kernel
+    pdl_launch_dependents();
     const int row = p.row_map[r];
     const int slot = row >> 1;
-    const int pos = p.slot_pos[slot];
     const int* pt = p.page_table + (long)row * p.max_pages;
+    int pte0 = warp < p.max_pages ? pt[warp] : 0, pte1 = warp + 8 < p.max_pages ? pt[warp + 8] : 0;
+    pdl_wait();
+    const int pos = p.slot_pos[slot];
     const float* qkv = p.qkv + (long)row * (3 * p.H * HD);
     bf16* kpool = p.kv;
     bf16* vpool = p.kv + p.kv_half;
@@ -191,20 +248,30 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
         vpool[base + tid] = __float2bfloat16(qkv[2 * p.H * HD + h * HD + tid]);
         vpool[base + tid + 32] = __float2bfloat16(qkv[2 * p.H * HD + h * HD + tid + 32]);
     }
-    __syncthreads();
     const int n = pos + 1, npages = (n + PAGE - 1) / PAGE;
     const int pp = lane >> 1, half = lane & 1;
+    // K and V of a page are fetched together; the page after it is in flight while this one is reduced.  Pages that do not
+    // hold the new position are fetched before the barrier (only the last page is written by this CTA).
+    uint4 ku[4], vu[4], kn[4], vn[4];
+    auto fetch = [&](int pte, uint4* k, uint4* v) {
+        const long off = (((long)pte * p.H + h) * PAGE + pp) * HD + half * 32;
+        const uint4* kp = reinterpret_cast<const uint4*>(kpool + off);
+        const uint4* vp = reinterpret_cast<const uint4*>(vpool + off);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { k[c] = kp[c]; v[c] = vp[c]; }
+    };
+    const bool early = warp < npages - 1;
+    if (early) fetch(pte0, ku, vu);
+    __syncthreads();
+    if (!early && warp < npages) fetch(pte0, ku, vu);
     float m = -INFINITY, lsum = 0.f;
     float acc[32];
 #pragma unroll
     for (int d = 0; d < 32; d++) acc[d] = 0.f;
     for (int pg = warp; pg < npages; pg += 8) {
-        const long off = (((long)pt[pg] * p.H + h) * PAGE + pp) * HD + half * 32;
-        const uint4* kp = reinterpret_cast<const uint4*>(kpool + off);
-        const uint4* vp = reinterpret_cast<const uint4*>(vpool + off);
-        uint4 ku[4], vu[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) { ku[c] = kp[c]; vu[c] = vp[c]; }
+        const int nx = pg + 8;
+        if (nx < npages) fetch(pte1, kn, vn);
+        const int pte2 = nx + 8 < npages ? pt[nx + 8] : 0;
         float sc = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -231,6 +298,9 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
                 acc[c * 8 + e * 2 + 1] = acc[c * 8 + e * 2 + 1] * corr + (pj > 0.f ? pj * f.y : 0.f);
             }
         }
+#pragma unroll
+        for (int c = 0; c < 4; c++) { ku[c] = kn[c]; vu[c] = vn[c]; }
+        pte1 = pte2;
     }
 #pragma unroll
     for (int d = 0; d < 32; d++) {
@@ -257,7 +327,8 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
             const float e = wm[w] == -INFINITY ? 0.f : expf(wm[w] - M);
             Lt += wl[w] * e; O += wo[w * HD + tid] * e;
         }
-        p.out[(long)row * (p.H * HD) + h * HD + tid] = O / Lt;
+        if (p.out_b) p.out_b[(long)row * (p.H * HD) + h * HD + tid] = __float2bfloat16(O / Lt);
+        else p.out[(long)row * (p.H * HD) + h * HD + tid] = O / Lt;
     }
 }
 
@@ -515,7 +586,7 @@ void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
     CBX_REQUIRE(p.K % 16 == 0 && (p.K / 16) % nwarps == 0, "gemv: K/16 must divide by the warp count");
     const int NT = p.rows <= 8 ? 1 : 2;
     const int S = p.strips_per_cta;
-    size_t smem = (size_t)8 * NT * (p.K + 8) * 2 + (size_t)nwarps * S * 16 * 8 * NT * 4;
+    size_t smem = (size_t)8 * NT * (p.K + 8) * 2 + (size_t)(nwarps + 1) * S * 16 * 8 * NT * 4 + 2 * 8 * NT * 4;
     int grid = cdiv(p.n_strips, S);
     ProfScope ps(PC_GEMV, (double)p.n_strips * 16 * p.K * 2 + (double)p.rows * (p.K + p.N) * 4, st);
     CBX_REQUIRE(smem <= 200 * 1024, "gemv: staging exceeds shared memory");

@@ -12,6 +12,12 @@ struct GemvParams {
     const int* row_map = nullptr; int rows = 0;   // compact row -> global row (slot*2 + cfg_row)
     const float* gain = nullptr; float eps = 1e-5f;   // non-null: RMSNorm the input rows first
     float* out = nullptr; long ld_out = 0; int epi = GEMV_STORE;
+    // bf16 activations between the kernels of a step (rows > 2 make the per-CTA input staging the dominant L2 traffic):
+    const bf16* xb = nullptr; long ldxb = 0;      // bf16 input rows (replaces x).  With ss_in they hold x * norm gain and
+    const float* ss_in = nullptr; int n_ss = 0;   // the outputs are scaled by rsqrt(sum(ss_in[row][0..n_ss)) / K + eps)
+    bf16* out_b = nullptr; long ld_out_b = 0;     // GLU: bf16 activations (instead of out); RESID: bf16(x_new * next_gain)
+    const float* next_gain = nullptr;             // RESID: gain of the RMSNorm that consumes the updated residual row
+    float* ss_out = nullptr;                      // RESID: [rows_total][n_strips] sum of squares of this strip's 16 new values
 };
 void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st);
 
@@ -27,7 +33,8 @@ struct T3SlotState {   // device-resident per-stream decode state
 
 struct DecodeAttnParams {
     const float* qkv = nullptr;          // [rows_total][3*H*64] fp32 (raw projections)
-    float* out = nullptr;                // [rows_total][H*64] fp32
+    float* out = nullptr;                // [rows_total][H*64] fp32 (or out_b: the same as bf16)
+    bf16* out_b = nullptr;
     bf16* kv = nullptr; long kv_half = 0;   // this layer's pool: K at kv, V at kv + kv_half; [page][H][16][64]
     const int* page_table = nullptr; int max_pages = 0;   // [rows_total][max_pages]
     const int* slot_pos = nullptr;       // [slots]

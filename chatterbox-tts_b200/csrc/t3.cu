@@ -274,7 +274,8 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         d.out_b = m.xb; d.ld_out_b = T3_D; d.next_gain = li + 1 < n_layers ? m.layers[li + 1].ln1 : m.final_norm; d.ss_out = m.ss;
         launch_gemv(d, 16, st);
     }
-    GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = 1;
+    static const int head_strips = [] { const char* v = getenv("CBX_T3_HEAD_STRIPS"); return v ? atoi(v) : 1; }();
+    GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = head_strips;
     h.xb = m.xb; h.ldxb = T3_D; h.ss_in = m.ss; h.n_ss = T3_D / 16;
     h.row_map = m.d_rowmap; h.rows = rows; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
     launch_gemv(h, 8, st);

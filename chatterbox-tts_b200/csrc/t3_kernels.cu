@@ -2,6 +2,7 @@
 // fused RMSNorm / residual / SwiGLU epilogues, RoPE + paged-KV decode attention, and the one-kernel
 // CFG-mix -> repetition-penalty -> temperature -> min-p -> top-p -> sample step.
 // Also the prefill helpers (embedding assembly, RoPE + KV page write).
+#include <cstdlib>
 #include "common.cuh"
 #include "t3_kernels.cuh"
 
@@ -39,6 +40,12 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
     if (tid < R) rmap[tid] = tid < p.rows ? p.row_map[tid] : 0;
     __syncthreads();
     pdl_wait();
+    // residual epilogue: the old value of this thread's output element is requested now, not after the main loop
+    float x_old = 0.f;
+    if (p.epi == GEMV_RESID && p.strips_per_cta == 1 && tid < 16 * R) {
+        const int f = tid / R, r = tid % R, col = blockIdx.x * 16 + f;
+        if (r < p.rows && col < p.N) x_old = p.out[(long)rmap[r] * p.ld_out + col];
+    }
     if (p.xb) {
         // ---- bf16 rows written by the producing kernel: 16-byte chunks, eight in flight per thread
         const int nch = p.K >> 3, sh = 31 - __clz(nch), total = R * nch;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
             if (col >= p.N) continue;
             float* o = p.out + (long)rmap[r] * p.ld_out + col;
             if (p.epi == GEMV_RESID) {
-                const float v = *o + s;
+                const float v = ((S == 1 && i == tid) ? x_old : *o) + s;
                 *o = v;
                 if (p.out_b) p.out_b[(long)rmap[r] * p.ld_out_b + col] = __float2bfloat16(v * p.next_gain[col]);
                 if (p.ss_out) sq[(sl * 16 + f) * (8 * NT) + r] = v * v;
@@ -218,6 +225,7 @@ constexpr int PAGE = 16, HD = 64;
 // Flash-decoding form: each of the 8 warps streams whole KV pages (K and V of a page are fetched together) and keeps an
 // online-softmax partial (m, l, o[64]); the partials are merged in shared memory -- two block barriers and two global
 // round trips instead of five and three.
+template <bool PIPE>
 __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams p) {
     __shared__ float qs[HD];
     __shared__ float wm[8], wl[8];
@@ -229,11 +237,25 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
     const int slot = row >> 1;
     const int* pt = p.page_table + (long)row * p.max_pages;
     int pte0 = warp < p.max_pages ? pt[warp] : 0, pte1 = warp + 8 < p.max_pages ? pt[warp + 8] : 0;
+    bf16* kpool = p.kv;
+    bf16* vpool = p.kv + p.kv_half;
+    const int pp = lane >> 1, half = lane & 1;
+    // K and V of a page are fetched together; the page after it is in flight while this one is reduced.  The first page of
+    // every warp is fetched BEFORE waiting for the QKV kernel: pages below the one that receives the new position were
+    // completed a whole step ago (unused table entries are 0, a valid page), so the read is safe and overlaps the
+    // previous kernel's tail; it is only used if it turns out not to be the last page.
+    uint4 ku[4], vu[4], kn[4], vn[4];
+    auto fetch = [&](int pte, uint4* k, uint4* v) {
+        const long off = (((long)pte * p.H + h) * PAGE + pp) * HD + half * 32;
+        const uint4* kp = reinterpret_cast<const uint4*>(kpool + off);
+        const uint4* vp = reinterpret_cast<const uint4*>(vpool + off);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { k[c] = kp[c]; v[c] = vp[c]; }
+    };
+    if (PIPE) fetch(pte0, ku, vu);
     pdl_wait();
     const int pos = p.slot_pos[slot];
     const float* qkv = p.qkv + (long)row * (3 * p.H * HD);
-    bf16* kpool = p.kv;
-    bf16* vpool = p.kv + p.kv_half;
     if (tid < 32) {
         // rotate_half RoPE: pairs (d, d+32)
         float sn, cs;
@@ -249,19 +271,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
         vpool[base + tid + 32] = __float2bfloat16(qkv[2 * p.H * HD + h * HD + tid + 32]);
     }
     const int n = pos + 1, npages = (n + PAGE - 1) / PAGE;
-    const int pp = lane >> 1, half = lane & 1;
-    // K and V of a page are fetched together; the page after it is in flight while this one is reduced.  Pages that do not
-    // hold the new position are fetched before the barrier (only the last page is written by this CTA).
-    uint4 ku[4], vu[4], kn[4], vn[4];
-    auto fetch = [&](int pte, uint4* k, uint4* v) {
-        const long off = (((long)pte * p.H + h) * PAGE + pp) * HD + half * 32;
-        const uint4* kp = reinterpret_cast<const uint4*>(kpool + off);
-        const uint4* vp = reinterpret_cast<const uint4*>(vpool + off);
-#pragma unroll
-        for (int c = 0; c < 4; c++) { k[c] = kp[c]; v[c] = vp[c]; }
-    };
-    const bool early = warp < npages - 1;
-    if (early) fetch(pte0, ku, vu);
+    const bool early = PIPE && warp < npages - 1;
     __syncthreads();
     if (!early && warp < npages) fetch(pte0, ku, vu);
     float m = -INFINITY, lsum = 0.f;
@@ -270,8 +280,11 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
     for (int d = 0; d < 32; d++) acc[d] = 0.f;
     for (int pg = warp; pg < npages; pg += 8) {
         const int nx = pg + 8;
-        if (nx < npages) fetch(pte1, kn, vn);
-        const int pte2 = nx + 8 < npages ? pt[nx + 8] : 0;
+        int pte2 = 0;
+        if (PIPE) {
+            if (nx < npages) fetch(pte1, kn, vn);
+            pte2 = nx + 8 < npages ? pt[nx + 8] : 0;
+        } else if (pg != warp) fetch(pt[pg], ku, vu);
         float sc = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -298,9 +311,11 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
                 acc[c * 8 + e * 2 + 1] = acc[c * 8 + e * 2 + 1] * corr + (pj > 0.f ? pj * f.y : 0.f);
             }
         }
+        if (PIPE) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) { ku[c] = kn[c]; vu[c] = vn[c]; }
-        pte1 = pte2;
+            for (int c = 0; c < 4; c++) { ku[c] = kn[c]; vu[c] = vn[c]; }
+            pte1 = pte2;
+        }
     }
 #pragma unroll
     for (int d = 0; d < 32; d++) {
@@ -361,9 +376,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) {
     pdl_prologue();
     __shared__ float red[32];
-    __shared__ float es[SAMP_T * SAMP_E];
-    __shared__ float wsum[32];
-    __shared__ unsigned int s_lo, s_hi;
+    __shared__ float wsum2[2 * 32 * 32];
     __shared__ float bestv[32];
     __shared__ int besti[32];
     const int slot = p.slots[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -409,36 +422,54 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
         for (int e = 0; e < SAMP_E; e++) z2 += ex[e];
         z2 = block_reduce_sum(z2, red);
         const float target = (1.f - st->top_p) * z2;
+        // 33-way search on the float bit pattern: invariant mass(e <= lo) <= target < mass(e <= hi).  Every thread keeps its
+        // nine values in registers and evaluates all 32 thresholds of a round; a butterfly leaves threshold j's warp total
+        // in lane j, the 32 warp totals are summed by every warp (fixed order), so all threads take the same decision with
+        // one block barrier per round.
+        unsigned int lo = 0u, hi = 0x3F800000u;
+        int round = 0;
+        while (hi - lo > 1u) {
+            const unsigned long long span = hi - lo;
+            float mj[32];
 #pragma unroll
-        for (int e = 0; e < SAMP_E; e++) es[tid + e * SAMP_T] = ex[e];
-        if (tid == 0) { s_lo = 0u; s_hi = 0x3F800000u; }
-        __syncthreads();
-        // 33-way search on the float bit pattern: invariant mass(e <= lo) <= target < mass(e <= hi)
-        while (true) {
-            unsigned int lo = s_lo, hi = s_hi;
-            if (hi - lo <= 1u) break;
-            unsigned long long span = hi - lo;
-            unsigned int t = lo + (unsigned int)((span * (unsigned)(warp + 1)) / 33ull);
-            if (t <= lo) t = lo + 1;
-            if (t >= hi) t = hi - 1;
-            float thr = __uint_as_float(t);
-            float m = 0.f;
-            for (int i = lane; i < SAMP_T * SAMP_E; i += 32) { float v = es[i]; m += (v <= thr) ? v : 0.f; }
-            m = warp_sum(m);
-            if (lane == 0) { wsum[warp] = m; red[warp] = __uint_as_float(t); }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned int nlo = lo, nhi = hi;
-                for (int q = 0; q < 32; q++) {
-                    unsigned int tq = __float_as_uint(red[q]);
-                    if (wsum[q] <= target) { if (tq > nlo) nlo = tq; }
-                    else { if (tq < nhi) nhi = tq; }
-                }
-                s_lo = nlo; s_hi = nhi;
+            for (int j = 0; j < 32; j++) {
+                unsigned int t = lo + (unsigned int)((span * (unsigned)(j + 1)) / 33ull);
+                t = t <= lo ? lo + 1 : t;
+                t = t >= hi ? hi - 1 : t;
+                const float thr = __uint_as_float(t);
+                float m = 0.f;
+#pragma unroll
+                for (int e = 0; e < SAMP_E; e++) m += (ex[e] <= thr) ? ex[e] : 0.f;
+                mj[j] = m;
             }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < o; i++) {
+                    const bool up = (lane & o) != 0;
+                    const float send = up ? mj[i] : mj[i + o];
+                    const float keep = up ? mj[i + o] : mj[i];
+                    mj[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            float* buf = wsum2 + (round & 1) * 1024;
+            buf[warp * 32 + lane] = mj[0];
             __syncthreads();
+            float tot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; q++) tot += buf[q * 32 + lane];
+            const unsigned int okm = __ballot_sync(0xffffffffu, tot <= target);
+            const int cnt = __popc(okm);                  // mass is monotone in the threshold: okm is a prefix mask
+            auto thr_of = [&](int j) {
+                unsigned int t = lo + (unsigned int)((span * (unsigned)(j + 1)) / 33ull);
+                t = t <= lo ? lo + 1 : t;
+                return t >= hi ? hi - 1 : t;
+            };
+            const unsigned int nlo = cnt > 0 ? thr_of(cnt - 1) : lo, nhi = cnt < 32 ? thr_of(cnt) : hi;
+            lo = nlo; hi = nhi;
+            round++;
         }
-        const float cut = __uint_as_float(s_lo);
+        const float cut = __uint_as_float(lo);
 #pragma unroll
         for (int e = 0; e < SAMP_E; e++)
             if (ex[e] <= cut) ex[e] = 0.f;
@@ -596,7 +627,12 @@ void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
 }
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st) {
     ProfScope ps(PC_DECODE_ATTN, 0.0, st);
-    launch_pdl(decode_attn_kernel, dim3(p.H, rows), dim3(256), 0, st, p);
+    // prefetching pays while the step is latency-bound (0.78 vs 0.81 ms at 2 rows); at 16 rows the speculative reads compete
+    // with the next projection's weight stream (1.08 vs 0.99 ms).  Both instances compute bit-identical results.
+    static const int pipe_env = [] { const char* v = getenv("CBX_T3_ATTN_PIPE"); return v ? atoi(v) : -1; }();
+    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : rows <= 4;
+    if (pipe) launch_pdl(decode_attn_kernel<true>, dim3(p.H, rows), dim3(256), 0, st, p);
+    else launch_pdl(decode_attn_kernel<false>, dim3(p.H, rows), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st) {

@@ -423,7 +423,13 @@ class TextToSpeechEngine:
         self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "8"))
         # later chunks of a request start when chunk 0's first slice is on its way: "audio" = its PCM has been sent (lowest
         # first-chunk latency), "tokens" = its tokens are decoded (their prefills overlap the first S3Gen call: +throughput)
+        # "auto": "audio" for a request that is alone on the GPU, "tokens" when others are in flight.  Measured at 8 streams:
+        # with 8 T3 stream slots "tokens" wins (first chunk p50 190 vs 251 ms), with the default 16 slots it loses badly
+        # (669 vs 227 ms: the released chunks rotate with the other requests' first chunks in the decode batches), so the
+        # default stays "audio"
         self.hold_until = os.environ.get("CBX_HOLD_UNTIL", "audio")
+        self._inflight = 0
+        self._inflight_lock = threading.Lock()
         # one worker thread per text chunk in flight: every request can have chunk_parallelism of them (most just wait for a T3
         # slot or for tokens), so the pool is sized for that product and a new request never queues behind waiting chunks
         self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=max(32, n * (self.chunk_parallelism + 1)), thread_name_prefix="cbx-chunk")
@@ -662,7 +668,7 @@ class TextToSpeechEngine:
                         # consecutive slices of this chunk can ride in the same batch when T3 runs ahead of S3Gen
                         if ci == 0 and first_slice:
                             trace("slice1_tokens")
-                            if self.hold_until == "tokens":
+                            if self.hold_until == "tokens" or (self.hold_until == "auto" and self._inflight > 1):
                                 first_slice_ready.set()
                         job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx)
                         prev_job = job
@@ -793,6 +799,8 @@ class TextToSpeechEngine:
                             raise _Cancelled()
 
             def work():
+                with self._inflight_lock:
+                    self._inflight += 1
                 try:
                     self._run_request(text, voice_id, cfg_guidance_weight, synthesis_temperature, text_processing_chunk_size,
                                       audio_tokens_per_slice, remove_trailing_milliseconds, remove_leading_milliseconds,
@@ -806,6 +814,9 @@ class TextToSpeechEngine:
                         emit(ex)
                     except _Cancelled:
                         pass
+                finally:
+                    with self._inflight_lock:
+                        self._inflight -= 1
 
             fut = loop.run_in_executor(self.request_executor, work)
             first = True

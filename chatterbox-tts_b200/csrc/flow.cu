@@ -117,7 +117,12 @@ void lane_alloc(cbx_engine* e, Lane& L, int bmax) {
     const long B = bmax;
     L.bmax = bmax;
     const long Tt = c.max_prompt_tokens + c.max_s3_tokens, T = 2 * Tt, Tg = 2L * c.max_s3_tokens;
-    CBX_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+    {   // CBX_S3GEN_PRIORITY=1: S3Gen lanes at the highest stream priority (their CTAs are placed before pending T3 ones)
+        int lo = 0, hi = 0;
+        CBX_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char* pr = getenv("CBX_S3GEN_PRIORITY");
+        CBX_CHECK(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, (pr && pr[0] == '1') ? hi : lo));
+    }
     CBX_CHECK(cudaEventCreateWithFlags(&L.ev_in, cudaEventDisableTiming));
     CBX_CHECK(cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
     if (bmax > 0) {   // bmax == 0: a vocoder-only workspace (parallel HiFT streams of a batch lane)

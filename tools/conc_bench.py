@@ -21,7 +21,7 @@ words = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 sd = random_state_dict(ModelConfig(), 0)
 for lanes in lanes_list:
     eng = TextToSpeechEngine("cuda:0", concurrent_requests=streams, sampling=SamplingDefaults(tokens_per_word=10), seed=0, state_dict=sd,
-                             native_kwargs=dict(n_lanes=lanes, max_streams=max(8, streams)))
+                             native_kwargs=dict(n_lanes=lanes, max_streams=max(16, streams)))
 
     async def main():
         await eng.ainit()
@@ -42,7 +42,7 @@ for lanes in lanes_list:
         dt = time.time() - t0
         audio = sum(r[0] for r in res) / 2 / 24000.0
         firsts = sorted(r[1] for r in res)
-        print(json.dumps({"streams": streams, "lanes": lanes, "audio_s_per_s": audio / dt, "seconds": dt, "first_chunk_ms_p50": firsts[len(firsts) // 2],
+        print(json.dumps({"streams": streams, "lanes": lanes, "audio_s_per_s": audio / dt, "seconds": dt, "first_chunk_ms_p50": firsts[len(firsts) // 2], "first_chunk_ms_all": [round(f, 1) for f in firsts], "s3gen_batches": dict(sorted(eng.s3gen.batches.items())),
                           "t3_rounds": eng.scheduler.rounds}), flush=True)
     asyncio.run(main())
     eng.shutdown()

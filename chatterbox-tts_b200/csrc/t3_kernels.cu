@@ -627,10 +627,11 @@ void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
 }
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st) {
     ProfScope ps(PC_DECODE_ATTN, 0.0, st);
-    // prefetching pays while the step is latency-bound (0.78 vs 0.81 ms at 2 rows); at 16 rows the speculative reads compete
-    // with the next projection's weight stream (1.08 vs 0.99 ms).  Both instances compute bit-identical results.
+    // prefetching pays while the step is latency-bound (0.78 vs 0.81 ms at 2 rows, 0.82 vs 0.89 ms at 8); at 16 rows the
+    // speculative reads compete with the next projection's weight stream (1.08 vs 0.99 ms).  Both instances compute
+    // bit-identical results.
     static const int pipe_env = [] { const char* v = getenv("CBX_T3_ATTN_PIPE"); return v ? atoi(v) : -1; }();
-    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : rows <= 4;
+    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : rows <= 8;
     if (pipe) launch_pdl(decode_attn_kernel<true>, dim3(p.H, rows), dim3(256), 0, st, p);
     else launch_pdl(decode_attn_kernel<false>, dim3(p.H, rows), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());

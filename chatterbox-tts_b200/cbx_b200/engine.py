@@ -205,11 +205,15 @@ class T3Scheduler(threading.Thread):
 class _S3Job:
     """One S3Gen call in flight: `dep` is the job whose source output is this call's cache_source (the previous slice of
     the same text chunk under the "full" overlap strategy), or None."""
-    __slots__ = ("voice", "toks", "dep", "seed", "done", "out", "err", "dropped")
+    __slots__ = ("voice", "toks", "dep", "seed", "done", "out", "err", "dropped", "urgent", "consumed")
 
-    def __init__(self, voice, toks, dep, seed):
+    def __init__(self, voice, toks, dep, seed, urgent=False):
         self.voice, self.toks, self.dep, self.seed = voice, toks, dep, seed
         self.done, self.out, self.err, self.dropped = threading.Event(), None, None, False
+        # urgent: the first audio of a request.  The batcher gives its consumer a short exclusive window before it starts the
+        # next batch: the PCM kernel + D2H of the emitter otherwise queue inside the driver behind the ~5 000-launch burst of the
+        # next S3Gen call (measured: the first chunk intermittently arrived 60-150 ms late, 4 ms late at best)
+        self.urgent, self.consumed = urgent, (threading.Event() if urgent else None)
 
     def wait(self):
         self.done.wait()
@@ -241,12 +245,13 @@ class S3GenBatcher:
         # after the first pending job shows up, wait this long for companions (slices of concurrent requests become ready
         # within a decode round of each other): one batch of 8 beats a single call followed by a batch of 7
         self.gather_s = float(os.environ.get("CBX_S3GEN_GATHER_MS", "2")) * 1e-3
+        self.urgent_window_s = float(os.environ.get("CBX_S3GEN_URGENT_MS", "15")) * 1e-3   # upper bound; the emitter ends it
         self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
         for t in self.threads:
             t.start()
 
-    def submit(self, voice, toks, dep: Optional[_S3Job], seed) -> _S3Job:
-        job = _S3Job(voice, toks, dep, seed)
+    def submit(self, voice, toks, dep: Optional[_S3Job], seed, urgent=False) -> _S3Job:
+        job = _S3Job(voice, toks, dep, seed, urgent)
         with self.cv:
             self.jobs.append(job)
             self.cv.notify_all()
@@ -341,6 +346,9 @@ class S3GenBatcher:
                         j.err = ex
                 for j in live:
                     j.done.set()
+                for j in live:
+                    if j.urgent and j.err is None and not j.dropped:
+                        j.consumed.wait(self.urgent_window_s)
             with self.cv:
                 self.cv.notify_all()     # jobs that were waiting for this batch's outputs are runnable now
 
@@ -532,15 +540,18 @@ class TextToSpeechEngine:
     def _pinned_get(self):
         """A pinned int16 staging buffer (one S3Gen call of PCM at most) from the engine's pool, or None without a GPU."""
         if self._backend is not None or self.device_sink:
-            return None
+            return None, None
         try:
             return self._pinned_pool.get_nowait()
         except queue.Empty:
-            return torch.empty(960 * 1100, dtype=torch.int16, pin_memory=True)
+            # (pinned host buffer, device buffer): the pair lives in the pool for the life of the engine, so the emit path of a
+            # request never allocates; every use is followed by a stream sync, so reuse across requests / streams is safe
+            return (torch.empty(960 * 1100, dtype=torch.int16, pin_memory=True),
+                    torch.empty(960 * 1100, dtype=torch.int16, device=f"cuda:{self.gpu_id}"))
 
-    def _pinned_put(self, buf):
-        if buf is not None:
-            self._pinned_pool.put(buf)
+    def _pinned_put(self, pair):
+        if pair is not None and pair[0] is not None:
+            self._pinned_pool.put(pair)
 
     def _wait_tokens(self, s: _T3Stream, n: int, token: Optional[CancellationToken]):
         """Blocks until the stream holds >= n tokens or is finished."""
@@ -588,7 +599,12 @@ class TextToSpeechEngine:
                 """crossfade (optional) + PCM on device, then D2H and hand the bytes to the event loop."""
                 if n_out <= 0:
                     return
-                pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0)
+                if pinned is not None and n_out <= pinned.shape[0]:
+                    pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0, out=pcm_dev)
+                else:
+                    pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0)
+                if not first_sent:
+                    trace("pcm_enqueued")
                 if self.device_sink:
                     emit(int(n_out))
                     return
@@ -596,6 +612,8 @@ class TextToSpeechEngine:
                 # multi-call staged copy that queues behind the launch bursts of the S3Gen thread inside the driver)
                 if pinned is not None and n_out <= pinned.shape[0]:
                     pinned[:n_out].copy_(pcm, non_blocking=True)
+                    if not first_sent:
+                        trace("d2h_enqueued")
                     torch.cuda.current_stream().synchronize()
                     data = pinned[:n_out].numpy().tobytes()
                 else:
@@ -604,7 +622,7 @@ class TextToSpeechEngine:
                     trace("first_pcm_host")
                 emit(data)
 
-            pinned = self._pinned_get()
+            pinned, pcm_dev = self._pinned_get()
             cancelled = (lambda: token is not None and token.is_cancelled())
             tr = self.stats.setdefault("trace", collections.deque(maxlen=64))
             trace = (lambda label: tr.append((label, round((time.time() - t_start) * 1e3, 1))))
@@ -670,7 +688,8 @@ class TextToSpeechEngine:
                             trace("slice1_tokens")
                             if self.hold_until == "tokens" or (self.hold_until == "auto" and self._inflight > 1):
                                 first_slice_ready.set()
-                        job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx)
+                        job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx,
+                                                urgent=(ci == 0 and first_slice))
                         prev_job = job
                         jobs.append(job)
                         outq[ci].put((job, first_slice, last))
@@ -755,6 +774,8 @@ class TextToSpeechEngine:
                                 if prev_tail is not None:
                                     send(prev_tail, prev_tail.shape[0], None)
                                 prev_tail = cur[n - fade_len:] if (fade_len > 0 and n > fade_len) else cur
+                        if job.urgent:
+                            job.consumed.set()
                         first_slice_ready.set()          # later chunks may start: the first audio no longer competes with them
                     first_slice_ready.set()
                     window.release()
@@ -764,7 +785,7 @@ class TextToSpeechEngine:
                     send(prev_tail, prev_tail.shape[0], None)     # reference `finally` flush (:756-760)
             finally:
                 stop.set()
-                self._pinned_put(pinned)
+                self._pinned_put((pinned, pcm_dev))
                 for j in jobs:
                     if not j.done.is_set():
                         j.dropped = True

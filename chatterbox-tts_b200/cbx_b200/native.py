@@ -220,8 +220,10 @@ class NativeEngine:
                                          C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, C.c_void_p(src.data_ptr()), _stream_ptr()))
         return src
 
-    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0):
-        out = torch.empty(n_out, device=cur.device, dtype=torch.int16)
+    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0, out=None):
+        # `out`: caller-owned int16 device buffer (the engine keeps one per request: an allocation on a request's fresh
+        # stream misses the caching allocator's per-stream pools and falls through to cudaMalloc, 4-50 ms with the GPU busy)
+        out = torch.empty(n_out, device=cur.device, dtype=torch.int16) if out is None else out[:n_out]
         L.check(self.lib.cbx_crossfade_pcm(self.h, C.c_void_p(cur.data_ptr()), n_out,
                                            C.c_void_p(prev_tail.data_ptr()) if prev_tail is not None else None, fade_len,
                                            C.c_void_p(out.data_ptr()), _stream_ptr()))

@@ -376,7 +376,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) {
     pdl_prologue();
     __shared__ float red[32];
-    __shared__ float wsum2[2 * 32 * 32];
+    __shared__ float wsum2[2 * 32];
     __shared__ float bestv[32];
     __shared__ int besti[32];
     const int slot = p.slots[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -422,51 +422,28 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
         for (int e = 0; e < SAMP_E; e++) z2 += ex[e];
         z2 = block_reduce_sum(z2, red);
         const float target = (1.f - st->top_p) * z2;
-        // 33-way search on the float bit pattern: invariant mass(e <= lo) <= target < mass(e <= hi).  Every thread keeps its
-        // nine values in registers and evaluates all 32 thresholds of a round; a butterfly leaves threshold j's warp total
-        // in lane j, the 32 warp totals are summed by every warp (fixed order), so all threads take the same decision with
-        // one block barrier per round.
+        // bisection on the float bit pattern: invariant mass(e <= lo) <= target < mass(e <= hi).  The whole block sits on one
+        // SM, so the search is bound by instruction issue, not latency: one threshold per round over the nine register-resident
+        // values of every thread (~30 rounds x ~60 instructions per warp) costs a fifth of evaluating 32 thresholds per round.
+        // Reduction order is fixed (thread: e ascending; warp: xor 16..1; block: the 32 warp totals by xor 16..1), every thread
+        // takes the same decision, one block barrier per round (double-buffered warp totals).
         unsigned int lo = 0u, hi = 0x3F800000u;
         int round = 0;
         while (hi - lo > 1u) {
-            const unsigned long long span = hi - lo;
-            float mj[32];
+            const unsigned int t = lo + ((hi - lo) >> 1);
+            const float thr = __uint_as_float(t);
+            float m = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                unsigned int t = lo + (unsigned int)((span * (unsigned)(j + 1)) / 33ull);
-                t = t <= lo ? lo + 1 : t;
-                t = t >= hi ? hi - 1 : t;
-                const float thr = __uint_as_float(t);
-                float m = 0.f;
+            for (int e = 0; e < SAMP_E; e++) m += (ex[e] <= thr) ? ex[e] : 0.f;
 #pragma unroll
-                for (int e = 0; e < SAMP_E; e++) m += (ex[e] <= thr) ? ex[e] : 0.f;
-                mj[j] = m;
-            }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-#pragma unroll
-                for (int i = 0; i < o; i++) {
-                    const bool up = (lane & o) != 0;
-                    const float send = up ? mj[i] : mj[i + o];
-                    const float keep = up ? mj[i + o] : mj[i];
-                    mj[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                }
-            }
-            float* buf = wsum2 + (round & 1) * 1024;
-            buf[warp * 32 + lane] = mj[0];
+            for (int o = 16; o >= 1; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+            float* buf = wsum2 + (round & 1) * 32;
+            if (lane == 0) buf[warp] = m;
             __syncthreads();
-            float tot = 0.f;
+            float tot = buf[lane];
 #pragma unroll
-            for (int q = 0; q < 32; q++) tot += buf[q * 32 + lane];
-            const unsigned int okm = __ballot_sync(0xffffffffu, tot <= target);
-            const int cnt = __popc(okm);                  // mass is monotone in the threshold: okm is a prefix mask
-            auto thr_of = [&](int j) {
-                unsigned int t = lo + (unsigned int)((span * (unsigned)(j + 1)) / 33ull);
-                t = t <= lo ? lo + 1 : t;
-                return t >= hi ? hi - 1 : t;
-            };
-            const unsigned int nlo = cnt > 0 ? thr_of(cnt - 1) : lo, nhi = cnt < 32 ? thr_of(cnt) : hi;
-            lo = nlo; hi = nhi;
+            for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (tot <= target) lo = t; else hi = t;
             round++;
         }
         const float cut = __uint_as_float(lo);

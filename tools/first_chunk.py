@@ -9,17 +9,20 @@ import bench
 from cbx_b200.engine import TextToSpeechEngine, SamplingDefaults
 
 async def main():
+    if os.environ.get('FC_GC') == '0':
+        import gc; gc.collect(); gc.freeze(); gc.disable()
     eng = TextToSpeechEngine("cuda:0", concurrent_requests=8, sampling=SamplingDefaults(tokens_per_word=bench.TOK_PER_WORD), seed=0)
     await eng.ainit()
     text = bench.synthetic_text(bench.WORDS)
-    for it in range(4):
+    for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
         eng._seq = 0
         eng.stats["trace"].clear() if "trace" in eng.stats else None
         t0 = time.time(); first = None
         async for chunk in eng.stream(text=text, output_format="raw_pcm", voice_id=None, request_id="bench", cancellation_token=None, **bench.REQ):
             if first is None and len(chunk):
                 first = (time.time() - t0) * 1e3
-        torch.cuda.synchronize()
-        print(it, "first chunk %.1f ms" % first, "total %.0f ms" % ((time.time() - t0) * 1e3), list(eng.stats["trace"])[:8], flush=True)
+        if os.environ.get("FC_SYNC", "1") == "1":
+            torch.cuda.synchronize()
+        print(it, "first chunk %.1f ms" % first, "total %.0f ms" % ((time.time() - t0) * 1e3), list(eng.stats["trace"])[3:9], flush=True)
     eng.shutdown()
 asyncio.run(main())

@@ -136,3 +136,30 @@ def test_priority_slots_serve_lowest_priority_first():
     assert order == [1, 3, 5]
     assert slots.acquire(9, cancelled=lambda: False)       # free again
     assert not slots.acquire(0, cancelled=lambda: True)    # a cancelled waiter gives up instead of blocking
+
+
+def test_urgent_job_gets_a_consumer_window_before_the_next_batch():
+    """The first audio of a request: the batcher does not start the next batch until the consumer has signalled that it
+    took the output (or the window expired), so the emitter's PCM kernel never queues behind the next call's launch burst."""
+    nat = BatchNative()
+    b = S3GenBatcher(nat, max_batch=8, workers=1)
+    b.urgent_window_s = 0.5
+    try:
+        first = b.submit(0, _toks(35), None, 1, urgent=True)
+        first.wait()
+        nxt = b.submit(0, _toks(70), first, 2)
+        time.sleep(0.15)
+        assert not nxt.done.is_set() and len(nat.batches) == 1      # still inside the window
+        first.consumed.set()
+        nxt.wait()
+        assert len(nat.batches) == 2
+        # a consumer that never answers (cancelled request) only costs the window
+        b.urgent_window_s = 0.05
+        u = b.submit(0, _toks(35, 3), None, 3, urgent=True)
+        u.wait()
+        t0 = time.time()
+        b.submit(0, _toks(35, 4), None, 4).wait()
+        assert time.time() - t0 < 2.0
+        assert not b.submit(0, _toks(3), None, 5).urgent
+    finally:
+        b.stop()

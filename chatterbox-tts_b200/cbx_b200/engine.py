@@ -116,15 +116,29 @@ class T3Scheduler(threading.Thread):
         self.lock = threading.Condition()
         self.running = True
         self.rounds = 0
+        # CBX_T3_ALIGN_OPENS_MS > 0 (opt-in, default 0): while every open stream is still at token 0 and other streams are being
+        # opened (their prefills run one after the other), the first decode round waits up to this long, so that requests that
+        # arrive together decode in lockstep and their first slices share ONE S3Gen batch instead of "first alone, rest in
+        # the next batch" (8 streams today: 120 ms for the first request, 220-234 ms for the other seven).  Host logic only;
+        # its effect on a B200 has not been measured yet.
+        self.align_s = float(os.environ.get("CBX_T3_ALIGN_OPENS_MS", "0")) * 1e-3
+        self.opening = 0
         self.start()
 
     def open(self, voice, text_ids, cfg_w, temp, sd: SamplingDefaults, seed, max_new) -> _T3Stream:
-        with self._ctx():
-            slot = self.native.t3_open(voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new)
-        s = _T3Stream(slot, max_new)
         with self.lock:
-            self.active.append(s)
-            self.lock.notify_all()
+            self.opening += 1
+        s = None
+        try:
+            with self._ctx():
+                slot = self.native.t3_open(voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new)
+            s = _T3Stream(slot, max_new)
+        finally:
+            with self.lock:
+                self.opening -= 1
+                if s is not None:
+                    self.active.append(s)
+                self.lock.notify_all()
         return s
 
     def cancel(self, s: _T3Stream):
@@ -149,6 +163,10 @@ class T3Scheduler(threading.Thread):
                     self.lock.wait(0.5)
                 if not self.running:
                     return
+                if self.align_s > 0 and self.opening > 0 and all(len(s.tokens) == 0 for s in self.active):
+                    t_end = time.time() + self.align_s
+                    while self.running and self.opening > 0 and time.time() < t_end:
+                        self.lock.wait(0.001)
                 batch = self.active[: self.max_batch]
             live = []
             for s in batch:

@@ -163,3 +163,52 @@ def test_urgent_job_gets_a_consumer_window_before_the_next_batch():
         assert not b.submit(0, _toks(3), None, 5).urgent
     finally:
         b.stop()
+
+
+def test_scheduler_can_align_streams_that_open_together(monkeypatch):
+    """CBX_T3_ALIGN_OPENS_MS (opt-in): streams whose prefills overlap in time start decoding in the same round."""
+    from cbx_b200.engine import T3Scheduler, SamplingDefaults
+    from fake_backend import FakeNative
+
+    class SlowOpen(FakeNative):
+        def __init__(self):
+            super().__init__()
+            self.first_batches, self.mu = [], threading.Lock()
+
+        def t3_open(self, *a, **kw):
+            with self.mu:                      # prefills are serialised on the device
+                time.sleep(0.03)
+                return super().t3_open(*a, **kw)
+
+        def t3_step(self, slots, n_steps=1, noise=None):
+            self.first_batches.append(sorted(slots))
+            return super().t3_step(slots, n_steps, noise)
+
+    def run(align_ms):
+        monkeypatch.setenv("CBX_T3_ALIGN_OPENS_MS", str(align_ms))
+        nat = SlowOpen()
+        sch = T3Scheduler(nat, max_batch=8)
+        try:
+            out = [None] * 4
+            def opener(i):
+                out[i] = sch.open(0, [255] + _toks(20, i) + [0], 0.5, 0.8, SamplingDefaults(), i, 40)
+            th = [threading.Thread(target=opener, args=(i,)) for i in range(4)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            for s in out:
+                with s.cv:
+                    while not s.finished:
+                        s.cv.wait(0.05)
+            return nat.first_batches[0], [list(s.tokens) for s in out]
+        finally:
+            sch.running = False
+            with sch.lock:
+                sch.lock.notify_all()
+
+    first_aligned, toks_aligned = run(500)
+    first_plain, toks_plain = run(0)
+    assert len(first_aligned) == 4            # all four streams in the first decode round
+    assert len(first_plain) < 4               # without alignment the first stream runs ahead of the others' prefills
+    assert sorted(map(tuple, toks_aligned)) == sorted(map(tuple, toks_plain))   # same tokens either way

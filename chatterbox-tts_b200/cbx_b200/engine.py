@@ -102,6 +102,7 @@ class _T3Stream:
         self.cancelled = False
         self.error: Optional[BaseException] = None
         self.cv = threading.Condition()
+        self.on_closed = None      # called once, after the native slot has been closed (releases the request's slot permit)
 
 
 class T3Scheduler(threading.Thread):
@@ -123,9 +124,17 @@ class T3Scheduler(threading.Thread):
         # its effect on a B200 has not been measured yet.
         self.align_s = float(os.environ.get("CBX_T3_ALIGN_OPENS_MS", "0")) * 1e-3
         self.opening = 0
+        self.unhealthy: Optional[BaseException] = None   # a native slot could not be closed: its pages are lost, refuse new work
         self.start()
 
-    def open(self, voice, text_ids, cfg_w, temp, sd: SamplingDefaults, seed, max_new) -> _T3Stream:
+    def open(self, voice, text_ids, cfg_w, temp, sd: SamplingDefaults, seed, max_new, on_closed=None) -> _T3Stream:
+        """Prefill + stream slot.  `on_closed` runs exactly once after the NATIVE slot has been closed (natural end, cancel or
+        error): the caller's slot permit must not be handed to another request before that, or the next t3_open finds no
+        free native slot."""
+        if self.unhealthy is not None:
+            raise RuntimeError(f"T3 engine is unhealthy after an unrecoverable error: {self.unhealthy}")
+        if not self.running:
+            raise RuntimeError("engine is shutting down")
         with self.lock:
             self.opening += 1
         s = None
@@ -133,6 +142,7 @@ class T3Scheduler(threading.Thread):
             with self._ctx():
                 slot = self.native.t3_open(voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new)
             s = _T3Stream(slot, max_new)
+            s.on_closed = on_closed
         finally:
             with self.lock:
                 self.opening -= 1
@@ -167,13 +177,11 @@ class T3Scheduler(threading.Thread):
                     t_end = time.time() + self.align_s
                     while self.running and self.opening > 0 and time.time() < t_end:
                         self.lock.wait(0.001)
-                batch = self.active[: self.max_batch]
-            live = []
-            for s in batch:
-                if s.cancelled:
-                    self._retire(s)
-                else:
-                    live.append(s)
+                dead = [s for s in self.active if s.cancelled]      # wherever they sit in the rotation
+                batch = [s for s in self.active if not s.cancelled][: self.max_batch]
+            for s in dead:
+                self._retire(s)
+            live = batch
             if not live:
                 continue
             try:
@@ -193,31 +201,43 @@ class T3Scheduler(threading.Thread):
             except BaseException as ex:  # surface engine failures to every waiting request
                 for s in live:
                     with s.cv:
-                        s.error, s.finished = ex, True
-                        s.cv.notify_all()
-                    self._retire(s, close=False)
+                        s.error = ex
+                    self._retire(s)      # always give the native slot and its KV pages back (or mark the engine unhealthy)
             # round-robin fairness when more streams than the batch size are open
             with self.lock:
                 if len(self.active) > self.max_batch:
                     self.active = self.active[self.max_batch:] + self.active[: self.max_batch]
 
-    def _retire(self, s: _T3Stream, close=True):
+    def _retire(self, s: _T3Stream):
         with self.lock:
-            if s in self.active:
-                self.active.remove(s)
-        if close:
-            try:
-                self.native.t3_close(s.slot)
-            except Exception:
-                pass
+            if s not in self.active:
+                return
+            self.active.remove(s)
+        try:
+            self.native.t3_close(s.slot)
+        except BaseException as ex:      # the slot and its pages are lost: stop handing out work instead of failing later opens
+            self.unhealthy = ex
+        cb, s.on_closed = s.on_closed, None
+        if cb is not None:
+            cb()
         with s.cv:
             s.finished = True
             s.cv.notify_all()
 
     def stop(self):
+        """Stops the scheduler and fails every stream that is still open, so no request thread waits for tokens forever."""
         self.running = False
         with self.lock:
             self.lock.notify_all()
+        if threading.current_thread() is not self:
+            self.join(timeout=10.0)
+        with self.lock:
+            rest = list(self.active)
+        for s in rest:
+            with s.cv:
+                if s.error is None and not s.finished:
+                    s.error = RuntimeError("engine is shutting down")
+            self._retire(s)
 
 
 class _S3Job:
@@ -467,8 +487,11 @@ class TextToSpeechEngine:
         self.scheduler: Optional[T3Scheduler] = None
         self.tokenizer = None
         self.seed = seed
+        self.weights_source = None
+        self._encoder_sd = None
         self.device_sink = device_sink   # bench `value` leg: PCM stays in HBM, emit() receives sample counts
         self._seq = 0
+        self._seq_lock = threading.Lock()
         self._ready = False
         self.stats = {"first_chunk_ms": []}
 
@@ -494,18 +517,24 @@ class TextToSpeechEngine:
         self.native = NativeEngine(self.cfg, device=self.gpu_id, **self.native_kwargs)
         sd = self._state_dict
         model_path = os.environ.get("MODEL_PATH", "models")
+        self.weights_source = "state_dict"
         if sd is None:
-            st = os.path.join(model_path, "cbx_b200.safetensors")
-            if os.path.exists(st):
-                from safetensors.torch import load_file
-                sd = load_file(st)
-            else:   # BASELINE.json configs: random-init Chatterbox weights
-                sd = random_state_dict(self.cfg, self.seed)
+            # merged file, or the upstream t3_cfg / s3gen files converted on the fly; a missing checkpoint is an ERROR as in
+            # the reference (from_local, :252-258) unless CBX_ALLOW_RANDOM_WEIGHTS=1 (checkpoint.py)
+            from .checkpoint import load_checkpoint
+            sd, self._encoder_sd, self.weights_source = load_checkpoint(model_path, self.cfg, self.seed)
         self.native.load_state_dict(sd)
         self._state_dict = None
         tj = os.path.join(model_path, "tokenizer.json")
         self.tokenizer = JsonTokenizer(tj) if os.path.exists(tj) else SyntheticTokenizer(self.cfg.t3.text_vocab)
-        self.default_conds = synthetic_conditionals(self.cfg)      # stands in for conds.pt (tts.conds, :399-404)
+        cp = os.path.join(model_path, "conds.pt")
+        if os.path.exists(cp):
+            from .checkpoint import load_conds
+            self.default_conds = load_conds(cp)                    # tts.conds (:399-404)
+        elif self.weights_source in ("state_dict", "random"):
+            self.default_conds = synthetic_conditionals(self.cfg)  # benchmark / tests: seeded tensors of trump.wav's shapes
+        else:
+            raise RuntimeError(f"{cp} is missing: a real checkpoint needs its default voice conditioning (reference :399-404)")
         self.voice_cache["default"] = self.native.voice_put("default", self.default_conds["t3"], self.default_conds["gen"])
         self.scheduler = T3Scheduler(self.native, max_batch=min(8, self.native_kwargs["max_streams"]))
         self.s3gen = S3GenBatcher(self.native)
@@ -546,6 +575,10 @@ class TextToSpeechEngine:
         from .weights import synthetic_conditionals
         import zlib
         import scipy.io.wavfile as wavfile
+        if self.weights_source in ("merged", "upstream"):
+            # a real checkpoint with seeded stand-in conditioning would silently speak in a random voice
+            raise RuntimeError("prepare_conditionals: the conditioning encoders (S3Tokenizer, CAMPPlus, VoiceEncoder) are not "
+                               "built yet (SURVEY 8f.1); with a real checkpoint use put_conditionals() with tensors computed upstream")
         sr, data = wavfile.read(wav_fpath)
         secs = min(data.shape[0] / float(sr), 10.0)
         ntok = max(3, min(int(secs * 25), 250))
@@ -571,13 +604,16 @@ class TextToSpeechEngine:
         if pair is not None and pair[0] is not None:
             self._pinned_pool.put(pair)
 
-    def _wait_tokens(self, s: _T3Stream, n: int, token: Optional[CancellationToken]):
-        """Blocks until the stream holds >= n tokens or is finished."""
+    def _wait_tokens(self, s: _T3Stream, n: int, token: Optional[CancellationToken], stop: Optional[threading.Event] = None):
+        """Blocks until the stream holds >= n tokens or is finished; gives up when the request is cancelled / stopped or the
+        scheduler has shut down (its streams would never finish)."""
         with s.cv:
             while len(s.tokens) < n and not s.finished:
-                if token is not None and token.is_cancelled():
+                if (token is not None and token.is_cancelled()) or (stop is not None and stop.is_set()):
                     self.scheduler.cancel(s)
                     return False
+                if not self.scheduler.running:
+                    raise RuntimeError("engine is shutting down")
                 s.cv.wait(0.05)
             if s.error:
                 raise s.error
@@ -586,20 +622,34 @@ class TextToSpeechEngine:
     # ------------------------------------------------------------------ the request pipeline (one thread per request)
     def _run_request(self, text, voice_id, cfg_w, temp, chunk_size, slice_len, trim_tail_ms, trim_lead_ms, overlap, fade_ms,
                      request_id, token: Optional[CancellationToken], emit, t_start):
-        nat, sched = self.native, self.scheduler
+        nat = self.native
         if self._backend is None:
             torch.cuda.set_device(self.gpu_id)
         with (torch.cuda.stream(torch.cuda.Stream()) if self._backend is None else contextlib.nullcontext()):
-            if voice_id:
-                vid = Path(voice_id).name
-                if vid not in self.voice_cache:
-                    path = self.voice_manager.get_voice_path(voice_id)
-                    if path is None:
-                        raise ValueError(f"voice '{voice_id}' not found")
-                    self.prepare_conditionals(path)
-                voice = self.voice_cache[vid]
-            else:
-                voice = self.voice_cache["default"]
+            vid = Path(voice_id).name if voice_id else "default"
+            if vid not in self.voice_cache or (hasattr(nat, "voice_slot") and nat.voice_slot(vid) is None):   # never seen, or evicted (LRU)
+                path = self.voice_manager.get_voice_path(voice_id)
+                if path is None:
+                    raise ValueError(f"voice '{voice_id}' not found")
+                self.prepare_conditionals(path)
+            # pinned for the life of the request: the native voice cache neither evicts nor rewrites a slot that an open
+            # request still reads (its T3 prefills and S3Gen jobs); released when every job of the request has retired
+            pinned_voice = hasattr(nat, "voice_acquire")
+            voice = nat.voice_acquire(vid) if pinned_voice else self.voice_cache[vid]
+            jobs = []                                         # every S3Gen job of this request (dropped on cancel)
+            try:
+                self._run_request_pinned(text, voice, jobs, cfg_w, temp, chunk_size, slice_len, trim_tail_ms, trim_lead_ms, overlap, fade_ms,
+                                         request_id, token, emit, t_start)
+            finally:
+                if pinned_voice:
+                    for j in jobs:       # dropped jobs are retired by the batcher's next pass; running ones finish their batch
+                        j.done.wait(5.0)
+                    nat.voice_release(voice)
+
+    def _run_request_pinned(self, text, voice, jobs, cfg_w, temp, chunk_size, slice_len, trim_tail_ms, trim_lead_ms, overlap, fade_ms,
+                            request_id, token: Optional[CancellationToken], emit, t_start):
+        nat, sched = self.native, self.scheduler
+        if True:
             chunks = split_text_into_chunks(text, chunk_size)
             if not chunks:
                 emit(b"")
@@ -610,17 +660,23 @@ class TextToSpeechEngine:
             trail = (trim_tail_ms * self.sr) // 1000
             prev_tail = None
             first_sent = False
-            self._seq += 1
-            base_seed = (self.seed << 20) ^ (zlib.crc32(str(request_id).encode()) & 0xFFFFF) ^ (self._seq << 8)
+            with self._seq_lock:      # concurrent arrivals must not swap or share sequence numbers (they feed the seed)
+                self._seq += 1
+                seq = self._seq
+            base_seed = (self.seed << 20) ^ (zlib.crc32(str(request_id).encode()) & 0xFFFFF) ^ (seq << 8)
+            fade_in = fade_out = None
+            if fade_len > 0 and self._backend is None:
+                from .native import fade_curves
+                fade_in, fade_out = fade_curves(fade_len, torch.device("cuda", self.gpu_id))   # per request, as the reference (:867-871)
 
             def send(cur, n_out, tail):
                 """crossfade (optional) + PCM on device, then D2H and hand the bytes to the event loop."""
                 if n_out <= 0:
                     return
+                kw = dict(fade_in=fade_in, fade_out=fade_out) if fade_in is not None else {}
                 if pinned is not None and n_out <= pinned.shape[0]:
-                    pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0, out=pcm_dev)
-                else:
-                    pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0)
+                    kw["out"] = pcm_dev
+                pcm = nat.crossfade_pcm(cur, n_out, tail, fade_len if tail is not None else 0, **kw)
                 if not first_sent:
                     trace("pcm_enqueued")
                 if self.device_sink:
@@ -645,7 +701,6 @@ class TextToSpeechEngine:
             tr = self.stats.setdefault("trace", collections.deque(maxlen=64))
             trace = (lambda label: tr.append((label, round((time.time() - t_start) * 1e3, 1))))
             trace("start")
-            jobs = []                                         # every S3Gen job of this request (dropped on cancel)
             streams = [None] * len(chunks)
             outq = [queue.Queue() for _ in chunks]           # per chunk: (cur, last) items, then None (or an exception)
             first_slice_ready = threading.Event()            # chunk 0's first slice has been synthesised (or chunk 0 is done)
@@ -666,17 +721,17 @@ class TextToSpeechEngine:
                     max_new = self.sampling.max_new_tokens
                     if self.sampling.tokens_per_word:
                         max_new = max(1, self.sampling.tokens_per_word * len(chunks[ci].split()))
-                    s = streams[ci] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + ci, max_new)
+                    # the permit travels with the stream: the scheduler releases it after the native slot is closed (natural
+                    # end, cancel or error), never earlier
+                    s = streams[ci] = sched.open(voice, ids, cfg_w, temp, self.sampling, base_seed + ci, max_new, on_closed=self.t3_slots.release)
+                    have_slot = False
                     if ci == 0:
                         trace("t3_open")
                     is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
                     consumed, slice_idx, acc, prev_job = 0, 0, [], None
                     while not stop.is_set():
-                        if not self._wait_tokens(s, consumed + slice_len + look_ahead, token):
+                        if not self._wait_tokens(s, consumed + slice_len + look_ahead, token, stop):
                             break
-                        if s.finished and have_slot:          # decoding is over: the slot can serve the next chunk
-                            self.t3_slots.release()
-                            have_slot = False
                         avail = len(s.tokens) - consumed
                         if avail >= slice_len + look_ahead:
                             new, last = s.tokens[consumed: consumed + slice_len], False
@@ -821,6 +876,9 @@ class TextToSpeechEngine:
             raise RuntimeError(f"TTS Engine on GPU {self.gpu_id} is not ready")
         if output_format not in ("raw_pcm", "wav"):
             raise ValueError(f"Unsupported format on the B200 path: {output_format} (containers are muxed by the caller)")
+        if cancellation_token is None:
+            # an abandoned generator (consumer stops iterating) must stop the worker too: internal token, set in `finally`
+            cancellation_token = CancellationToken()
         async with self.tts_semaphore:
             loop = asyncio.get_running_loop()
             q: asyncio.Queue = asyncio.Queue(maxsize=int(os.environ.get("TTS_PCM_CHUNK_QUEUE_MAX_SIZE", "3")))

@@ -41,13 +41,14 @@ SIGNATURES = {
     "cbx_t3_tokens": (_I, [_P, _I, _I, _I, _P, _P]),
     "cbx_t3_logits": (_I, [_P, _I, _P, _P]),
     "cbx_t3_close": (_I, [_P, _I]),
+    "cbx_t3_stats": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "cbx_s3gen_infer": (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P, _P, _U64, _P]),
     "cbx_s3gen_infer_batch": (_I, [_P, C.POINTER(S3GenCall), _I, _P]),
     "cbx_flow_infer": (_I, [_P, _I, _P, _I, _P, _P]),
     "cbx_hift_infer": (_I, [_P, _P, _I, _P, _L, _P, _P, _P, _P, _U64, _P]),
     "cbx_hift_f0": (_I, [_P, _P, _I, _P, _P]),
     "cbx_hift_source": (_I, [_P, _P, _I, _P, _P, _U64, _P, _P]),
-    "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P]),
+    "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P, _P, _P]),
     "cbx_gpu_launches": (_L, [_P]),
     "cbx_gemm_tc_launches": (C.c_longlong, []),
     "cbx_attn_tc_launches": (C.c_longlong, []),

@@ -1,6 +1,7 @@
 """Thin Python object over the C-ABI engine.  torch is used only for device buffers and streams;
 every computation happens inside libcbx_b200.so."""
 import ctypes as C
+import os
 import threading
 
 import numpy as np
@@ -27,14 +28,22 @@ def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+def fade_curves(fade_len: int, device):
+    """(fade_in, fade_out) exactly as the reference builds them per request (src/tts_streaming.py:867-871)."""
+    t = torch.linspace(0, 1, fade_len, device=device)
+    return torch.sin(t * 0.5 * torch.pi), torch.cos(t * 0.5 * torch.pi)
+
+
 class NativeEngine:
     """One engine per GPU (reference: one worker process per device, src/master.py:56-77)."""
 
     def __init__(self, cfg: ModelConfig = None, device: int = 0, max_streams=8, max_seq=1536, max_text=512,
-                 max_s3_tokens=1056, max_prompt_tokens=250, n_voices=8, n_lanes=2):
+                 max_s3_tokens=1056, max_prompt_tokens=250, n_voices=None, n_lanes=2):
         if not torch.cuda.is_available():
             raise RuntimeError("NativeEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.cfg = cfg or ModelConfig()
+        if n_voices is None:
+            n_voices = int(os.environ.get("CBX_VOICE_SLOTS", "32"))
         self.lib = L.load()
         self.device = device
         torch.cuda.set_device(device)
@@ -44,7 +53,9 @@ class NativeEngine:
         h = C.c_void_p()
         L.check(self.lib.cbx_engine_create(C.byref(self.ccfg), device, C.byref(h)))
         self.h = h
-        self._voice_ids = {}
+        self._voices = {}          # key -> {"slot", "refs", "used"}
+        self._retired = []         # records of keys that were re-put / dropped while requests still read the old slot
+        self._tick = 0
         self._voice_lock = threading.Lock()
         self.n_voices = n_voices
         self.max_s3_tokens = max_s3_tokens
@@ -73,17 +84,32 @@ class NativeEngine:
         L.check(self.lib.cbx_finalize(self.h))
 
     # ------------------------------------------------------------------ voices
+    # The reference's voice_cache is an unbounded dict (src/tts_streaming.py:178); the device cache has `n_voices` slots, so
+    # it evicts least-recently-used voices -- but never one that an open request still reads (refcount > 0), and re-putting
+    # a key that is in use goes to a NEW slot (the old one is recycled when its last reader releases it).
+    def _free_slot_locked(self):
+        used = {r["slot"] for r in self._voices.values()} | {r["slot"] for r in self._retired}
+        for i in range(self.n_voices):
+            if i not in used:
+                return i
+        idle = [k for k, r in self._voices.items() if r["refs"] == 0 and k != "default"]
+        if not idle:
+            raise RuntimeError(f"voice cache is full: all {self.n_voices} slots are pinned by requests in flight (raise CBX_VOICE_SLOTS)")
+        victim = min(idle, key=lambda k: self._voices[k]["used"])
+        slot = self._voices.pop(victim)["slot"]
+        L.check(self.lib.cbx_voice_drop(self.h, slot))
+        return slot
+
     def voice_put(self, key, t3_cond: dict, gen: dict) -> int:
         """Caches one voice's conditioning on the device; returns its slot (reference voice_cache, tts_streaming.py:178)."""
         with self._voice_lock:
-            if key in self._voice_ids:
-                slot = self._voice_ids[key]
+            rec = self._voices.get(key)
+            if rec is not None and rec["refs"] == 0:
+                slot = rec["slot"]                       # nobody reads it: rewrite in place
             else:
-                used = set(self._voice_ids.values())
-                free = [i for i in range(self.n_voices) if i not in used]
-                if not free:
-                    raise RuntimeError("voice cache is full")
-                slot = free[0]
+                if rec is not None:                      # in use: the readers keep the old slot until they release it
+                    self._retired.append(self._voices.pop(key))
+                slot = self._free_slot_locked()
             spk = _f32(t3_cond["speaker_emb"]).reshape(-1)
             ct = _i32(torch.as_tensor(t3_cond["cond_prompt_speech_tokens"]).cpu().numpy().reshape(-1))
             emo = float(torch.as_tensor(t3_cond["emotion_adv"]).reshape(-1)[0])
@@ -92,17 +118,47 @@ class NativeEngine:
             xv = _f32(gen["embedding"]).reshape(-1)
             L.check(self.lib.cbx_voice_put(self.h, slot, spk.ctypes.data, ct.ctypes.data, len(ct), emo, pt.ctypes.data, len(pt),
                                            pf.ctypes.data, pf.shape[0], xv.ctypes.data, _stream_ptr()))
-            self._voice_ids[key] = slot
+            self._tick += 1
+            self._voices[key] = {"slot": slot, "refs": 0, "used": self._tick}
             return slot
 
     def voice_slot(self, key):
-        return self._voice_ids.get(key)
+        with self._voice_lock:
+            rec = self._voices.get(key)
+            return None if rec is None else rec["slot"]
+
+    def voice_acquire(self, key) -> int:
+        """Pins the voice for a request (T3 prefills + S3Gen jobs read its device buffers); pair with voice_release(slot)."""
+        with self._voice_lock:
+            rec = self._voices[key]
+            rec["refs"] += 1
+            self._tick += 1
+            rec["used"] = self._tick
+            return rec["slot"]
+
+    def voice_release(self, slot: int):
+        with self._voice_lock:
+            for rec in self._voices.values():
+                if rec["slot"] == slot:
+                    rec["refs"] = max(0, rec["refs"] - 1)
+                    return
+            for rec in self._retired:
+                if rec["slot"] == slot:
+                    rec["refs"] -= 1
+                    if rec["refs"] <= 0:
+                        self._retired.remove(rec)
+                        L.check(self.lib.cbx_voice_drop(self.h, slot))
+                    return
 
     def voice_drop(self, key):
         with self._voice_lock:
-            slot = self._voice_ids.pop(key, None)
-            if slot is not None:
-                L.check(self.lib.cbx_voice_drop(self.h, slot))
+            rec = self._voices.pop(key, None)
+            if rec is None:
+                return
+            if rec["refs"] > 0:
+                self._retired.append(rec)                # still read by a request: recycled on its release
+            else:
+                L.check(self.lib.cbx_voice_drop(self.h, rec["slot"]))
 
     # ------------------------------------------------------------------ T3
     def t3_open(self, voice, text_ids, cfg_weight=0.5, temperature=0.8, rep_penalty=1.2, min_p=0.05, top_p=0.95, seed=0, max_new=1000):
@@ -139,6 +195,12 @@ class NativeEngine:
 
     def t3_close(self, slot):
         L.check(self.lib.cbx_t3_close(self.h, slot))
+
+    def t3_stats(self):
+        """(free KV pages, open stream slots)"""
+        f, o = C.c_int(), C.c_int()
+        L.check(self.lib.cbx_t3_stats(self.h, C.byref(f), C.byref(o)))
+        return f.value, o.value
 
     # ------------------------------------------------------------------ S3Gen
     def s3gen_infer(self, voice, tokens, cache_source=None, seed=0, phase=None, noise=None, return_mel=False):
@@ -220,12 +282,17 @@ class NativeEngine:
                                          C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, C.c_void_p(src.data_ptr()), _stream_ptr()))
         return src
 
-    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0, out=None):
+    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0, out=None, fade_in=None, fade_out=None):
         # `out`: caller-owned int16 device buffer (the engine keeps one per request: an allocation on a request's fresh
         # stream misses the caching allocator's per-stream pools and falls through to cudaMalloc, 4-50 ms with the GPU busy)
+        # fade_in / fade_out: the request's curves (reference src/tts_streaming.py:867-871); built here the same way when absent
         out = torch.empty(n_out, device=cur.device, dtype=torch.int16) if out is None else out[:n_out]
+        if prev_tail is not None and fade_len > 0 and fade_in is None:
+            fade_in, fade_out = fade_curves(fade_len, cur.device)
         L.check(self.lib.cbx_crossfade_pcm(self.h, C.c_void_p(cur.data_ptr()), n_out,
                                            C.c_void_p(prev_tail.data_ptr()) if prev_tail is not None else None, fade_len,
+                                           C.c_void_p(fade_in.data_ptr()) if fade_in is not None else None,
+                                           C.c_void_p(fade_out.data_ptr()) if fade_out is not None else None,
                                            C.c_void_p(out.data_ptr()), _stream_ptr()))
         return out
 

@@ -30,22 +30,20 @@ class Backend:
         self.device = device
         self.lock = threading.Lock()
         self.slots = collections.OrderedDict()      # key -> native voice slot name (LRU order)
+        self.weights_source, self.encoder_sd = "injected", None
         if _factory is not None:
             self.native = _factory(ckpt_dir, device)
         else:
             if "cuda" not in str(device):
                 raise RuntimeError("the B200-native chatterbox shim needs a cuda:N device; there is no CPU fallback")
             from cbx_b200.native import NativeEngine
-            from cbx_b200.weights import random_state_dict
+            from cbx_b200.checkpoint import load_checkpoint
             gpu = int(str(device).split(":")[-1]) if ":" in str(device) else 0
             n = int(os.environ.get("CONCURRENT_REQUESTS_PER_WORKER", "1"))
-            self.native = NativeEngine(self.cfg, device=gpu, max_streams=max(8, n), n_lanes=max(2, min(n, 4)), n_voices=16)
-            st = os.path.join(ckpt_dir or "", "cbx_b200.safetensors")
-            if os.path.exists(st):
-                from safetensors.torch import load_file
-                sd = load_file(st)
-            else:   # BASELINE.json configs: random-init Chatterbox weights
-                sd = random_state_dict(self.cfg, 0)
+            # merged / upstream checkpoint files; a missing checkpoint raises like from_local does, unless
+            # CBX_ALLOW_RANDOM_WEIGHTS=1 (BASELINE.json configs: random-init weights)
+            sd, self.encoder_sd, self.weights_source = load_checkpoint(ckpt_dir or "", self.cfg, 0)
+            self.native = NativeEngine(self.cfg, device=gpu, max_streams=max(8, n), n_lanes=max(2, min(n, 4)))
             self.native.load_state_dict(sd)
         self.max_slots = max(2, getattr(self.native, "n_voices", 16) - 1)
 
@@ -71,6 +69,14 @@ class Backend:
             slot = self.native.voice_put(key, t3 if t3 is not None else self._dummy_t3(), gen if gen is not None else self._dummy_gen())
             self.slots[key] = slot
             return slot
+
+
+    def require_synthetic(self, what: str):
+        """The conditioning encoders are seeded stand-ins: fine on random-init weights, an error on a real
+        checkpoint, where they would silently produce a random voice."""
+        if self.weights_source in ("merged", "upstream"):
+            raise RuntimeError(f"{what}: the conditioning encoders are not built on the B200 path yet (SURVEY 8f.1); "
+                               "with a real checkpoint pass conditioning tensors computed upstream")
 
 
 def new_key(prefix: str) -> str:

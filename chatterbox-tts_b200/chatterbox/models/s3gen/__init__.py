@@ -16,6 +16,7 @@ class _S3Tokenizer:
         self._b = backend
 
     def forward(self, wavs, max_len=None):
+        self._b.require_synthetic("s3gen.tokenizer.forward")
         out, lens = [], []
         for w in wavs:
             w = np.asarray(w, dtype=np.float32).reshape(-1)
@@ -39,6 +40,7 @@ class S3Gen(torch.nn.Module):
     def embed_ref(self, ref_wav, ref_sr, device="auto", ref_fade_out=True):
         """-> ref_dict (opaque to the engine apart from .to() on tensor values, :115-117).  Shapes follow the clip (25 prompt
         tokens / 50 mel frames per second, at most 10 s); contents are seeded until the encoders of SURVEY 8f.1 exist."""
+        self._b.require_synthetic("s3gen.embed_ref")
         w = np.asarray(ref_wav.detach().cpu().numpy() if torch.is_tensor(ref_wav) else ref_wav, dtype=np.float32).reshape(-1)
         fc = self._b.cfg.flow
         n = max(3, min(int(len(w) / float(ref_sr) * 25), 250))

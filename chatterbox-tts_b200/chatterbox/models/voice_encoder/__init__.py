@@ -13,6 +13,8 @@ class VoiceEncoder(torch.nn.Module):
         self._b = backend
 
     def embeds_from_wavs(self, wavs, sample_rate=16000, as_spk=False, **kw):
+        if self._b is not None:
+            self._b.require_synthetic("ve.embeds_from_wavs")
         out = []
         for w in wavs:
             w = np.asarray(w, dtype=np.float32).reshape(-1)

@@ -32,17 +32,16 @@ struct StreamBridge {   // order engine-internal stream `in` after the caller's 
     }
 };
 
-__global__ void crossfade_pcm_kernel(const float* __restrict__ cur, long n, const float* __restrict__ prev, int fade_len, short* out) {
+// fade_in / fade_out: the request's curves built the reference's way (torch.sin / torch.cos of linspace(0, 1, fade_len) * pi/2
+// on the device, src/tts_streaming.py:867-871); the mix rounds like torch's three separate elementwise ops (no FMA
+// contraction), so the int16 output is bit-exact with `(prev * fade_out) + (head * fade_in)` -> clamp -> * 32767 -> int16.
+__global__ void crossfade_pcm_kernel(const float* __restrict__ cur, long n, const float* __restrict__ prev, int fade_len,
+                                     const float* __restrict__ fade_in, const float* __restrict__ fade_out, short* out) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x = cur[i];
-    if (prev && i < fade_len) {
-        // torch.linspace(0, 1, fade_len): t_i = i / (fade_len - 1)
-        float t = fade_len > 1 ? (float)i / (float)(fade_len - 1) : 0.f;
-        float a = t * 0.5f * 3.14159265358979323846f;
-        x = prev[i] * cosf(a) + x * sinf(a);
-    }
-    x = fminf(fmaxf(x, -1.f), 1.f) * 32767.f;
+    if (prev && i < fade_len) x = __fadd_rn(__fmul_rn(prev[i], fade_out[i]), __fmul_rn(x, fade_in[i]));
+    x = __fmul_rn(fminf(fmaxf(x, -1.f), 1.f), 32767.f);
     out[i] = (short)x;   // truncation toward zero, as torch .to(int16)
 }
 
@@ -291,6 +290,17 @@ int cbx_t3_close(cbx_engine* e, int slot) {
     CBX_API_END
 }
 
+int cbx_t3_stats(cbx_engine* e, int* free_pages, int* open_slots) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && free_pages && open_slots, "null argument");
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    *free_pages = (int)e->t3.free_pages.size();
+    int n = 0;
+    for (int u : e->t3.slot_used) n += u ? 1 : 0;
+    *open_slots = n;
+    CBX_API_END
+}
+
 int cbx_flow_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, float* mel_out_d, void* stream) {
     CBX_API_BEGIN
     CBX_REQUIRE(e && e->finalized && tokens_h && mel_out_d, "bad argument");
@@ -463,12 +473,14 @@ int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_call
     CBX_API_END
 }
 
-int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const float* prev_tail_d, int fade_len, int16_t* out_d, void* stream) {
+int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const float* prev_tail_d, int fade_len, const float* fade_in_d,
+                      const float* fade_out_d, int16_t* out_d, void* stream) {
     CBX_API_BEGIN
     CBX_REQUIRE(e && cur_d && out_d && n_out >= 0, "bad argument");
+    CBX_REQUIRE(!prev_tail_d || fade_len == 0 || (fade_in_d && fade_out_d), "crossfade: a previous tail needs both fade curves");
     CBX_CHECK(cudaSetDevice(e->device));
     if (n_out > 0) {
-        crossfade_pcm_kernel<<<cdiv(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cur_d, n_out, prev_tail_d, fade_len, out_d);
+        crossfade_pcm_kernel<<<cdiv(n_out, 256), 256, 0, (cudaStream_t)stream>>>(cur_d, n_out, fade_len > 0 ? prev_tail_d : nullptr, fade_len, fade_in_d, fade_out_d, out_d);
         CBX_CHECK(cudaGetLastError());
         e->gpu_launches += 1;
     }

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CBX_ABI_VERSION 1
+#define CBX_ABI_VERSION 2
 
 typedef struct cbx_engine cbx_engine;
 
@@ -80,6 +80,8 @@ int cbx_t3_tokens(cbx_engine* e, int slot, int from, int count, int32_t* out_h, 
 int cbx_t3_logits(cbx_engine* e, int slot, float* out_h, void* stream);
 /* generator close()/GC: releases the KV pages             -- cancel path, src/tts_streaming.py:505-519 */
 int cbx_t3_close(cbx_engine* e, int slot);
+/* allocator state (tests / health checks): free KV pages and open stream slots */
+int cbx_t3_stats(cbx_engine* e, int* free_pages, int* open_slots);
 
 /* S3Gen.inference(speech_tokens, ref_dict, cache_source) -> (wav, source)
  *                                                        -- src/tts_streaming.py:316-320, :583-590
@@ -110,10 +112,12 @@ int cbx_hift_source(cbx_engine* e, const float* f0_d, int frames, const float* p
                     float* source_out_d, void* stream);
 
 /* equal-power crossfade + clamp + int16 conversion        -- src/tts_streaming.py:710-746 and :149-155
- * out[i] = int16(clamp(x,-1,1) * 32767) with x = prev_tail[i]*cos + cur[i]*sin for i < fade_len (when prev_tail_d),
- * x = cur[i] otherwise, for i in [0, n_out). */
+ * out[i] = int16(clamp(x,-1,1) * 32767) with x = prev_tail[i]*fade_out[i] + cur[i]*fade_in[i] for i < fade_len (when
+ * prev_tail_d), x = cur[i] otherwise, for i in [0, n_out).  fade_in_d / fade_out_d [fade_len]: the request's curves, built
+ * by the caller exactly as the reference builds them (:867-871); products and sum round separately, as torch's do, so the
+ * PCM is bit-exact. */
 int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const float* prev_tail_d, int fade_len,
-                      int16_t* out_d, void* stream);
+                      const float* fade_in_d, const float* fade_out_d, int16_t* out_d, void* stream);
 
 /* counters for bench.py: kernels launched by this library since engine creation */
 int64_t cbx_gpu_launches(cbx_engine* e);

@@ -77,7 +77,7 @@ class FakeNative:
     def s3gen_infer(self, voice, tokens, cache_source=None, seed=0, **kw):
         return FakeModel.s3gen(tokens, cache_source)
 
-    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0):
+    def crossfade_pcm(self, cur, n_out, prev_tail=None, fade_len=0, **kw):
         x = cur[:n_out].clone()
         if prev_tail is not None and fade_len > 0:
             t = torch.linspace(0, 1, fade_len)

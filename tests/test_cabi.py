@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/cbx_b200.h but not exported"
         assert s in L.SIGNATURES, f"{s} has no ctypes signature"
-    assert lib.cbx_abi_version() == 1
+    assert lib.cbx_abi_version() == 2
 
 
 def _manifest(cfg):

@@ -13,7 +13,9 @@ def engine(tiny_cfg):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from cbx_b200.engine import TextToSpeechEngine, SamplingDefaults
-    eng = TextToSpeechEngine("cuda:0", cfg=tiny_cfg, concurrent_requests=4, sampling=SamplingDefaults(tokens_per_word=10), seed=0,
+    from cbx_b200.weights import random_state_dict
+    eng = TextToSpeechEngine("cuda:0", cfg=tiny_cfg, state_dict=random_state_dict(tiny_cfg, 0), concurrent_requests=4,
+                             sampling=SamplingDefaults(tokens_per_word=10), seed=0,
                              native_kwargs=dict(max_s3_tokens=400, n_lanes=4))
     asyncio.run(eng.ainit())
     yield eng

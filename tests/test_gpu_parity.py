@@ -342,16 +342,22 @@ def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev):
 
 
 def test_crossfade_pcm(tiny, dev):
+    """Integer output is bit-exact: the fade curves are passed in as arrays built the reference's way (torch.sin / torch.cos of
+    linspace on the device, src/tts_streaming.py:867-871) and the mix rounds like torch's separate mul / mul / add."""
+    from cbx_b200.native import fade_curves
     eng = tiny[0]
     g = torch.Generator().manual_seed(0)
+    for fade_len, n_cur, n_out in ((720, 5000, 4000), (240, 1000, 760), (1, 50, 50), (720, 1440, 720)):
+        cur = (torch.rand(n_cur, generator=g) * 2.4 - 1.2).to(dev)
+        prev = (torch.rand(fade_len, generator=g) * 2 - 1).to(dev)
+        fi, fo = fade_curves(fade_len, dev)
+        out = eng.crossfade_pcm(cur, n_out, prev, fade_len, fade_in=fi, fade_out=fo)
+        t = torch.linspace(0, 1, fade_len, device=dev)
+        ref = cur[:n_out].clone()
+        ref[:fade_len] = (prev * torch.cos(t * 0.5 * torch.pi)) + (cur[:fade_len] * torch.sin(t * 0.5 * torch.pi))
+        ref = (torch.clamp(ref, -1.0, 1.0) * 32767).to(torch.int16)
+        assert torch.equal(out, ref), f"fade_len {fade_len}: {int((out != ref).sum())} samples differ"
+        assert torch.equal(eng.crossfade_pcm(cur, n_out, prev, fade_len), ref)     # curves built inside the binding
     cur = (torch.rand(5000, generator=g) * 2.4 - 1.2).to(dev)
-    prev = (torch.rand(720, generator=g) * 2 - 1).to(dev)
-    out = eng.crossfade_pcm(cur, 4000, prev, 720)
-    t = torch.linspace(0, 1, 720, device=dev)
-    ref = cur[:4000].clone()
-    ref[:720] = prev * torch.cos(t * 0.5 * torch.pi) + cur[:720] * torch.sin(t * 0.5 * torch.pi)
-    ref = (torch.clamp(ref, -1.0, 1.0) * 32767).to(torch.int16)
-    diff = (out.int() - ref.int()).abs()
-    assert diff.max() <= 1 and (diff > 0).float().mean() < 1e-3   # sin/cos rounding may flip a truncation
     out2 = eng.crossfade_pcm(cur, 5000)
     assert torch.equal(out2, (torch.clamp(cur, -1.0, 1.0) * 32767).to(torch.int16))

@@ -82,61 +82,139 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ oracle legs
-def oracle_sample(threads=None):
-    """Bounded CPU sample of the same workload: first text chunk, T3 prefill + 42 decode steps (first slice +
-    look-ahead), then one S3Gen call on the first 35-token slice (prompt 194 tokens / 388 frames).  fp32, eager."""
+WORKLOAD = ("configs[1]: single stream per GPU, 200-word paragraph streamed in chunks, cfg 0.5, temp 0.8, slice 35, overlap full, "
+            "crossfade 30 ms, 10 speech tokens/word, fixed seed")
+
+
+def host_threads():
+    """All host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)."""
     import torch
-    from oracle import t3 as OT, flow as OF, hift as OH
-    from cbx_b200.config import ModelConfig
-    from cbx_b200.weights import random_state_dict, synthetic_conditionals
-    from cbx_b200.text_processing import split_text_into_chunks, SyntheticTokenizer
-    if threads:
-        torch.set_num_threads(threads)
-    cfg = ModelConfig()
-    if not hasattr(oracle_sample, "sd"):
-        oracle_sample.sd = random_state_dict(cfg, 0)
-        oracle_sample.conds = synthetic_conditionals(cfg)
-    sd, conds = oracle_sample.sd, oracle_sample.conds
-    chunk = split_text_into_chunks(synthetic_text(WORDS), 150)[0]
-    ids = [255] + SyntheticTokenizer().text_to_tokens(chunk)[0].tolist() + [0]
-    text = torch.tensor([ids, ids])
-    g = torch.Generator().manual_seed(1234)
-    t0 = time.time()
-    with torch.no_grad():
-        toks = []
-        for tok in OT.inference_stream(sd, cfg.t3, conds["t3"], text, 42, noise_fn=lambda i: torch.empty(8194).exponential_(generator=g)):
-            toks.append(tok)
-        sl = [t for t in toks[:35] if t < 6561]
-        while len(sl) < 3:
-            sl.append(0)
-        mel = OF.flow_inference(sd, cfg.flow, torch.tensor(sl), conds["gen"])
-        T = mel.shape[-1]
-        wav, _ = OH.hift_inference(sd, cfg.hift, mel, None, torch.zeros(9), torch.randn(9, T * 480, generator=g))
-    dt = time.time() - t0
-    return wav.shape[-1] / 24000.0, dt, torch.get_num_threads()
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def slice_schedule(n_tokens, slice_len=35, look_ahead=7):
+    """Token counts of the slices the reference emits for one text chunk (src/tts_streaming.py:499-501, :535-565)."""
+    out, consumed = [], 0
+    while n_tokens - consumed >= slice_len + look_ahead:
+        out.append(slice_len)
+        consumed += slice_len
+    if n_tokens - consumed > 0:
+        out.append(n_tokens - consumed)
+    return out
+
+
+class OracleChunk:
+    """The reference's CPU path for the FIRST text chunk of the benchmark paragraph, on the oracle port: T3 prefill + decode
+    (CFG rows, sampling), then per 35-token slice one S3Gen call over [prompt | all tokens so far] ("full" overlap: token
+    accumulation, EOS(0) append, <6561 filter, source cache chained; src/tts_streaming.py:655-699) and only the new tail
+    counted as audio.  `n_slices` bounds the sample: the T3 loop stops at the tokens those slices need (35 k + 7 look-ahead)."""
+
+    def __init__(self):
+        import torch
+        from cbx_b200.config import ModelConfig
+        from cbx_b200.weights import random_state_dict, synthetic_conditionals
+        from cbx_b200.text_processing import split_text_into_chunks, SyntheticTokenizer
+        self.cfg = ModelConfig()
+        self.sd = random_state_dict(self.cfg, 0)
+        self.conds = synthetic_conditionals(self.cfg)
+        chunk = split_text_into_chunks(synthetic_text(WORDS), 150)[0]
+        self.words = len(chunk.split())
+        ids = [255] + SyntheticTokenizer().text_to_tokens(chunk)[0].tolist() + [0]
+        self.text = torch.tensor([ids, ids])
+        self.n_tokens = TOK_PER_WORD * self.words
+        self.schedule = slice_schedule(self.n_tokens)
+
+    def run(self, n_slices=None):
+        """-> (audio seconds emitted, seconds, {"t3_s", "s3gen_s": [per slice]})"""
+        import torch
+        from oracle import t3 as OT, flow as OF, hift as OH
+        sched = self.schedule if n_slices is None else self.schedule[:max(1, n_slices)]
+        whole = len(sched) == len(self.schedule)
+        need = self.n_tokens if whole else sum(sched) + 7
+        g = torch.Generator().manual_seed(1234)
+        t0 = time.time()
+        with torch.no_grad():
+            toks = []
+            for tok in OT.inference_stream(self.sd, self.cfg.t3, self.conds["t3"], self.text, need,
+                                           noise_fn=lambda i: torch.empty(8194).exponential_(generator=g)):
+                toks.append(tok)
+            t_t3 = time.time() - t0
+            acc, cache, prev_len, emitted, per = [], None, 0, 0, []
+            for k, n in enumerate(sched):
+                t1 = time.time()
+                acc = acc + toks[sum(sched[:k]): sum(sched[:k]) + n]
+                cur = list(acc) + ([0] if (whole and k == len(sched) - 1) else [])
+                cur = [t for t in cur if t < 6561]
+                while len(cur) < 3:
+                    cur.append(0)
+                mel = OF.flow_inference(self.sd, self.cfg.flow, torch.tensor(cur), self.conds["gen"])
+                T = mel.shape[-1]
+                wav, cache = OH.hift_inference(self.sd, self.cfg.hift, mel, cache, torch.zeros(9), torch.randn(9, T * 480, generator=g))
+                emitted += wav.shape[-1] - prev_len
+                prev_len = wav.shape[-1]
+                per.append(time.time() - t1)
+        return emitted / 24000.0, time.time() - t0, {"t3_s": t_t3, "s3gen_s": per}
+
+    def slices_for_budget(self, probe, seconds):
+        """Largest slice count whose predicted cost fits `seconds`, from a one-slice probe (T3 cost per token; S3Gen cost taken
+        as proportional to the sequence length 388 + 70 k frames)."""
+        t3_tok = probe["t3_s"] / 42.0
+        s1 = probe["s3gen_s"][0] / 458.0
+        best = 1
+        for k in range(1, len(self.schedule) + 1):
+            whole = k == len(self.schedule)
+            ntok = self.n_tokens if whole else sum(self.schedule[:k]) + 7
+            cost = t3_tok * ntok + sum(s1 * (388 + 2 * sum(self.schedule[:j + 1])) for j in range(k))
+            if cost <= seconds:
+                best = k
+        return best
+
+    def describe(self, k, th):
+        sched = self.schedule[:k]
+        return (f"oracle fp32 eager on {th} host threads: first text chunk of the paragraph ({self.words} words, {self.n_tokens} tokens), "
+                f"T3 prefill + {self.n_tokens if k == len(self.schedule) else sum(sched) + 7} decode steps, {k} of its {len(self.schedule)} "
+                f"full-overlap S3Gen slices {sched} (prompt 194 tokens; every slice re-synthesises all accumulated tokens)")
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port; the reference's own model package is not installable),
+    all host cores, same config / metric / unit as the B200 arm; each step is a bounded sample of that workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    for _ in range(args.warmup):
-        oracle_sample()
+    th = host_threads()
+    oc = OracleChunk()
+    _, _, probe = oc.run(1)                                   # untimed warm-up, also the cost probe
+    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "240"))
+    k = oc.slices_for_budget(probe, budget / max(1, args.steps))
+    for _ in range(max(0, args.warmup - 1)):
+        oc.run(1)                                             # warm-up steps need not be full samples: eager CPU has no graphs to capture
     secs, times = 0.0, 0.0
     for _ in range(args.steps):
-        a, dt, th = oracle_sample()
+        a, dt, _ = oc.run(k)
         secs += a
         times += dt
     v = secs / times
     line = {"metric": "audio_sec_per_sec", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": times / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": "configs[1] single stream, 200-word paragraph (bounded sample per step: first chunk, 42 T3 steps + first 35-token S3Gen slice)"},
-            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": th, "kind": "port",
-                             "sample": "oracle fp32 eager: T3 prefill + 42 decode steps, one S3Gen call on 35 tokens (T=458 CFM frames), 1.4 s audio"},
+            "data": "synthetic", "impl": "reference", "config": bench_config(),
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": th, "kind": "port", "sample": oc.describe(k, th),
+                             "audio_s_per_step": secs / args.steps},
             "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def bench_config():
+    """`config` of BOTH arms (the driver compares them): the workload, not how much of it a step samples."""
+    return {"workload": WORKLOAD, "words": WORDS, "tokens_per_word": TOK_PER_WORD, "weights": "random-init seed 0",
+            "voice": "cached conditioning of trump.wav's shapes (194 prompt tokens, 388 mel frames)",
+            "l2": "no flush needed: every T3 step streams 1.02 GB of weights (> 126 MB L2)"}
 
 
 def aggregate_ranks(ms, e2e_ms, audio_s, e2e_audio_s, world, device):
@@ -194,9 +272,13 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cbx_b200.config import ModelConfig
+    from cbx_b200.weights import random_state_dict
     text = synthetic_text(WORDS)
     sampling = SamplingDefaults(tokens_per_word=TOK_PER_WORD)
-    eng = TextToSpeechEngine(f"cuda:{local}", concurrent_requests=int(os.environ.get("BENCH_CONCURRENT", "8")), sampling=sampling, seed=0)
+    # BASELINE.json configs: random-init Chatterbox weights (seed 0), passed explicitly -- the engine refuses to invent weights
+    eng = TextToSpeechEngine(f"cuda:{local}", state_dict=random_state_dict(ModelConfig(), 0), concurrent_requests=int(os.environ.get("BENCH_CONCURRENT", "8")),
+                             sampling=sampling, seed=0)
     lib = L.load()
 
     def barrier():
@@ -224,28 +306,69 @@ def run_b200(args):
             nbytes += len(chunk)
         return nbytes, first
 
-    async def concurrent_leg(n_streams=8, words=100):
-        """BASELINE.json configs[2]: 8 concurrent streams batched on one B200, 100-word prompts, cached voice conditioning."""
-        texts = [synthetic_text(words, seed=1234 + i) for i in range(n_streams)]
-
+    async def run_streams(texts, tag):
+        """All texts as concurrent requests through stream(): -> (audio seconds, wall seconds, first-PCM-chunk ms per request)."""
         async def one(i):
             nb, t0, first = 0, time.time(), None
-            async for chunk in eng.stream(text=texts[i], output_format="raw_pcm", voice_id=None, request_id=f"c{i}", cancellation_token=None, **REQ):
+            async for chunk in eng.stream(text=texts[i], output_format="raw_pcm", voice_id=None, request_id=f"{tag}{i}", cancellation_token=None, **REQ):
                 if first is None and len(chunk):
                     first = (time.time() - t0) * 1e3
                 nb += len(chunk)
             return nb, first
-        await asyncio.gather(*[one(i) for i in range(n_streams)])      # warm-up: captures the S3Gen graphs of every lane
         torch.cuda.synchronize()
         t0 = time.time()
-        res = await asyncio.gather(*[one(i) for i in range(n_streams)])
+        res = await asyncio.gather(*[one(i) for i in range(len(texts))])
         torch.cuda.synchronize()
         dt = time.time() - t0
-        audio = sum(r[0] for r in res) / 2 / 24000.0
-        firsts = sorted(r[1] for r in res if r[1] is not None)
+        return sum(r[0] for r in res) / 2 / 24000.0, dt, [r[1] for r in res if r[1] is not None]
+
+    def pct(xs, q):
+        xs = sorted(xs)
+        return xs[min(len(xs) - 1, int(round(q * (len(xs) - 1))))] if xs else None
+
+    async def concurrent_leg(n_streams=8, words=100, repeats=5):
+        """BASELINE.json configs[2]: 8 concurrent streams batched on one B200, 100-word prompts, cached voice conditioning.
+        One untimed pass, then `repeats` timed passes (all requests arrive together); first-chunk percentiles over all
+        repeats x streams."""
+        texts = [synthetic_text(words, seed=1234 + i) for i in range(n_streams)]
+        await run_streams(texts, "w")
+        vals, firsts = [], []
+        for r in range(repeats):
+            a, dt, f = await run_streams(texts, f"c{r}_")
+            vals.append(a / dt)
+            firsts += f
+        v = statistics.median(vals)
         return {"workload": "configs[2]: 8 concurrent streams on one B200, 100-word prompts, cached voice conditioning", "streams": n_streams,
-                "value": audio / dt, "unit": "audio-s/s", "per_stream_x_realtime": audio / dt / n_streams,
-                "first_chunk_ms_p50": firsts[len(firsts) // 2] if firsts else None, "seconds": dt}
+                "repeats": repeats, "value": v, "unit": "audio-s/s", "values": vals, "spread": (max(vals) - min(vals)) / v, "per_stream_x_realtime": v / n_streams,
+                "first_chunk_ms_p50": pct(firsts, 0.5), "first_chunk_ms_p95": pct(firsts, 0.95), "first_chunk_ms_min": min(firsts) if firsts else None,
+                "target": {"audio_s_per_s": 400.0, "first_chunk_ms_p50": 150.0}}
+
+    async def mixed_leg(per_gpu=8, repeats=2):
+        """BASELINE.json configs[3]: 8 x N concurrent streams of mixed 20-400-word prompts (word counts randint(20, 400), seed
+        1234), dealt round-robin to the ranks as the reference's ZeroMQ PUSH socket deals requests to workers (src/master.py:56-98,
+        SURVEY 8e: not load-aware).  Every rank runs its share concurrently; job time = max over ranks, audio = sum over ranks."""
+        r = random.Random(1234)
+        counts = [r.randint(20, 400) for _ in range(per_gpu * world)]
+        mine = [(i, c) for i, c in enumerate(counts) if i % world == rank]
+        texts = [synthetic_text(c, seed=5000 + i) for i, c in mine]
+        await run_streams(texts[:2], "mw")
+        out = []
+        for k in range(repeats):
+            barrier()
+            a, dt, f = await run_streams(texts, f"m{k}_")
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            tmin = t.clone()
+            au = torch.tensor([a], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+                dist.all_reduce(au, op=dist.ReduceOp.SUM)
+            out.append((float(au[0]) / float(t[0]), float(t[0]), float(tmin[0]), f))
+        best = max(out, key=lambda x: x[0])
+        return {"workload": f"configs[3]: {per_gpu * world} concurrent streams of mixed 20-400-word prompts over {world} GPU(s), round-robin dispatch",
+                "streams": per_gpu * world, "words_total": sum(counts), "value": statistics.median(o[0] for o in out), "unit": "audio-s/s", "values": [o[0] for o in out],
+                "slowest_rank_s": best[1], "fastest_rank_s": best[2], "imbalance": best[1] / max(best[2], 1e-9),
+                "first_chunk_ms_p50_rank0": pct(best[3], 0.5), "first_chunk_ms_p95_rank0": pct(best[3], 0.95)}
 
     async def main():
         await eng.ainit()
@@ -282,6 +405,9 @@ def run_b200(args):
         e2e_audio = e2e_bytes / 2 / 24000.0
         agg = aggregate_ranks(ms, e2e_s * 1e3, audio_s, e2e_audio, world, "cuda")
         ms_max, e2e_ms_max, value, e2e_val = agg["ms_max"], agg["e2e_ms_max"], agg["value"], agg["e2e_value"]
+        mixed = None
+        if not args.no_concurrent and (world > 1 or os.environ.get("BENCH_MIXED", "0") == "1"):
+            mixed = await mixed_leg()
         if rank != 0:
             return
         # instrumented pass for the roofline (rank 0)
@@ -290,7 +416,7 @@ def run_b200(args):
         n = 8
         counts, pms, work = (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
         lib.cbx_profile_end(counts, pms, work, n)
-        names = ["gemm_mma_kernel (CFM/HiFT/encoder/T3-prefill GEMM + implicit conv)", "attn_kernel (CFM/encoder/prefill attention)",
+        names = ["gemm_tc_kernel class (tcgen05 GEMM + implicit conv: CFM / HiFT / encoder / T3 prefill)", "attn_tc_kernel class (tcgen05 flash attention: CFM / encoder / T3 prefill)",
                  "t3_decode_step (GEMV projections + decode attention + sampler of one step, graph replay)", "decode_attn_kernel", "sampler_kernel", "norm_kernel", "elementwise", "hift misc"]
         kern = []
         for i in range(n):
@@ -327,15 +453,16 @@ def run_b200(args):
         roof["t3_step"] = t3_step_leg(eng, pk)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            a, dt, th = oracle_sample()
-            cpu = {"value": a / dt, "unit": "audio-s/s", "cores": th, "kind": "port",
-                   "sample": "oracle fp32 eager on host: T3 prefill + 42 decode steps and one S3Gen call on the first 35-token slice (1.4 s audio); %.1f s" % dt}
+            th = host_threads()
+            oc = OracleChunk()
+            _, _, probe = oc.run(1)
+            k = oc.slices_for_budget(probe, float(os.environ.get("BENCH_CPU_BUDGET_S", "25")))
+            a, dt, _ = oc.run(k)
+            cpu = {"value": a / dt, "unit": "audio-s/s", "cores": th, "kind": "port", "sample": oc.describe(k, th) + "; %.1f s for %.2f s of audio" % (dt, a)}
         firsts = [f for f in firsts if f is not None]
         line = {"metric": "audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "configs[1]: single stream per GPU, 200-word paragraph streamed in chunks, cfg 0.5, temp 0.8, slice 35, overlap full, crossfade 30 ms, 10 speech tokens/word, fixed seed",
-                           "chunk_parallelism": eng.chunk_parallelism,
-                           "audio_s_per_step": audio_s / args.steps, "weights": "random-init seed 0", "l2": "no flush needed: every T3 step streams 1.02 GB of weights (> 126 MB L2)"},
+                "config": bench_config(), "engine": {"chunk_parallelism": eng.chunk_parallelism, "audio_s_per_step": audio_s / args.steps / world},
                 "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(4 * (WORDS * 6 + WORDS * TOK_PER_WORD * 4)), "d2h_bytes_per_step": int(e2e_bytes / args.steps + 4 * WORDS * TOK_PER_WORD),
                         "first_chunk_ms_p50": statistics.median(firsts) if firsts else None, "rtf": (e2e_ms_max / 1e3) / max(e2e_audio, 1e-9)},
@@ -344,6 +471,8 @@ def run_b200(args):
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_concurrent:
             line["concurrent8"] = await concurrent_leg()
+        if mixed is not None:
+            line["mixed_streams"] = mixed
         line["s3gen_batch_sizes"] = {str(k): int(v) for k, v in sorted(eng.s3gen.batches.items())}
         line["s3gen_padding"] = {"tokens_requested": int(eng.s3gen.pad_stats[0]), "tokens_after_padding": int(eng.s3gen.pad_stats[1])}
         print(json.dumps(line), flush=True)
@@ -364,6 +493,6 @@ if __name__ == "__main__":
     ap.add_argument("--no-concurrent", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
-        run_reference(a)
+        run_reference(a)      # rank 0 only; the other ranks return at once
     else:
         run_b200(a)

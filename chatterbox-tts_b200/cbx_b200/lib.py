@@ -58,6 +58,10 @@ SIGNATURES = {
     "cbx_profile_begin": (_I, []),
     "cbx_profile_end": (_I, [_P, _P, _P, _I]),
     "cbx_op_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "cbx_op_gemm_ex": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "cbx_op_cfm_tail": (_I, [_I, _I] + [_P] * 15),
+    "cbx_cfm_tail_launches": (C.c_longlong, []),
+    "cbx_cfm_tail_trace": (_I, [_P]),
     "cbx_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
 }
 

@@ -3,15 +3,17 @@
 // the legacy tensor path (~140 TFLOP/s); this one puts both products on the 5th-generation tensor cores:
 //
 //   CTA = 128 queries of one (batch, head); per 128-key block j
-//     S_j  = Q K_j^T   tcgen05.mma M128 N128 K64 (Q, K: K-major SWIZZLE_128B tiles loaded by TMA)  -> TMEM S[j&1] (double-buffered)
+//     S_j  = Q K_j^T   tcgen05.mma M128 N128 K64 (Q, K: K-major SWIZZLE_128B tiles loaded by TMA)  -> TMEM S
 //     softmax          8 warps, two threads per query row (64 score columns / 32 output columns each): tcgen05.ld S twice
 //                      (max pass, exp pass), online rescale of the register-resident O row, P (bf16) written to shared
 //                      memory in the K-major SWIZZLE_128B layout
 //     PV_j = P_j V_j   tcgen05.mma M128 N64 K128 (V tile as loaded by TMA = MN-major B operand)    -> TMEM PV
 //     O += PV_j        read back by the softmax threads during block j+1
 //
-// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = softmax.  S_{j+1} is issued before the softmax of block j
-// starts (two S buffers, two K / V stages), so the tensor core, TMA and the softmax warps overlap inside one CTA.
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = softmax.  The per-block chain S -> softmax -> PV -> O is serial
+// inside a CTA, so TWO CTAs share an SM (256 TMEM columns and ~100 KB of shared memory each: one S buffer, two K stages,
+// one V stage): while one CTA's softmax warps wait for the tensor core, the other CTA's run.  Round 1 ran one CTA per SM
+// (512 TMEM columns, double-buffered S) at 2.6 us per 128 x 128 score block against ~0.9 us of softmax issue time.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
@@ -20,8 +22,8 @@ namespace {
 
 constexpr int D = 64, BQ = 128, BK = 128, THREADS = 320;
 constexpr int TILE = 128 * 128;                 // bytes of a [128 rows x 64 bf16] SWIZZLE_128B tile
-constexpr int SMEM = 7 * TILE + 1024 + 2048 + 256;   // Q, 2 K, 2 V, P (two 64-key halves), alignment slack, row exchange, barriers
-constexpr int TMEM_COLS = 512, S_COL = 0, PV_COL = 256;
+constexpr int SMEM = 6 * TILE + 1024 + 2048 + 256;   // Q, 2 K, V, P (two 64-key halves), alignment slack, row exchange, barriers
+constexpr int TMEM_COLS = 256, S_COL = 0, PV_COL = 128;
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -71,13 +73,13 @@ struct AttnTcArgs {
     int kv_len[16]; int kv_div;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                              const __grid_constant__ CUtensorMap tmV, const AttnTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sQ = base, sK = base + TILE, sV = base + 3 * TILE, sP = base + 5 * TILE, xch = base + 7 * TILE, bars = xch + 2048;
-    const uint32_t q_full = bars, k_full = bars + 8, k_empty = bars + 24, v_full = bars + 40, v_empty = bars + 56, s_full = bars + 72,
-                   p_ready = bars + 88, pv_done = bars + 96, tmem_slot = bars + 104;   // k/v/s barriers come in pairs (stage 0, 1)
+    const uint32_t sQ = base, sK = base + TILE, sV = base + 3 * TILE, sP = base + 4 * TILE, xch = base + 6 * TILE, bars = xch + 2048;
+    const uint32_t q_full = bars, k_full = bars + 8, k_empty = bars + 24, v_full = bars + 40, v_empty = bars + 48, s_full = bars + 56,
+                   p_ready = bars + 64, pv_done = bars + 72, tmem_slot = bars + 80;   // the K barriers come in pairs (stage 0, 1)
     float* xchf = reinterpret_cast<float*>(smem_raw + (xch - smem_u32(smem_raw)));     // [2 parities][2 halves][128 rows] row max / row sum exchange
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_consta
 
     if (warp == 0 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1); mbar_init(s_full + 8 * s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); }
+        mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(s_full, 1);
         mbar_init(p_ready, 256); mbar_init(pv_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_consta
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {   // TMA producer: two K / V stages
+        if (lane == 0) {   // TMA producer: two K stages (S_{j+1} follows PV_j at once), one V stage
             mbar_expect_tx(q_full, TILE);
             tma_load_3d(sQ, &tmQ, q_full, h * D, q0, b);
             for (int j = 0; j < nkv; j++) {
@@ -114,9 +117,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_consta
                 mbar_wait(k_empty + 8 * s, ph ^ 1);
                 mbar_expect_tx(k_full + 8 * s, TILE);
                 tma_load_3d(sK + s * TILE, &tmK, k_full + 8 * s, h * D, j * BK, b);
-                mbar_wait(v_empty + 8 * s, ph ^ 1);
-                mbar_expect_tx(v_full + 8 * s, TILE);
-                tma_load_3d(sV + s * TILE, &tmV, v_full + 8 * s, h * D, j * BK, b);
+                mbar_wait(v_empty, (j & 1) ^ 1);
+                mbar_expect_tx(v_full, TILE);
+                tma_load_3d(sV, &tmV, v_full, h * D, j * BK, b);
             }
         }
     } else if (warp == 1) {
@@ -125,30 +128,30 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_consta
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BK >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
             const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
             const uint64_t qd = umma_desc(sQ), pd = umma_desc(sP);
-            auto issue_s = [&](int j) {   // S_j = Q K_j^T into S buffer j & 1
+            auto issue_s = [&](int j) {   // S_j = Q K_j^T (one S buffer: the softmax of block j-1 has finished reading it)
                 const int s = j & 1;
                 mbar_wait(k_full + 8 * s, (j >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t kd = umma_desc(sK + s * TILE);
 #pragma unroll
-                for (int k = 0; k < D / 16; k++) umma_bf16(tmem_base + S_COL + s * BK, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);   // +32 B per K=16
-                umma_commit(s_full + 8 * s);
+                for (int k = 0; k < D / 16; k++) umma_bf16(tmem_base + S_COL, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);   // +32 B per K=16
+                umma_commit(s_full);
                 umma_commit(k_empty + 8 * s);
             };
             mbar_wait(q_full, 0);
             issue_s(0);
             for (int j = 0; j < nkv; j++) {
-                // the softmax of block j-1 has released S buffer (j+1)&1 (p_ready(j-1) was awaited below): run ahead
-                if (j + 1 < nkv) issue_s(j + 1);
                 mbar_wait(p_ready, j & 1);      // P_j is in shared memory and S_j has been read out of TMEM
-                mbar_wait(v_full + 8 * (j & 1), (j >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t vd = umma_desc(sV + (j & 1) * TILE);
+                if (j + 1 < nkv) issue_s(j + 1);   // first: the next block's softmax starts with its scores
+                mbar_wait(v_full, j & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t vd = umma_desc(sV);
 #pragma unroll
                 for (int k = 0; k < BK / 16; k++)   // A: P half k/4, +32 B per 16 keys; B: V rows 16k.. = +2048 B
                     umma_bf16(tmem_base + PV_COL, pd + (uint64_t)((k >> 2) * (TILE >> 4) + 2 * (k & 3)), vd + (uint64_t)(k * (2048 >> 4)), idesc_pv, k != 0);
                 umma_commit(pv_done);
-                umma_commit(v_empty + 8 * (j & 1));
+                umma_commit(v_empty);
             }
         }
     } else {               // softmax warps 2..9: TMEM lane quarter = warp % 4; score-column / output-column half = (warp - 2) / 4
@@ -160,9 +163,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_kernel(const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; i++) o[i] = 0.f;
         for (int j = 0; j < nkv; j++) {
-            mbar_wait(s_full + 8 * (j & 1), (j >> 1) & 1);
+            mbar_wait(s_full, j & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t scol = trow + S_COL + (j & 1) * BK + half * 64;
+            const uint32_t scol = trow + S_COL + half * 64;
             const int kbase = j * BK + half * 64;
             const bool tail = kbase + 64 > Tk;
             float mx = -INFINITY;

@@ -502,6 +502,31 @@ int cbx_op_gemm(const void* a, const void* w, const float* bias, float* out, int
     CBX_API_END
 }
 
+int cbx_op_gemm_ex(const void* a, const void* w, const float* bias, const float* res, float* out_f, void* out_b, int M, int N, int K, int act, void* stream) {
+    CBX_API_BEGIN
+    ops_init_once();
+    CBX_REQUIRE(out_f || out_b, "gemm_ex: no output");
+    GemmParams g; g.A = (const bf16*)a; g.lda = K; g.kc = K; g.W = (const bf16*)w; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias;
+    g.act = act; g.res = res; g.ldr = N; g.outF = out_f; g.outB = (bf16*)out_b; g.ldc = N;
+    launch_gemm(g, (cudaStream_t)stream);
+    CBX_API_END
+}
+
+int cbx_op_cfm_tail(int mode, int M, const void* attn_o, float* h, const void* wout, const float* b_out, const float* ln3_g, const float* ln3_b,
+                    const void* w0, const float* b0, const void* w2, const float* b2, const float* ln1_g, const float* ln1_b, const void* wqkv,
+                    void* qkv_out, void* stream) {
+    CBX_API_BEGIN
+    ops_init_once();
+    CBX_REQUIRE(cfm_tail_available(), "cfm_tail kernel is not available on this device");
+    CfmTailWeights blk, nxt;
+    cfm_tail_weights(blk, (const bf16*)wout, (const bf16*)w0, (const bf16*)w2, nullptr);
+    cfm_tail_weights(nxt, nullptr, nullptr, nullptr, (const bf16*)wqkv);
+    CfmTailArgs a; a.M = M; a.mode = mode; a.h = h; a.b_out = b_out; a.ln3_g = ln3_g; a.ln3_b = ln3_b; a.b0 = b0; a.b2 = b2; a.ln1_g = ln1_g; a.ln1_b = ln1_b;
+    a.qkv = (bf16*)qkv_out;
+    launch_cfm_tail(a, (const bf16*)attn_o, &blk, &nxt, (cudaStream_t)stream);
+    CBX_API_END
+}
+
 int cbx_op_attention(const void* qkv, void* out, int T, int H, int batch, int causal, void* stream) {
     CBX_API_BEGIN
     ops_init_once();

@@ -10,6 +10,7 @@
 #include "kernels.cuh"
 #include "t3_kernels.cuh"
 #include "hift_kernels.cuh"
+#include "cfm_tail.cuh"
 #include "../../include/cbx_b200.h"
 
 enum DType { DT_F32 = 0, DT_BF16 = 1 };
@@ -52,7 +53,7 @@ struct T3Model {
 
 struct ConformerLayer { LNp nm, nf; Lin qkv4, pos, out, w1, w2; };
 struct ResnetP { Lin c1, c2, res; LNp n1, n2; int cin; };
-struct TfmP { LNp n1, n3; Lin qkv, out, ff0, ff2; };
+struct TfmP { LNp n1, n3; Lin qkv, out, ff0, ff2; CfmTailWeights tw; };
 struct FlowModel {
     float* tok_emb; Lin spk_aff_dummy; float *spk_w, *spk_b; Lin enc_proj;
     Lin embed, up_embed; LNp embed_ln, up_embed_ln, after_norm; Lin pl1, pl2, upconv;

@@ -103,6 +103,8 @@ void flow_finalize(cbx_engine* e, cudaStream_t st) {
         g = mk(f.tmlp[r], h2, C_TDIM, n, C_TDIM, 0); g.outF = f.tproj + (long)r * n * C_CH; g.ldc = C_CH; launch_gemm(g, st);
     }
     CBX_CHECK(cudaStreamSynchronize(st));
+    if (cfm_tail_available())
+        for (auto& t : f.tfms) cfm_tail_weights(t.tw, t.out.w, t.ff0.w, t.ff2.w, t.qkv.w);     // TMA descriptors of the static weights
 }
 
 static constexpr int CH = 2;   // causal halo rows (k=3)
@@ -268,9 +270,38 @@ static void tfm_block(cbx_engine* e, Lane& L, const TfmP& t, int T, bool pre_nor
     e->gpu_launches += 5;
 }
 
+// Rows from which the fused block tail (cfm_tail.cu: one kernel for out-proj + LN + GELU-FF + next LN + QKV per 128-row tile)
+// replaces the six separate launches.  A tile is a ~40 us serial chain on ONE SM, so a single call (M ~ 900 rows = 8 tiles)
+// is faster through the wide separate GEMMs; batches fill the SMs with tiles.
+static int fused_tail_min_rows() {
+    static const int v = [] { const char* e = getenv("CBX_CFM_TAIL_MIN_ROWS"); return e ? atoi(e) : 4096; }();
+    return v;
+}
+
 // the transformer blocks [j0, j0 + nb) of one estimator stage
 static void tfm_stage(cbx_engine* e, Lane& L, int j0, int nb, int T, cudaStream_t st) {
     FlowModel& f = e->flow;
+    const int M = 2 * L.nb * T;
+    if (cfm_tail_available() && !fuse_ln() && M >= fused_tail_min_rows()) {
+        // stage opener: LayerNorm1 + QKV of the first block; then per block: attention, fused tail (+ next block's LN1 / QKV)
+        CfmTailArgs a; a.M = M; a.h = L.c_h; a.qkv = L.c_qkv;
+        a.mode = CFM_TAIL_QKV; a.ln1_g = f.tfms[j0].n1.g; a.ln1_b = f.tfms[j0].n1.b;
+        launch_cfm_tail(a, nullptr, nullptr, &f.tfms[j0].tw, st);
+        for (int j = 0; j < nb; j++) {
+            const TfmP& t = f.tfms[j0 + j];
+            AttnParams at; at.q = L.c_qkv; at.k = L.c_qkv + C_INNER; at.v = L.c_qkv + 2 * C_INNER; at.ldq = at.ldk = at.ldv = 3 * C_INNER;
+            at.q_bs = at.k_bs = at.v_bs = (long)T * 3 * C_INNER; at.o = L.c_o; at.ldo = C_INNER; at.o_bs = (long)T * C_INNER; at.T = T; at.H = 8; at.batch = 2 * L.nb; at.scale = 0.125f;
+            set_kv_len(at, L, 2, 2);
+            launch_attention(at, st);
+            const bool more = j + 1 < nb;
+            CfmTailArgs b; b.M = M; b.h = L.c_h; b.qkv = L.c_qkv; b.mode = CFM_TAIL_OUT | CFM_TAIL_FF | (more ? CFM_TAIL_QKV : 0);
+            b.b_out = t.out.b; b.ln3_g = t.n3.g; b.ln3_b = t.n3.b; b.b0 = t.ff0.b; b.b2 = t.ff2.b;
+            if (more) { b.ln1_g = f.tfms[j0 + j + 1].n1.g; b.ln1_b = f.tfms[j0 + j + 1].n1.b; }
+            launch_cfm_tail(b, L.c_o, &t.tw, more ? &f.tfms[j0 + j + 1].tw : nullptr, st);
+        }
+        e->gpu_launches += 1 + 2 * nb;
+        return;
+    }
     for (int j = 0; j < nb; j++)
         tfm_block(e, L, f.tfms[j0 + j], T, fuse_ln() && j > 0, (fuse_ln() && j + 1 < nb) ? &f.tfms[j0 + j + 1].n1 : nullptr, st);
 }

@@ -174,8 +174,10 @@ void init_cfg() {
 
 }  // namespace
 
+void cfm_tail_init();
 void gemm_init() {
     gemm_tc_init();
+    cfm_tail_init();
     init_cfg<128, 128, 4, 4>();
     init_cfg<64, 64, 2, 4>();
 }

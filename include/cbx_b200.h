@@ -144,6 +144,20 @@ int cbx_profile_end(int64_t* counts, double* ms, double* work, int n_classes);
 /* single-op hooks (kernel unit tests): C[M][N] = A[M][K] * W[N][K]^T (+bias), bf16 in, fp32 out; attention over
  * fused q|k|v rows; all pointers device. */
 int cbx_op_gemm(const void* a_bf16_d, const void* w_bf16_d, const float* bias_d, float* out_d, int M, int N, int K, void* stream);
+/* the same with the fused epilogue the model uses: act (0 none, 1 GELU, 2 SiLU, 3 Mish, 4 LeakyReLU, 5 ELU), optional fp32
+ * residual [M][N] added after the activation, fp32 and / or bf16 output */
+int cbx_op_gemm_ex(const void* a_bf16_d, const void* w_bf16_d, const float* bias_d, const float* res_d, float* out_f32_d,
+                   void* out_bf16_d, int M, int N, int K, int act, void* stream);
+/* fused tail of a CFM transformer block (kernel unit tests): mode bit 1 = out projection + residual (attn_o [M][512] bf16,
+ * wout [256][512]), bit 2 = LayerNorm3 + GELU feed-forward + residual (w0 [1024][256], w2 [256][1024]), bit 4 = LayerNorm1 +
+ * QKV projection of the next block (wqkv [1536][256]) -> qkv_out [M][1536] bf16; h [M][256] fp32 is updated in place */
+int cbx_op_cfm_tail(int mode, int M, const void* attn_o_bf16_d, float* h_d, const void* wout_d, const float* b_out_d, const float* ln3_g_d,
+                    const float* ln3_b_d, const void* w0_d, const float* b0_d, const void* w2_d, const float* b2_d, const float* ln1_g_d,
+                    const float* ln1_b_d, const void* wqkv_d, void* qkv_out_bf16_d, void* stream);
+/* launches served by the fused CFM block-tail kernel (process-wide) */
+long long cbx_cfm_tail_launches(void);
+/* debug: %globaltimer stamps (ns) of CTA 0 of the last fused-tail launch (9 phase boundaries, see cfm_tail.cu) */
+int cbx_cfm_tail_trace(unsigned long long* out_h);
 int cbx_op_attention(const void* qkv_bf16_d, void* out_bf16_d, int T, int H, int batch, int causal, void* stream);
 
 #ifdef __cplusplus

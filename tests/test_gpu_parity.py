@@ -82,6 +82,43 @@ def test_attention_op(dev, T, H, B, causal):
         assert lib.cbx_attn_tc_launches() == before + 1
 
 
+@pytest.mark.parametrize("M,mode", [(128, 7), (300, 7), (1000, 3), (1000, 4), (5000, 7), (77, 1), (2049, 6)])
+def test_cfm_tail_op(dev, M, mode):
+    """Fused tail of a CFM transformer block (cfm_tail.cu) against plain fp32 torch with bf16 rounding at the same hand-over
+    points (LayerNorm outputs and GELU activations are bf16 GEMM operands, the residual stream stays fp32)."""
+    import torch.nn.functional as F
+    from cbx_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(M + mode)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    bf = lambda t: t.to(torch.bfloat16)
+    o = bf(rnd(M, 512)).to(dev)
+    h = rnd(M, 256).to(dev)
+    wout, w0, w2, wqkv = (bf(rnd(256, 512, sc=0.03)).to(dev), bf(rnd(1024, 256, sc=0.06)).to(dev), bf(rnd(256, 1024, sc=0.02)).to(dev),
+                          bf(rnd(1536, 256, sc=0.06)).to(dev))
+    b_out, b0, b2 = rnd(256, sc=0.1).to(dev), rnd(1024, sc=0.1).to(dev), rnd(256, sc=0.1).to(dev)
+    g3, b3, g1, b1 = (1 + rnd(256, sc=0.1)).to(dev), rnd(256, sc=0.1).to(dev), (1 + rnd(256, sc=0.1)).to(dev), rnd(256, sc=0.1).to(dev)
+    ref_h = h.clone()
+    if mode & 1:
+        ref_h = ref_h + o.float() @ wout.float().t() + b_out
+    if mode & 2:
+        x3 = bf(F.layer_norm(ref_h, (256,), g3, b3)).float()
+        ff = bf(F.gelu(x3 @ w0.float().t() + b0)).float()
+        ref_h = ref_h + ff @ w2.float().t() + b2
+    ref_qkv = bf(F.layer_norm(ref_h, (256,), g1, b1)).float() @ wqkv.float().t() if mode & 4 else None
+    qkv = torch.zeros(M, 1536, device=dev, dtype=torch.bfloat16)
+    hh = h.clone()
+    before = lib.cbx_cfm_tail_launches()
+    L.check(lib.cbx_op_cfm_tail(mode, M, o.data_ptr(), hh.data_ptr(), wout.data_ptr(), b_out.data_ptr(), g3.data_ptr(), b3.data_ptr(), w0.data_ptr(),
+                                b0.data_ptr(), w2.data_ptr(), b2.data_ptr(), g1.data_ptr(), b1.data_ptr(), wqkv.data_ptr(), qkv.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert lib.cbx_cfm_tail_launches() == before + 1
+    assert torch.isfinite(hh).all()
+    assert _rel(hh, ref_h) < 2e-3, f"h: {_rel(hh, ref_h)}"
+    if mode & 4:
+        assert _rel(qkv.float(), ref_qkv) < 6e-3, f"qkv: {_rel(qkv.float(), ref_qkv)}"
+
+
 def _text(L, seed=3):
     g = torch.Generator().manual_seed(seed)
     t = torch.randint(1, 700, (1, L), generator=g)

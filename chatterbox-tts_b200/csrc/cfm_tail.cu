@@ -4,17 +4,21 @@
 // round trips through HBM / L2 between the five GEMMs and two LayerNorms):
 //
 //   OUT : h   = h + attn_o . Wout^T + b_out                      (M128 N256 K512, accumulator ACC0)
-//   FF  : x3  = LayerNorm3(h)                      -> bf16 tile X in shared memory (K-major SWIZZLE_128B)
-//         for 16 chunks of 64 hidden units:  S_j = X . W0_j^T    (M128 N64 K256, two S buffers in TMEM)
-//                                            G_j = GELU(S_j + b0) -> bf16, shared memory
-//                                            Y  += G_j . W2_j^T  (M128 N256 K64, ACC0)
+//   FF  : x3  = LayerNorm3(h)                      -> bf16 A operand X in TENSOR MEMORY (two values per column along K)
+//         for 16 chunks of 64 hidden units:  S_j = X . W0_j^T    (M128 N64 K256, A from TMEM, two S buffers)
+//                                            G_j = GELU(S_j + b0) -> bf16, written over S_j in TMEM
+//                                            Y  += G_j . W2_j^T  (M128 N256 K64, A from TMEM, ACC)
 //         h   = h + Y + b2
-//   QKV : xn  = LayerNorm1_next(h)                 -> X
-//         qkv = xn . Wqkv_next^T                   (6 chunks of M128 N256 K256, ACC1 / ACC0 alternating) -> bf16
+//   QKV : xn  = LayerNorm1_next(h)                 -> X (TMEM)
+//         qkv = xn . Wqkv_next^T                   (12 chunks of M128 N128 K256, A from TMEM, two accumulators) -> bf16
 //
-// warp 0 = TMA producer (4 x 32 KB ring), warp 1 = tcgen05.mma issuer, warps 2..9 = 256 element-wise threads (thread = one
-// row x one column half; TMEM lane quarter = warp % 4).  S_{j+1} is issued before GELU(S_j) starts and Y += G_{j-1} W2 runs
-// meanwhile, so the tensor core, the TMA ring and the GELU warps overlap inside the CTA; the QKV accumulators ping-pong.
+// warp 0 = TMA producer (5 x 32 KB weight ring), warp 1 = tcgen05.mma issuer, warps 2..9 = 256 element-wise threads (thread =
+// one row x one column half; TMEM lane quarter = warp % 4).  The activations never touch shared memory: with both operands in
+// shared memory the loop was bound by shared-memory bandwidth (the tensor core re-reads the 4 KB A slice for every K = 16 step;
+// measured 1.1 us per 64-unit chunk against 0.54 us of tensor time), so X and G live in TMEM and only the weights stream
+// through the ring.  S_{j+1} is issued before GELU(S_j) starts and Y += G_{j-1} W2 runs meanwhile; the QKV accumulators
+// ping-pong.  Residual rows and QKV tiles move through per-warp TMA pipelines ([32 x 32] fp32 / [32 x 64] bf16 atoms, two
+// staging slots per warp): thread-per-row global accesses cost 32 L1 wavefronts per instruction.
 // `mode` selects the phases: QKV alone opens a stage (LayerNorm1 + QKV of its first block), OUT|FF|QKV follows every
 // attention but the stage's last, OUT|FF closes it.
 #include <cuda.h>
@@ -26,10 +30,12 @@ namespace {
 
 constexpr int TM = 128, C = 256, CI = 512, CF = 1024, NQKV = 1536;
 constexpr int ATOM = 16384;                    // [128 rows x 64 bf16] SWIZZLE_128B tile
-constexpr int STAGE = 32768, NST = 4;
-constexpr int X_OFF = 0, RING_OFF = 4 * ATOM, G_OFF = RING_OFF + NST * STAGE, BAR_OFF = G_OFF + 2 * ATOM;
+constexpr int STAGE = 32768, NST = 5;
+constexpr int RING_OFF = 0, IO_OFF = NST * STAGE, BAR_OFF = IO_OFF + 8 * 8192;      // weight ring, 8 warps x 2 x 4 KB I/O staging, barriers
 constexpr int SMEM = BAR_OFF + 512 + 1024;     // + barriers / TMEM slot, + alignment slack
-constexpr int ACC0 = 0, ACC1 = 256, TMEM_COLS = 512;
+// tensor memory: ACC = out-proj / FF accumulator, row cache of the LayerNorms, QKV accumulators (2 x 128); SB = two score buffers
+// (GELU output overwrites them in place); XT = LayerNorm output as the bf16 A operand (256 values = 128 columns per row)
+constexpr int ACC = 0, SB = 256, XT = 384, TMEM_COLS = 512;
 constexpr int THREADS = 320;
 
 __device__ unsigned long long g_tail_trace[16];
@@ -151,15 +157,21 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return 0.5f * x * (1.f + copysignf(e, x));
 }
 
+// A operand from tensor memory (rows = lanes, two bf16 per 32-bit column along K), B from shared memory
+__device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(tmem_c), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmWout,
                                                               const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW2,
                                                               const __grid_constant__ CUtensorMap tmWqkv, const __grid_constant__ CUtensorMap tmH,
                                                               const __grid_constant__ CUtensorMap tmQ, const CfmTailArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sX = base + X_OFF, sR = base + RING_OFF, sG = base + G_OFF, bars = base + BAR_OFF;
-    const uint32_t full0 = bars, empty0 = bars + 32, y_full = bars + 64, x_ready = bars + 72, s_full0 = bars + 80, g_ready0 = bars + 96,
-                   g_free0 = bars + 112, q_full0 = bars + 128, q_empty0 = bars + 144, tmem_slot = bars + 160, hbar0 = bars + 168;
+    const uint32_t sR = base + RING_OFF, sIO = base + IO_OFF, bars = base + BAR_OFF;
+    const uint32_t full0 = bars, empty0 = bars + 8 * NST, y_full = bars + 96, x_ready = bars + 104, s_full0 = bars + 112, g_ready0 = bars + 128,
+                   q_full0 = bars + 144, q_empty0 = bars + 160, tmem_slot = bars + 176, hbar0 = bars + 192;     // hbar: [8 warps][2 slots]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TM;
     const bool do_out = p.mode & CFM_TAIL_OUT, do_ff = p.mode & CFM_TAIL_FF, do_qkv = p.mode & CFM_TAIL_QKV;
@@ -168,10 +180,10 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
         for (int s = 0; s < NST; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(y_full, 1); mbar_init(x_ready, 256);
         for (int s = 0; s < 2; s++) {
-            mbar_init(s_full0 + 8 * s, 1); mbar_init(g_ready0 + 8 * s, 256); mbar_init(g_free0 + 8 * s, 1);
+            mbar_init(s_full0 + 8 * s, 1); mbar_init(g_ready0 + 8 * s, 256);
             mbar_init(q_full0 + 8 * s, 1); mbar_init(q_empty0 + 8 * s, 256);
         }
-        for (int s = 0; s < 4; s++) mbar_init(hbar0 + 8 * s, 1);
+        for (int s = 0; s < 16; s++) mbar_init(hbar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {   // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {   // ------------------------------------------------------------------ TMA producer (weights + attn_o)
             int g = 0;
             auto acquire = [&](uint32_t bytes) -> uint32_t {     // next ring stage, armed for `bytes`
                 const int s = g % NST;
@@ -222,10 +234,11 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
                 }
             }
             if (do_qkv) {
-                for (int c = 0; c < NQKV / 256; c++)
-                    for (int kb = 0; kb < 4; kb++) {
+                for (int c = 0; c < NQKV / 128; c++)
+                    for (int kp = 0; kp < 2; kp++) {      // two k-blocks of [128 rows x 64] per stage
                         const uint32_t s = acquire(STAGE);
-                        tma_load_2d(sR + s * STAGE, &tmWqkv, full0 + 8 * s, kb * 64, c * 256);
+                        tma_load_2d(sR + s * STAGE, &tmWqkv, full0 + 8 * s, (2 * kp) * 64, c * 128);
+                        tma_load_2d(sR + s * STAGE + ATOM, &tmWqkv, full0 + 8 * s, (2 * kp + 1) * 64, c * 128);
                         g++;
                     }
             }
@@ -233,8 +246,8 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
     } else if (warp == 1) {
         if (lane == 0) {   // ------------------------------------------------------------------ MMA issuer
             constexpr uint32_t ID = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);   // D f32, A = B = bf16, K-major, M = 128
-            constexpr uint32_t ID256 = ID | ((uint32_t)(256 >> 3) << 17), ID64 = ID | ((uint32_t)(64 >> 3) << 17);
-            int g = 0, xr = 0, yf = 0;
+            constexpr uint32_t ID256 = ID | ((uint32_t)(256 >> 3) << 17), ID128 = ID | ((uint32_t)(128 >> 3) << 17), ID64 = ID | ((uint32_t)(64 >> 3) << 17);
+            int g = 0, xr = 0;
             auto stage_wait = [&]() -> uint32_t {
                 const int s = g % NST;
                 mbar_wait(full0 + 8 * s, (g / NST) & 1);
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
                 return sR + s * STAGE;
             };
             auto stage_free = [&]() { umma_commit(empty0 + 8 * (g % NST)); g++; };
-            if (do_out) {
+            if (do_out) {      // ACC = attn_o . Wout^T: both operands from shared memory
                 for (int kb = 0; kb < CI / 64; kb++) {
                     const uint32_t a = stage_wait();
                     const int ga = g;
@@ -250,153 +263,150 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
                     const uint32_t b = stage_wait();
                     const uint64_t ad = umma_desc(a), bd = umma_desc(b);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(tmem_base + ACC0, ad + 2 * k, bd + 2 * k, ID256, (kb | k) != 0);
+                    for (int k = 0; k < 4; k++) umma_bf16(tmem_base + ACC, ad + 2 * k, bd + 2 * k, ID256, (kb | k) != 0);
                     umma_commit(empty0 + 8 * (ga % NST));
                     stage_free();
                 }
                 umma_commit(y_full);
-                yf++;
             }
             if (do_ff) {
                 mbar_wait(x_ready, xr & 1); xr++;
                 tc_fence_after();
-                auto issue_s = [&](int j) {      // S_j = X . W0_j^T into S buffer j & 1
+                auto issue_s = [&](int j) {      // S_j = X . W0_j^T into S buffer j & 1; X (the LayerNorm output) is read from TMEM
                     const uint32_t w = stage_wait();
 #pragma unroll
-                    for (int kb = 0; kb < 4; kb++) {
-                        const uint64_t ad = umma_desc(sX + kb * ATOM), bd = umma_desc(w + kb * 8192);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(tmem_base + ACC1 + 64 * (j & 1), ad + 2 * k, bd + 2 * k, ID64, (kb | k) != 0);
+                    for (int kk = 0; kk < 16; kk++) {
+                        if ((p.mode & 16) && (kk & 1)) continue;     // debug: half the S instructions (timing experiment, wrong results)
+                        const uint64_t bd = umma_desc(w + (kk >> 2) * 8192) + 2 * (kk & 3);
+                        umma_ts_bf16(tmem_base + SB + 64 * (j & 1), tmem_base + XT + kk * 8, bd, ID64, kk != 0);
                     }
                     umma_commit(s_full0 + 8 * (j & 1));
                     stage_free();
                 };
                 issue_s(0);
                 for (int j = 0; j < CF / 64; j++) {
-                    // S buffer (j+1)&1 was last read by GELU(j-1): g_ready(j-1) was awaited one iteration ago
+                    // S buffer (j+1)&1 holds G_{j-1}: Y += G_{j-1} W2 was issued one iteration ago and the tensor pipe runs in order
                     if (j + 1 < CF / 64) issue_s(j + 1);
                     mbar_wait(g_ready0 + 8 * (j & 1), (j >> 1) & 1);
                     tc_fence_after();
                     const uint32_t w = stage_wait();
-                    const uint64_t ad = umma_desc(sG + (j & 1) * ATOM), bd = umma_desc(w);
+                    const uint64_t bd = umma_desc(w);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(tmem_base + ACC0, ad + 2 * k, bd + 2 * k, ID256, (j | k) != 0);
-                    umma_commit(g_free0 + 8 * (j & 1));
+                    for (int kk = 0; kk < 4; kk++)       // G_j sits in its S buffer: hidden units 0..31 in columns 0..15, 32..63 in columns 32..47
+                        umma_ts_bf16(tmem_base + ACC, tmem_base + SB + 64 * (j & 1) + (kk < 2 ? kk * 8 : 32 + (kk - 2) * 8), bd + 2 * kk, ID256, (j | kk) != 0);
                     stage_free();
                 }
                 umma_commit(y_full);
-                yf++;
             }
             if (do_qkv) {
                 mbar_wait(x_ready, xr & 1); xr++;
                 tc_fence_after();
-                for (int c = 0; c < NQKV / 256; c++) {
-                    const int a = (c + 1) & 1;            // chunk 0 -> ACC1 (the S buffers are dead), chunk 1 -> ACC0 (Y has been read), ...
+                for (int c = 0; c < NQKV / 128; c++) {
+                    const int a = c & 1;
                     mbar_wait(q_empty0 + 8 * a, ((c >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    for (int kb = 0; kb < 4; kb++) {
+                    for (int kp = 0; kp < 2; kp++) {
                         const uint32_t w = stage_wait();
-                        const uint64_t ad = umma_desc(sX + kb * ATOM), bd = umma_desc(w);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(tmem_base + (a ? ACC1 : ACC0), ad + 2 * k, bd + 2 * k, ID256, (kb | k) != 0);
+                        for (int kk = 0; kk < 8; kk++) {
+                            const uint64_t bd = umma_desc(w + (kk >> 2) * ATOM) + 2 * (kk & 3);
+                            umma_ts_bf16(tmem_base + ACC + 128 * a, tmem_base + XT + (kp * 8 + kk) * 8, bd, ID128, (kp | kk) != 0);
+                        }
                         stage_free();
                     }
                     umma_commit(q_full0 + 8 * a);
                 }
             }
-            (void)yf;
         }
     } else {   // ---------------------------------------------------------------------------------- element-wise warps 2..9
-        const int hh = (warp - 2) >> 2;                        // column half
-        const int r = (warp & 3) * 32 + lane;                  // row of the tile = TMEM lane
-        const bool leader = threadIdx.x == 64;                 // issues the bulk loads / stores of the residual rows and the QKV tiles
-        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t swz = (uint32_t)(r & 7);
-        int yf = 0;
+        const int wid = warp - 2, hh = wid >> 2, q = warp & 3;  // column half, TMEM lane quarter
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t swz = (uint32_t)(lane & 7);
+        const uint32_t io = sIO + wid * 8192;                   // this warp's two 4 KB staging slots
+        const uint32_t hb = hbar0 + wid * 16;
+        const int mrow = m0 + q * 32;                           // first global row of this warp's 32-row slab
+        int yf = 0, qslot = 0;
 
-        // One pass over the tile's residual rows: v = acc (+ bias) + h -> h (if `store`), cached in ACC0; LayerNorm(v) -> X (bf16).
-        // Global traffic goes through the TMA: fp32 atoms [128 rows x 32 cols] (SWIZZLE_128B) land in the four X slots (X itself is
-        // written only afterwards), results leave through the two G slots -- a thread-per-row access pattern straight to global
-        // memory costs 32 L1 wavefronts per instruction and was the bottleneck of the first version of this kernel.
+        // One pass over the warp's slab of the residual rows: v = acc (+ bias) + h -> h (if `store`), cached in ACC; then
+        // LayerNorm(v) -> X (bf16, TMEM).  Every warp runs its own TMA pipeline over [32 rows x 32 cols] fp32 atoms (two staging
+        // slots, results written back in place and stored from there): no block barriers, the eight warps overlap each other's
+        // latencies.  The warp pair (q, hh = 0 / 1) of a row quarter takes the even / odd atoms.
         auto row_pass = [&](bool has_acc, const float* bias, bool store, const float* gamma, const float* beta, bool make_x) {
-            if (leader) {
-                bulk_wait_all();               // earlier stores of h (previous pass) are complete before h is read again
-                for (int a = 0; a < 4; a++) { mbar_expect_tx(hbar0 + 8 * a, ATOM); tma_load_2d(sX + a * ATOM, &tmH, hbar0 + 8 * a, a * 32, m0); }
+            if (lane == 0) {
+                bulk_wait_all();               // this warp's earlier stores of h are complete before the rows are read again
+                for (int k = 0; k < 2; k++) { mbar_expect_tx(hb + 8 * k, 4096); tma_load_2d(io + k * 4096, &tmH, hb + 8 * k, (hh + 2 * k) * 32, mrow); }
             }
             float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-            for (int a = 0; a < 8; a++) {
-                const int c0 = a * 32 + hh * 16;
-                float v[16];
-                if (has_acc) tmem_ld16(trow + ACC0 + c0, v);
+            for (int k = 0; k < 4; k++) {
+                const int c0 = (hh + 2 * k) * 32, slot = k & 1;
+                float v[32];
+                if (has_acc) tmem_ld32(trow + ACC + c0, v);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    for (int i = 0; i < 32; i++) v[i] = 0.f;
                 }
                 if (bias) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) { const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i); v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w; }
+                    for (int i = 0; i < 32; i += 4) { const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + i); v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w; }
                 }
-                mbar_wait(hbar0 + 8 * (a & 3), (a >> 2) & 1);
-                const uint32_t in = sX + (uint32_t)((a & 3) * ATOM + r * 128);
+                mbar_wait(hb + 8 * slot, (k >> 1) & 1);
+                const uint32_t row = io + slot * 4096 + lane * 128;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int c = 0; c < 8; c++) {
                     float x0, x1, x2, x3;
-                    ld_shared_v4(in + (((uint32_t)(hh * 4 + q) ^ swz) << 4), x0, x1, x2, x3);
-                    v[4 * q] += x0; v[4 * q + 1] += x1; v[4 * q + 2] += x2; v[4 * q + 3] += x3;
+                    ld_shared_v4(row + (((uint32_t)c ^ swz) << 4), x0, x1, x2, x3);
+                    v[4 * c] += x0; v[4 * c + 1] += x1; v[4 * c + 2] += x2; v[4 * c + 3] += x3;
                 }
                 if (make_x) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
-                    tmem_st16(trow + ACC0 + c0, v);
+                    for (int i = 0; i < 32; i++) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+                    tmem_st32(trow + ACC + c0, v);
                 }
                 if (store) {
-                    const uint32_t out = sG + (uint32_t)((a & 1) * ATOM + r * 128);
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out + (((uint32_t)(hh * 4 + q) ^ swz) << 4)),
-                                     "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+                    for (int c = 0; c < 8; c++)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)c ^ swz) << 4)),
+                                     "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
                     fence_async_smem();
-                    if (leader) bulk_wait_read0();      // the store of atom a-1 has drained its slot (the one atom a+1 will use)
                 }
-                ew_bar();                               // input slot a&3 is consumed, output slot a&1 is complete
-                if (leader) {
-                    if (store) tma_store_2d(&tmH, sG + (a & 1) * ATOM, a * 32, m0);
-                    if (a + 4 < 8) { mbar_expect_tx(hbar0 + 8 * (a & 3), ATOM); tma_load_2d(sX + (a & 3) * ATOM, &tmH, hbar0 + 8 * (a & 3), (a + 4) * 32, m0); }
+                __syncwarp();
+                if (lane == 0) {
+                    if (store) tma_store_2d(&tmH, io + slot * 4096, c0, mrow);
+                    if (k + 2 < 4) {
+                        if (store) bulk_wait_read0();      // the store has drained the slot
+                        mbar_expect_tx(hb + 8 * slot, 4096);
+                        tma_load_2d(io + slot * 4096, &tmH, hb + 8 * slot, (hh + 2 * (k + 2)) * 32, mrow);
+                    }
                 }
             }
             if (!make_x) return;
-            // the two column halves of a row exchange their partial sums through two spare TMEM columns of the row's lane
-            tmem_st2(trow + ACC1 + hh * 2, sum, sq);
+            // the two warps of a row quarter exchange their partial sums through two spare TMEM columns of the row's lane
+            tmem_st2(trow + SB + hh * 2, sum, sq);
             tc_fence_before();
-            ew_bar();
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
             tc_fence_after();
             {
                 float s2, q2;
-                tmem_ld2(trow + ACC1 + (hh ^ 1) * 2, s2, q2);
+                tmem_ld2(trow + SB + (hh ^ 1) * 2, s2, q2);
                 sum += s2; sq += q2;
             }
             const float mean = sum * (1.f / C);
             const float rstd = rsqrtf(fmaxf(sq * (1.f / C) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll 1
-            for (int a = 0; a < 8; a++) {
-                const int c0 = a * 32 + hh * 16;
-                float v[16];
-                tmem_ld16(trow + ACC0 + c0, v);
-                uint32_t pk[8];
+            for (int k = 0; k < 4; k++) {
+                const int c0 = (hh + 2 * k) * 32;
+                float v[32];
+                tmem_ld32(trow + ACC + c0, v);
+                float pk[16];
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
+                for (int i = 0; i < 32; i += 4) {
                     const float4 gg = *reinterpret_cast<const float4*>(gamma + c0 + i), bb = *reinterpret_cast<const float4*>(beta + c0 + i);
-                    pk[i >> 1] = pack_bf16((v[i] - mean) * rstd * gg.x + bb.x, (v[i + 1] - mean) * rstd * gg.y + bb.y);
-                    pk[(i >> 1) + 1] = pack_bf16((v[i + 2] - mean) * rstd * gg.z + bb.z, (v[i + 3] - mean) * rstd * gg.w + bb.w);
+                    pk[i >> 1] = __uint_as_float(pack_bf16((v[i] - mean) * rstd * gg.x + bb.x, (v[i + 1] - mean) * rstd * gg.y + bb.y));
+                    pk[(i >> 1) + 1] = __uint_as_float(pack_bf16((v[i + 2] - mean) * rstd * gg.z + bb.z, (v[i + 3] - mean) * rstd * gg.w + bb.w));
                 }
-                const uint32_t xrow = sX + (uint32_t)((a >> 1) * ATOM + r * 128);      // k-block a/2, 16-byte chunks (a&1)*4 + hh*2 + {0,1}
-#pragma unroll
-                for (int q = 0; q < 2; q++)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xrow + (((uint32_t)((a & 1) * 4 + hh * 2 + q) ^ swz) << 4)),
-                                 "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                tmem_st16(trow + XT + (c0 >> 1), pk);      // K-major A operand: two bf16 per column
             }
-            fence_async_smem();        // generic-proxy writes of X -> visible to tcgen05.mma
             tc_fence_before();
             mbar_arrive(x_ready);
         };
@@ -409,33 +419,25 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
         if (do_ff) {
             row_pass(do_out, do_out ? p.b_out : nullptr, do_out, p.ln3_g, p.ln3_b, true);
             TAIL_TRACE(3);
-            if (leader) bulk_wait_read0();                 // the G slots become GELU tiles
-            ew_bar();
             for (int j = 0; j < CF / 64; j++) {
-                mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+                mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);      // S_j is complete (and, the pipe being in order, G_{j-2} has been consumed)
                 tc_fence_after();
-                if (j >= 2) mbar_wait(g_free0 + 8 * (j & 1), ((j >> 1) & 1) ^ 1);      // Y += G_{j-2} W2 has read this G buffer
                 float v[32];
-                tmem_ld32(trow + ACC1 + 64 * (j & 1) + hh * 32, v);
+                tmem_ld32(trow + SB + 64 * (j & 1) + hh * 32, v);
                 const float* b0 = p.b0 + j * 64 + hh * 32;
-                uint32_t pk[16];
+                float pk[16];
                 if (p.mode & 8) {      // debug: identity instead of GELU (locates the bottleneck of the loop)
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16(v[i], v[i + 1]);
+                    for (int i = 0; i < 32; i += 2) pk[i >> 1] = __uint_as_float(pack_bf16(v[i], v[i + 1]));
                 } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(b0 + i);
-                    pk[i >> 1] = pack_bf16(gelu_fast(v[i] + bb.x), gelu_fast(v[i + 1] + bb.y));
-                    pk[(i >> 1) + 1] = pack_bf16(gelu_fast(v[i + 2] + bb.z), gelu_fast(v[i + 3] + bb.w));
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(b0 + i);
+                        pk[i >> 1] = __uint_as_float(pack_bf16(gelu_fast(v[i] + bb.x), gelu_fast(v[i + 1] + bb.y)));
+                        pk[(i >> 1) + 1] = __uint_as_float(pack_bf16(gelu_fast(v[i + 2] + bb.z), gelu_fast(v[i + 3] + bb.w)));
+                    }
                 }
-                }
-                const uint32_t grow = sG + (uint32_t)((j & 1) * ATOM + r * 128);
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(grow + (((uint32_t)(hh * 4 + q) ^ swz) << 4)),
-                                 "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-                fence_async_smem();
+                tmem_st16(trow + SB + 64 * (j & 1) + hh * 32, pk);   // G_j overwrites the first half of this thread's own score columns
                 tc_fence_before();
                 mbar_arrive(g_ready0 + 8 * (j & 1));
             }
@@ -452,33 +454,37 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
             row_pass(true, p.b_out, true, nullptr, nullptr, false);
         }
         if (do_qkv) {
-            // accumulator -> bf16 atoms [128 rows x 64 cols] in the G slots -> TMA store (coalesced by the copy engine)
-            for (int c = 0; c < NQKV / 256; c++) {
-                const int a = (c + 1) & 1;
+            // accumulator -> bf16 atoms [32 rows x 64 cols] in the warp's staging slots -> TMA store (coalesced by the copy engine)
+            for (int c = 0; c < NQKV / 128; c++) {
+                const int a = c & 1;
                 mbar_wait(q_full0 + 8 * a, (c >> 1) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int g4 = 0; g4 < 4; g4++) {
-                    const int t = c * 4 + g4;
-                    float v[32];
-                    tmem_ld32(trow + (a ? ACC1 : ACC0) + g4 * 64 + hh * 32, v);
-                    const uint32_t out = sG + (uint32_t)((t & 1) * ATOM + r * 128);
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out + (((uint32_t)(hh * 4 + q) ^ swz) << 4)),
-                                     "r"(pack_bf16(v[8 * q], v[8 * q + 1])), "r"(pack_bf16(v[8 * q + 2], v[8 * q + 3])),
-                                     "r"(pack_bf16(v[8 * q + 4], v[8 * q + 5])), "r"(pack_bf16(v[8 * q + 6], v[8 * q + 7])) : "memory");
-                    fence_async_smem();
-                    if (leader) bulk_wait_read0();      // store t-1 has drained the slot that step t+1 will fill
-                    ew_bar();
-                    if (leader) tma_store_2d(&tmQ, out - r * 128, c * 256 + g4 * 64, m0);
-                }
+                float v0[32], v1[32];
+                tmem_ld32(trow + ACC + 128 * a + hh * 64, v0);
+                tmem_ld32(trow + ACC + 128 * a + hh * 64 + 32, v1);
                 tc_fence_before();
-                mbar_arrive(q_empty0 + 8 * a);
+                mbar_arrive(q_empty0 + 8 * a);             // the accumulator is in registers: hand it back to the tensor core
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store that last used this slot has drained it
+                __syncwarp();
+                const uint32_t row = io + qslot * 4096 + lane * 128;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; c8++)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)c8 ^ swz) << 4)),
+                                 "r"(pack_bf16(v0[8 * c8], v0[8 * c8 + 1])), "r"(pack_bf16(v0[8 * c8 + 2], v0[8 * c8 + 3])),
+                                 "r"(pack_bf16(v0[8 * c8 + 4], v0[8 * c8 + 5])), "r"(pack_bf16(v0[8 * c8 + 6], v0[8 * c8 + 7])) : "memory");
+#pragma unroll
+                for (int c8 = 0; c8 < 4; c8++)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)(c8 + 4) ^ swz) << 4)),
+                                 "r"(pack_bf16(v1[8 * c8], v1[8 * c8 + 1])), "r"(pack_bf16(v1[8 * c8 + 2], v1[8 * c8 + 3])),
+                                 "r"(pack_bf16(v1[8 * c8 + 4], v1[8 * c8 + 5])), "r"(pack_bf16(v1[8 * c8 + 6], v1[8 * c8 + 7])) : "memory");
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tma_store_2d(&tmQ, io + qslot * 4096, c * 128 + hh * 64, mrow);
+                qslot ^= 1;
             }
         }
         TAIL_TRACE(7);
-        if (leader) bulk_wait_all();       // shared memory must outlive the bulk stores
+        if (lane == 0) bulk_wait_all();       // shared memory must outlive the bulk stores
         TAIL_TRACE(8);
     }
     tc_fence_before();
@@ -522,7 +528,7 @@ void cfm_tail_weights(CfmTailWeights& w, const bf16* wout, const bf16* w0, const
     if (wout) ok = ok && map2d(reinterpret_cast<CUtensorMap*>(w.out), wout, CI, C, CI, 256);
     if (w0) ok = ok && map2d(reinterpret_cast<CUtensorMap*>(w.w0), w0, C, CF, C, 64);
     if (w2) ok = ok && map2d(reinterpret_cast<CUtensorMap*>(w.w2), w2, CF, C, CF, 256);
-    if (wqkv) ok = ok && map2d(reinterpret_cast<CUtensorMap*>(w.qkv), wqkv, C, NQKV, C, 256);
+    if (wqkv) ok = ok && map2d(reinterpret_cast<CUtensorMap*>(w.qkv), wqkv, C, NQKV, C, 128);
     CBX_REQUIRE(ok, "cfm_tail: cuTensorMapEncodeTiled failed for a weight");
     w.has_out = wout != nullptr; w.has_ff = w0 != nullptr && w2 != nullptr; w.has_qkv = wqkv != nullptr;
 }
@@ -535,8 +541,8 @@ void launch_cfm_tail(const CfmTailArgs& a, const bf16* attn_o, const CfmTailWeig
     CBX_REQUIRE(!(a.mode & CFM_TAIL_FF) || (blk && blk->has_ff && a.b0 && a.b2 && a.ln3_g && a.ln3_b), "cfm_tail: FF phase needs the feed-forward weights");
     CBX_REQUIRE(!(a.mode & CFM_TAIL_QKV) || (nxt && nxt->has_qkv && a.ln1_g && a.ln1_b && a.qkv), "cfm_tail: QKV phase needs the next block's weights");
     alignas(64) CUtensorMap tmO, tmH, tmQ;
-    CBX_REQUIRE(map2d(&tmH, a.h, C, a.M, C, 128, true), "cfm_tail: tensor map for the residual rows");
-    if (a.mode & CFM_TAIL_QKV) CBX_REQUIRE(map2d(&tmQ, a.qkv, NQKV, a.M, NQKV, 128), "cfm_tail: tensor map for the qkv output");
+    CBX_REQUIRE(map2d(&tmH, a.h, C, a.M, C, 32, true), "cfm_tail: tensor map for the residual rows");
+    if (a.mode & CFM_TAIL_QKV) CBX_REQUIRE(map2d(&tmQ, a.qkv, NQKV, a.M, NQKV, 32), "cfm_tail: tensor map for the qkv output");
     else tmQ = tmH;
     const CfmTailWeights* any = blk ? blk : nxt;
     if (a.mode & CFM_TAIL_OUT) CBX_REQUIRE(map2d(&tmO, attn_o, CI, a.M, CI, 128), "cfm_tail: tensor map for attn_o");

@@ -273,9 +273,9 @@ static void tfm_block(cbx_engine* e, Lane& L, const TfmP& t, int T, bool pre_nor
 // Rows from which the fused block tail (cfm_tail.cu: one kernel for out-proj + LN + GELU-FF + next LN + QKV per 128-row tile)
 // replaces the six separate launches.  A tile is a ~40 us serial chain on ONE SM, so a single call (M ~ 900 rows = 8 tiles)
 // is faster through the wide separate GEMMs; batches fill the SMs with tiles.
-static int fused_tail_min_rows() {
-    static const int v = [] { const char* e = getenv("CBX_CFM_TAIL_MIN_ROWS"); return e ? atoi(e) : 4096; }();
-    return v;
+static int fused_tail_min_rows() {      // read per call (once per estimator stage): tests switch paths at run time
+    const char* e = getenv("CBX_CFM_TAIL_MIN_ROWS");
+    return e ? atoi(e) : 4096;
 }
 
 // the transformer blocks [j0, j0 + nb) of one estimator stage

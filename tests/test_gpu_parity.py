@@ -332,18 +332,21 @@ def test_s3gen_end_to_end_shapes(tiny, tiny_cfg, dev):
     assert torch.allclose(wav2, wav, atol=1e-6), "same tokens + full cache_source => same audio"
 
 
-def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev):
+@pytest.mark.parametrize("tail_min_rows", ["0", "1000000000"])      # every call through the fused block-tail kernel / through the separate GEMMs
+def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev, monkeypatch, tail_min_rows):
     """cbx_s3gen_infer_batch pads the calls to the longest sequence and runs one token->mel pass; padding is exact
     (causal convs, per-frame norms, per-sequence attention masks, zeroed look-ahead rows), so every call must
     reproduce its single-call result: mel to float rounding (GEMM tile membership changes nothing in the K order,
     only the padded tail differs), waveform likewise with the same seed and source cache."""
     from cbx_b200.weights import synthetic_conditionals
+    monkeypatch.setenv("CBX_CFM_TAIL_MIN_ROWS", tail_min_rows)      # single calls and batches must take the SAME kernels for a float-rounding comparison
     eng, sd_dev, conds, voice = tiny
     c2 = synthetic_conditionals(tiny_cfg, 77, prompt_tokens=23)    # a second voice with a different prompt length
     c2["gen"]["prompt_feat"] = c2["gen"]["prompt_feat"].to(torch.bfloat16).float()
     v2 = eng.voice_put("w", c2["t3"], c2["gen"])
     g = torch.Generator().manual_seed(9)
-    lens = [35, 3, 70, 41, 12]
+    o = 0 if tail_min_rows == "0" else 1      # different lengths per variant: single calls replay CUDA graphs keyed by (voice, length)
+    lens = [35 + o, 3 + o, 70 + o, 41 + o, 12 + o]
     voices = [voice, v2, voice, v2, voice]
     toks = [torch.randint(0, 6561, (n,), generator=g).numpy().astype(np.int32) for n in lens]
     single = []
@@ -364,7 +367,7 @@ def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev):
         assert torch.equal(got[1], ref[1]) or _rel(got[1], ref[1]) < 1e-4
         assert _rel(got[0], ref[0]) < 1e-3
     # more than 8 calls in one batch (the capacity is 16), lengths all different
-    lens12 = [3 + 5 * i for i in range(12)]
+    lens12 = [3 + o + 5 * i for i in range(12)]
     toks12 = [torch.randint(0, 6561, (n,), generator=g).numpy().astype(np.int32) for n in lens12]
     ref12 = [eng.s3gen_infer(voices[i % 5], t, seed=9, return_mel=True)[2].clone() for i, t in enumerate(toks12)]
     got12 = eng.s3gen_infer_batch([(voices[i % 5], t, None, 9) for i, t in enumerate(toks12)], return_mel=True)

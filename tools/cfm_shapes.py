@@ -65,7 +65,7 @@ for M in rows:
     o, h, qkv = bf(M, 512), torch.randn(M, 256, device=dev), torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
     wout, w0, w2, wq = bf(256, 512), bf(1024, 256), bf(256, 1024), bf(1536, 256)
     v256, v1024 = torch.randn(256, device=dev) * 0.1, torch.randn(1024, device=dev) * 0.1
-    for mode, name in ((7, "OUT|FF|QKV"), (3, "OUT|FF"), (4, "QKV"), (11, "OUT|FF id")):
+    for mode, name in ((7, "OUT|FF|QKV"), (3, "OUT|FF"), (4, "QKV"), (11, "OUT|FF id"), (27, "id, S/2")):
         fl = 2.0 * M * ((256 * 512 if mode & 1 else 0) + (2 * 256 * 1024 if mode & 2 else 0) + (256 * 1536 if mode & 4 else 0))
         us = bench(lambda: L.check(lib.cbx_op_cfm_tail(mode, M, o.data_ptr(), h.data_ptr(), wout.data_ptr(), v256.data_ptr(), v256.data_ptr(), v256.data_ptr(),
                                                        w0.data_ptr(), v1024.data_ptr(), w2.data_ptr(), v256.data_ptr(), v256.data_ptr(), v256.data_ptr(),

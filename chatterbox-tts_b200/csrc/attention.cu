@@ -197,12 +197,13 @@ __global__ void __launch_bounds__(NT) attn_kernel(const AttnParams p) {
 
 }  // namespace
 
-void attention_init() { attention_tc_init(); CBX_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 2 * KVS * STAGE_BYTES)); }
+void attention_init() { attention_fa_init(); attention_tc_init(); CBX_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 2 * KVS * STAGE_BYTES)); }
 
 void launch_attention(const AttnParams& p, cudaStream_t st) {
     CBX_REQUIRE(p.T > 0 && p.H > 0 && p.batch > 0, "attention: empty problem");
     CBX_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "attention: row strides must keep 16B alignment");
-    if (launch_attention_tc(p, st)) return;   // tcgen05 kernel: full attention without bias (the CFM transformer blocks)
+    if (launch_attention_fa(p, st)) return;   // tcgen05 kernel, second generation: full / causal attention without bias (CFM blocks, T3 prefill)
+    if (launch_attention_tc(p, st)) return;   // first-generation tcgen05 kernel (CBX_DISABLE_ATTN_FA=1)
     const int smem = TILE_BYTES + 2 * KVS * STAGE_BYTES;
     ProfScope ps(PC_ATTN, 4.0 * p.T * p.T * D * p.H * p.batch * (p.causal ? 0.5 : 1.0), st);
     dim3 grid(cdiv(p.T, BQ), p.H, p.batch);

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_consta
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {   // TMA producer: two K stages (S_{j+1} follows PV_j at once), one V stage
+        if (elect_one()) {   // TMA producer: two K stages (S_{j+1} follows PV_j at once), one V stage
             mbar_expect_tx(q_full, TILE);
             tma_load_3d(sQ, &tmQ, q_full, h * D, q0, b);
             for (int j = 0; j < nkv; j++) {
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // MMA issuer
+        if (elect_one()) {   // MMA issuer
             // instruction descriptors: D=f32, A=B=bf16; S: N=128, both K-major; PV: N=64, B (= V) MN-major
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BK >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
             const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
@@ -298,4 +298,6 @@ bool launch_attention_tc(const AttnParams& p, cudaStream_t st) {
     return true;
 }
 
-extern "C" long long cbx_attn_tc_launches(void) { return g_launches; }
+extern "C" long long cbx_attn_fa_launches(void);
+// both tcgen05 attention kernels (this one and attention_fa.cu)
+extern "C" long long cbx_attn_tc_launches(void) { return g_launches + cbx_attn_fa_launches(); }

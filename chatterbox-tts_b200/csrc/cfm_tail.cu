@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {   // ------------------------------------------------------------------ TMA producer (weights + attn_o)
+        if (elect_one()) {   // ------------------------------------------------------------------ TMA producer (weights + attn_o)
             int g = 0;
             auto acquire = [&](uint32_t bytes) -> uint32_t {     // next ring stage, armed for `bytes`
                 const int s = g % NST;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {   // ------------------------------------------------------------------ MMA issuer
             constexpr uint32_t ID = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);   // D f32, A = B = bf16, K-major, M = 128
             constexpr uint32_t ID256 = ID | ((uint32_t)(256 >> 3) << 17), ID128 = ID | ((uint32_t)(128 >> 3) << 17), ID64 = ID | ((uint32_t)(64 >> 3) << 17);
             int g = 0, xr = 0;

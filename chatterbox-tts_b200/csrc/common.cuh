@@ -105,6 +105,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// One lane of a converged warp (elect.sync).  Use this, not `lane == 0`, to pick the thread that issues tcgen05.mma / TMA
+// instructions: their operands live in uniform registers, and under a lane test the compiler cannot prove the region is
+// single-threaded, so it wraps EVERY such instruction in an election loop with one R2UR broadcast per operand (~80 cycles per
+// tcgen05.mma, measured in attention_fa.cu, against 32-64 cycles of tensor-pipe time).  After elect.sync the instructions are
+// issued back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- Philox4x32-10 (counter-based RNG)
 struct Philox {
     __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
@@ -203,4 +214,6 @@ struct AttnParams {
 void launch_attention(const AttnParams& p, cudaStream_t st);
 void attention_init();
 void attention_tc_init();
+void attention_fa_init();
+bool launch_attention_fa(const AttnParams& p, cudaStream_t st);   // false: not applicable (additive bias / alignment)
 bool launch_attention_tc(const AttnParams& p, cudaStream_t st);   // false: not applicable (bias / causal / alignment)

@@ -389,7 +389,8 @@ int cbx_s3gen_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, co
         CBX_CHECK(cudaStreamSynchronize(L.st));          // previous call's read of the pinned params has retired
         L.g_dyn_h->cache_len = m; L.g_dyn_h->seed = seed;
         CBX_CHECK(cudaMemcpyAsync(L.g_dyn, L.g_dyn_h, sizeof(SourceDyn), cudaMemcpyHostToDevice, L.st));
-        const unsigned long long key = ((unsigned long long)voice << 48) | ((unsigned long long)(v.version & 0xFFFF) << 32) | ((unsigned long long)v.n_prompt << 16) | (unsigned long long)n;
+        const unsigned long long key = ((unsigned long long)voice << 48) | ((unsigned long long)(v.version & 0xFFFF) << 32) | ((unsigned long long)v.n_prompt << 16) | (unsigned long long)n |
+                                       (flow_tail_path(4L * (v.n_prompt + n)) ? 1ull << 63 : 0ull);     // which kernels the capture holds
         auto it = L.graphs.find(key);
         if (it == L.graphs.end()) {
             const long before = e->gpu_launches.load();

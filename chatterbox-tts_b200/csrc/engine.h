@@ -135,6 +135,7 @@ void hift_build(cbx_engine* e);
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
                 const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr);
 void flow_stage(cbx_engine* e, Lane& L, const int* const* tokens_h, cudaStream_t st);   // L.nb / L.call[] set by the caller
+bool flow_tail_path(long rows);                                                          // fused block-tail kernels for a call of this many estimator rows?
 void flow_run(cbx_engine* e, Lane& L, cudaStream_t st);                                  // -> L.melb
 void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st);
 void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* cache_src_dev, long m, float* src_out,

@@ -278,11 +278,15 @@ static int fused_tail_min_rows() {      // read per call (once per estimator sta
     return e ? atoi(e) : 4096;
 }
 
+// does a call of `rows` estimator rows (2 x calls x frames) take the fused-tail kernels?  (part of the CUDA-graph key of a
+// single call: the setting can change at run time)
+bool flow_tail_path(long rows) { return cfm_tail_available() && !fuse_ln() && rows >= fused_tail_min_rows(); }
+
 // the transformer blocks [j0, j0 + nb) of one estimator stage
 static void tfm_stage(cbx_engine* e, Lane& L, int j0, int nb, int T, cudaStream_t st) {
     FlowModel& f = e->flow;
     const int M = 2 * L.nb * T;
-    if (cfm_tail_available() && !fuse_ln() && M >= fused_tail_min_rows()) {
+    if (flow_tail_path(M)) {
         // stage opener: LayerNorm1 + QKV of the first block; then per block: attention, fused tail (+ next block's LN1 / QKV)
         CfmTailArgs a; a.M = M; a.h = L.c_h; a.qkv = L.c_qkv;
         a.mode = CFM_TAIL_QKV; a.ln1_g = f.tfms[j0].n1.g; a.ln1_b = f.tfms[j0].n1.b;

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__
     // warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer; afterwards all 8 warps run the epilogue
     // (TMEM lane quarter = warp % 4, column half = warp / 4)
     if (warp == 0) {
-        if (lane == 0) {   // TMA producer
+        if (elect_one()) {   // TMA producer
             for (int kb = 0; kb < KB; kb++) {
                 const int s = kb % C::STAGES, ph = (kb / C::STAGES) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {   // MMA issuer
+        if (elect_one()) {   // MMA issuer
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int kb = 0; kb < KB; kb++) {
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_persistent_kernel(const __grid
     auto tile_coords = [&](int t, int& m0, int& n0, int& b) { n0 = (t % tiles_n) * BN; m0 = ((t / tiles_n) % tiles_m) * TM; b = t / (tiles_n * tiles_m); };
 
     if (warp == 0) {
-        if (lane == 0) {   // TMA producer: the ring runs ahead into the next tile
+        if (elect_one()) {   // TMA producer: the ring runs ahead into the next tile
             int g = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 int m0, n0, b;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_persistent_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // MMA issuer: accumulator it & 1
+        if (elect_one()) {   // MMA issuer: accumulator it & 1
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             int g = 0, it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {

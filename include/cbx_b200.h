@@ -123,8 +123,12 @@ int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const fl
 int64_t cbx_gpu_launches(cbx_engine* e);
 /* GEMM launches that took the tcgen05/TMA path (process-wide; 0 means the mma.sync fallback served everything) */
 long long cbx_gemm_tc_launches(void);
-/* attention launches served by the tcgen05 flash-attention kernel (process-wide) */
+/* attention launches served by the tcgen05 flash-attention kernels (process-wide; both generations) */
 long long cbx_attn_tc_launches(void);
+/* of those, the launches of the second-generation kernel (P and O in tensor memory, attention_fa.cu) */
+long long cbx_attn_fa_launches(void);
+/* debug (CBX_ATTN_FA_DBG=4): %globaltimer stamps of the first CTA of the last launch (MMA issuer and softmax row 0 per key block) */
+int cbx_attn_fa_trace(unsigned long long* out_h);
 /* debug: %globaltimer stamps (ns) of the last tcgen05 GEMM's CTA 0: start, setup done, first TMA landed, MMAs issued,
  * accumulator ready, epilogue done, teardown */
 int cbx_gemm_tc_trace(unsigned long long* out_h);

@@ -14,12 +14,22 @@ def engine(tiny_cfg):
         pytest.skip("no CUDA device")
     from cbx_b200.engine import TextToSpeechEngine, SamplingDefaults
     from cbx_b200.weights import random_state_dict
+    # The CFM block tail has two kernel paths chosen by the ROWS of a batched call (fused tail from 4096 rows, csrc/flow.cu):
+    # which requests share a batch depends on timing, so bit-exact reproducibility is a property of a PINNED path.  These
+    # tests pin the fused tail for every call (that also puts it on the end-to-end path of a small model).
+    import os
+    old = os.environ.get("CBX_CFM_TAIL_MIN_ROWS")
+    os.environ["CBX_CFM_TAIL_MIN_ROWS"] = "0"
     eng = TextToSpeechEngine("cuda:0", cfg=tiny_cfg, state_dict=random_state_dict(tiny_cfg, 0), concurrent_requests=4,
                              sampling=SamplingDefaults(tokens_per_word=10), seed=0,
                              native_kwargs=dict(max_s3_tokens=400, n_lanes=4))
     asyncio.run(eng.ainit())
     yield eng
     eng.shutdown()
+    if old is None:
+        os.environ.pop("CBX_CFM_TAIL_MIN_ROWS", None)
+    else:
+        os.environ["CBX_CFM_TAIL_MIN_ROWS"] = old
 
 
 REQ = dict(output_format="raw_pcm", voice_id=None, cfg_guidance_weight=0.5, synthesis_temperature=0.8, text_processing_chunk_size=150,

@@ -63,7 +63,8 @@ def test_gemm_op(dev, M, N, K):
         assert _rel(out, ref) < 1e-5
 
 
-@pytest.mark.parametrize("T,H,B,causal", [(64, 8, 2, 0), (100, 8, 1, 0), (333, 16, 2, 1), (1000, 8, 2, 0), (128, 8, 1, 0), (458, 8, 16, 0), (129, 1, 1, 0)])
+@pytest.mark.parametrize("T,H,B,causal", [(64, 8, 2, 0), (100, 8, 1, 0), (333, 16, 2, 1), (1000, 8, 2, 0), (128, 8, 1, 0), (458, 8, 16, 0), (129, 1, 1, 0),
+                                          (668, 8, 16, 0), (257, 8, 2, 0), (256, 8, 2, 1), (185, 16, 4, 1), (1200, 16, 1, 1), (1, 8, 1, 0)])
 def test_attention_op(dev, T, H, B, causal):
     from cbx_b200 import lib as L
     lib = L.load()
@@ -75,11 +76,13 @@ def test_attention_op(dev, T, H, B, causal):
     q, k, v = (t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(H * 64, dim=-1))
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=bool(causal)).transpose(1, 2).reshape(B, T, H * 64)
     assert _rel(out.float(), ref) < 1e-2   # P is rounded to bf16 before the PV product
-    if not causal:   # full attention without bias must be served by the tcgen05 kernel
-        before = lib.cbx_attn_tc_launches()
-        L.check(lib.cbx_op_attention(qkv.data_ptr(), out.data_ptr(), T, H, B, causal, None))
-        torch.cuda.synchronize()
-        assert lib.cbx_attn_tc_launches() == before + 1
+    # attention without an additive bias (full or causal) must be served by the tcgen05 kernel with P and O in tensor memory
+    before = lib.cbx_attn_fa_launches()
+    out2 = torch.empty_like(out)
+    L.check(lib.cbx_op_attention(qkv.data_ptr(), out2.data_ptr(), T, H, B, causal, None))
+    torch.cuda.synchronize()
+    assert lib.cbx_attn_fa_launches() == before + 1
+    assert torch.equal(out, out2), "run-to-run determinism"
 
 
 @pytest.mark.parametrize("M,mode", [(128, 7), (300, 7), (1000, 3), (1000, 4), (5000, 7), (77, 1), (2049, 6)])
@@ -367,7 +370,7 @@ def test_s3gen_batch_matches_single_calls(tiny, tiny_cfg, dev, monkeypatch, tail
         assert torch.equal(got[1], ref[1]) or _rel(got[1], ref[1]) < 1e-4
         assert _rel(got[0], ref[0]) < 1e-3
     # more than 8 calls in one batch (the capacity is 16), lengths all different
-    lens12 = [3 + o + 5 * i for i in range(12)]
+    lens12 = [5 + o + 6 * i for i in range(12)]
     toks12 = [torch.randint(0, 6561, (n,), generator=g).numpy().astype(np.int32) for n in lens12]
     ref12 = [eng.s3gen_infer(voices[i % 5], t, seed=9, return_mel=True)[2].clone() for i, t in enumerate(toks12)]
     got12 = eng.s3gen_infer_batch([(voices[i % 5], t, None, 9) for i, t in enumerate(toks12)], return_mel=True)

@@ -36,7 +36,7 @@ def bench(fn, reps=20):
     return a.elapsed_time(b) * 1e3 / (5 * reps)
 
 
-rows = [int(x) for x in (sys.argv[1:] or ["916", "7328", "10688", "21376"])]
+rows = [] if sys.argv[1:2] == ["attn"] else [int(x) for x in (sys.argv[1:] or ["916", "7328", "10688", "21376"])]
 print(f"{'M':>6} {'N':>5} {'K':>5} | {'ours us':>8} {'TF/s':>7} | {'cublas us':>9} {'TF/s':>7} | layer")
 for M in rows:
     for (N, K, name) in [(1536, 256, "qkv"), (256, 512, "attn out"), (1024, 256, "ff0"), (256, 1024, "ff2"), (256, 768, "resnet conv k3"), (256, 960, "resnet c1 (320 x 3)")]:
@@ -75,10 +75,18 @@ for M in rows:
         d = [int(tr[i]) - int(tr[0]) for i in range(9)]
         print(f"  M={M:6d} {name:10s}: {us:8.2f} us  {fl / us / 1e6:7.1f} TFLOP/s  ({-(-M // 128)} tiles)  ns since start: deps {d[1]}, out-acc {d[2]}, ln3 {d[3]}, gelu {d[4]}, ff-acc {d[5]}, pass2 {d[6]}, qkv {d[7]}, end {d[8]}")
 print("attention (tcgen05), 8 heads x 64:")
-for (T, B) in [(458, 2), (458, 16), (668, 16), (878, 16), (668, 32)]:
+for (T, B) in [(458, 2), (458, 16), (668, 2), (668, 16), (878, 16), (668, 32), (2048, 16)]:
     qkv = torch.randn(B, T, 3 * 512, device=dev).to(torch.bfloat16)
     o = torch.empty(B, T, 512, device=dev, dtype=torch.bfloat16)
     us = bench(lambda: L.check(lib.cbx_op_attention(qkv.data_ptr(), o.data_ptr(), T, 8, B, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))))
     print(f"  T={T:4d} B={B:2d}: {us:8.2f} us  {4.0 * T * T * 64 * 8 * B / us / 1e6:7.1f} TFLOP/s")
+    if os.environ.get("CBX_ATTN_FA_DBG", "0") == "4":
+        tr = (C.c_ulonglong * 256)()
+        lib.cbx_attn_fa_trace(tr)
+        t0 = int(tr[128 + 1])
+        for j in range(min(8, -(-T // 128))):
+            for g in range(2):
+                i, k = 64 + (j * 2 + g) * 3, 128 + (j * 2 + g) * 4
+                print(f"      j={j} g={g}: issuer wait {int(tr[i]) - t0:6d} -> {int(tr[i + 1]) - t0:6d}, issued {int(tr[i + 2]) - t0:6d} | softmax wait {int(tr[k]) - t0:6d} -> {int(tr[k + 1]) - t0:6d}, S in regs {int(tr[k + 2]) - t0:6d}, max {int(tr[192 + (j * 2 + g) * 4]) - t0:6d}, O ok {int(tr[193 + (j * 2 + g) * 4]) - t0:6d}, turn {int(tr[194 + (j * 2 + g) * 4]) - t0:6d}, exp done {int(tr[195 + (j * 2 + g) * 4]) - t0:6d}, P out {int(tr[k + 3]) - t0:6d}")
 x = torch.randn(1 << 16, device=dev)
 print("empty-ish torch kernel:", bench(lambda: x.add_(1.0)), "us")

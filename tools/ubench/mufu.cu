@@ -1,0 +1,52 @@
+// Micro-benchmark: MUFU.EX2 issue rate per SM sub-partition on sm_100a (one or two warps per sub-partition), alone and in the
+// softmax instruction mix (FFMA + EX2 + FADD + pack).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mufu mufu.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int MODE>
+__global__ void k(float* out, long long* cyc, float a, float b, int iters) {
+    float s[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) s[i] = a * (float)(i + threadIdx.x) * 1e-3f;
+    float l0 = 0.f, l1 = 0.f;
+    unsigned acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+            if (MODE == 0) { s[i] = ex2(s[i]); s[i + 1] = ex2(s[i + 1]); }
+            else {
+                float e0 = ex2(fmaf(s[i], a, b)), e1 = ex2(fmaf(s[i + 1], a, b));
+                l0 += e0; l1 += e1;
+                if (MODE == 2) { __nv_bfloat162 v = __floats2bfloat162_rn(e0, e1); acc ^= *reinterpret_cast<unsigned*>(&v); }
+                s[i] = e0 - 1.0f; s[i + 1] = e1 - 1.0f;
+            }
+        }
+    }
+    long long t1 = clock64();
+    float r = l0 + l1 + __uint_as_float(acc);
+    for (int i = 0; i < 64; i++) r += s[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+int main() {
+    float* out; long long* cyc; cudaMalloc(&out, 1 << 24); cudaMalloc(&cyc, 8);
+    const int iters = 200;
+    for (int mode = 0; mode < 3; mode++)
+        for (int threads : {128, 256, 512}) {
+            long long c = 0;
+            for (int rep = 0; rep < 2; rep++) {
+                if (mode == 0) k<0><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
+                if (mode == 1) k<1><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
+                if (mode == 2) k<2><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
+                cudaDeviceSynchronize();
+            }
+            cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+            const double per_sub = (double)iters * 64 * (threads / 128);      // warp-wide ex2 per sub-partition
+            printf("mode %d (%s) warps/subpartition %d: %.2f cycles per warp-wide EX2 per sub-partition (%s)\n", mode,
+                   mode == 0 ? "ex2 only" : mode == 1 ? "ffma+ex2+fadd+fadd" : "ffma+ex2+fadd+fadd+pack", threads / 128, (double)c / per_sub, cudaGetErrorString(cudaGetLastError()));
+        }
+    return 0;
+}

@@ -117,12 +117,12 @@ class T3Scheduler(threading.Thread):
         self.lock = threading.Condition()
         self.running = True
         self.rounds = 0
-        # CBX_T3_ALIGN_OPENS_MS > 0 (opt-in, default 0): while every open stream is still at token 0 and other streams are being
-        # opened (their prefills run one after the other), the first decode round waits up to this long, so that requests that
-        # arrive together decode in lockstep and their first slices share ONE S3Gen batch instead of "first alone, rest in
-        # the next batch" (8 streams today: 120 ms for the first request, 220-234 ms for the other seven).  Host logic only;
-        # its effect on a B200 has not been measured yet.
-        self.align_s = float(os.environ.get("CBX_T3_ALIGN_OPENS_MS", "0")) * 1e-3
+        # CBX_T3_ALIGN_OPENS_MS (default 30, 0 = off): while every open stream is still at token 0 and other streams are being
+        # opened (their prefills run one after the other, ~3 ms each), the first decode round waits up to this long, so that
+        # requests that arrive together decode in lockstep and their first slices share ONE S3Gen batch instead of "first
+        # alone, rest in the next batch".  Measured on a B200 (tools/conc_bench.py, 8 streams x 100 words, second wave): first
+        # chunk p50 468 ms without, 255 ms at 5 ms, 207 ms at 15 ms.  A lone request never waits (nothing else is opening).
+        self.align_s = float(os.environ.get("CBX_T3_ALIGN_OPENS_MS", "30")) * 1e-3
         self.opening = 0
         self.unhealthy: Optional[BaseException] = None   # a native slot could not be closed: its pages are lost, refuse new work
         self.start()
@@ -282,7 +282,7 @@ class S3GenBatcher:
         n = workers or int(os.environ.get("CBX_S3GEN_WORKERS", "1"))
         # after the first pending job shows up, wait this long for companions (slices of concurrent requests become ready
         # within a decode round of each other): one batch of 8 beats a single call followed by a batch of 7
-        self.gather_s = float(os.environ.get("CBX_S3GEN_GATHER_MS", "2")) * 1e-3
+        self.gather_s = float(os.environ.get("CBX_S3GEN_GATHER_MS", "3")) * 1e-3
         self.urgent_window_s = float(os.environ.get("CBX_S3GEN_URGENT_MS", "15")) * 1e-3   # upper bound; the emitter ends it
         self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
         for t in self.threads:
@@ -329,9 +329,16 @@ class S3GenBatcher:
         while True:
             with self.cv:
                 batch = []
+                idle = not self.jobs      # nothing accumulated while the previous batch ran: the next job opens a gather window
                 while self.running:
-                    if self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch:
-                        self.cv.wait(self.gather_s)
+                    if idle and self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch:
+                        # every submit wakes this wait: keep gathering until the window (counted from the first job) closes
+                        t_end = time.time() + self.gather_s
+                        while self.running and len(self.jobs) < self.max_batch:
+                            left = t_end - time.time()
+                            if left <= 0:
+                                break
+                            self.cv.wait(left)
                     batch = self._take() if self.jobs else []
                     if batch:
                         break
@@ -536,7 +543,8 @@ class TextToSpeechEngine:
         else:
             raise RuntimeError(f"{cp} is missing: a real checkpoint needs its default voice conditioning (reference :399-404)")
         self.voice_cache["default"] = self.native.voice_put("default", self.default_conds["t3"], self.default_conds["gen"])
-        self.scheduler = T3Scheduler(self.native, max_batch=min(8, self.native_kwargs["max_streams"]))
+        # up to 16 streams (32 rows) decode in ONE pass over the weights; more are rotated in groups
+        self.scheduler = T3Scheduler(self.native, max_batch=min(int(os.environ.get("CBX_T3_MAX_BATCH", "16")), self.native_kwargs["max_streams"]))
         self.s3gen = S3GenBatcher(self.native)
         self.t3_slots = PrioritySlots(self.native_kwargs["max_streams"] - 1)   # one slot stays free for warm-up / direct opens
         # warm-up, as the reference does (:274-326): 4 T3 tokens with cfg 0, one tiny S3Gen call

@@ -28,10 +28,26 @@ def _f32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 
 
+_FADE_CACHE = {}
+_FADE_LOCK = threading.Lock()
+
+
 def fade_curves(fade_len: int, device):
-    """(fade_in, fade_out) exactly as the reference builds them per request (src/tts_streaming.py:867-871)."""
-    t = torch.linspace(0, 1, fade_len, device=device)
-    return torch.sin(t * 0.5 * torch.pi), torch.cos(t * 0.5 * torch.pi)
+    """(fade_in, fade_out) exactly as the reference builds them per request (src/tts_streaming.py:867-871).  The values
+    depend only on (length, device), so they are built once and kept: building them per request allocates on the request
+    thread's fresh CUDA stream, which misses the caching allocator's per-stream pools and falls through to cudaMalloc --
+    measured as 40-90 ms before the request's first T3 launch in one request out of three (tools/first_chunk.py)."""
+    key = (int(fade_len), str(device))
+    with _FADE_LOCK:
+        c = _FADE_CACHE.get(key)
+        if c is None:
+            t = torch.linspace(0, 1, fade_len, device=device)
+            c = (torch.sin(t * 0.5 * torch.pi), torch.cos(t * 0.5 * torch.pi))
+            torch.cuda.synchronize(device)      # other streams read these
+            if len(_FADE_CACHE) > 64:
+                _FADE_CACHE.clear()
+            _FADE_CACHE[key] = c
+    return c
 
 
 class NativeEngine:

@@ -234,7 +234,7 @@ static void enqueue_sampler(cbx_engine* e, int n, const float* noise, cudaStream
 static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t st) {
     T3Model& m = e->t3;
     const int rows = 2 * n;
-    if (m.mega) {   // whole step = one persistent cooperative kernel + the sampler
+    if (m.mega && rows <= 16) {   // whole step = one persistent cooperative kernel + the sampler (instances for up to 16 rows)
         MegaParams p;
         p.layers = m.d_layers; p.n_layers = e->cfg.t3_layers; p.head_f = m.head_f; p.head_items = T3_VPAD / 16; p.vocab = T3_V; p.final_norm = m.final_norm;
         p.x = m.x; p.logits = m.logits; p.ld_logits = T3_VPAD;
@@ -284,7 +284,7 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
 
 void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* noise_dev, cudaStream_t st) {
     T3Model& m = e->t3;
-    CBX_REQUIRE(n >= 1 && n <= e->cfg.max_streams && 2 * n <= 16, "t3_step: between 1 and 8 streams per call");
+    CBX_REQUIRE(n >= 1 && n <= e->cfg.max_streams && 2 * n <= 32, "t3_step: between 1 and 16 streams per call");
     std::vector<int> act(slots, slots + n);
     for (int s : act) CBX_REQUIRE(s >= 0 && s < e->cfg.max_streams && m.slot_used[s], "t3_step: slot is not open");
     if (act != m.h_active) {
@@ -295,7 +295,8 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
         CBX_CHECK(cudaStreamSynchronize(st));
         m.h_active = act;
     }
-    const long per_step = m.mega ? 2 : 5L * e->cfg.t3_layers + 2;
+    const bool mega = m.mega && 2 * n <= 16;
+    const long per_step = mega ? 2 : (5L + (2 * n > 16 ? 1 : 0)) * e->cfg.t3_layers + 2;     // > 16 rows: the down projection runs as two passes
     // algorithmic bytes of one step: every weight once for all rows + the KV cache of every row (host-side position estimate)
     double kv_pos = 0;
     for (int s : act) { kv_pos += 2.0 * m.slot_pos_h[s]; m.slot_pos_h[s] += n_steps; }
@@ -303,7 +304,7 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
     if (noise_dev) {
         for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev ? noise_dev + (long)i * n * T3_V : nullptr, st);
     } else {
-        const int gkey = n + (m.mega ? 1000 : 0);
+        const int gkey = n + (mega ? 1000 : 0);
         auto it = m.step_graphs.find(gkey);
         if (it == m.step_graphs.end()) {
             cudaGraph_t graph;

@@ -579,6 +579,7 @@ __global__ void scale_vec_kernel(float* out, const float* __restrict__ w, float 
 void t3_kernels_init() {
     CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 void launch_prompt_embed(float* out, const float* emb, const float* pos, const int* ids, int n, int D, cudaStream_t st) {
     launch_pdl(prompt_embed_kernel, dim3(cdiv((long)n * D, 256)), dim3(256), 0, st, out, emb, pos, ids, n, D);
@@ -590,16 +591,27 @@ void launch_scale_vec(float* out, const float* w, float s, int n, cudaStream_t s
 }
 
 void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st) {
-    CBX_REQUIRE(p.rows >= 1 && p.rows <= 16, "gemv: rows must be in [1,16]");
+    CBX_REQUIRE(p.rows >= 1 && p.rows <= 32, "gemv: rows must be in [1,32]");
     CBX_REQUIRE(p.K % 16 == 0 && (p.K / 16) % nwarps == 0, "gemv: K/16 must divide by the warp count");
-    const int NT = p.rows <= 8 ? 1 : 2;
+    const int NT = p.rows <= 8 ? 1 : p.rows <= 16 ? 2 : 4;
     const int S = p.strips_per_cta;
     size_t smem = (size_t)8 * NT * (p.K + 8) * 2 + (size_t)(nwarps + 1) * S * 16 * 8 * NT * 4 + 2 * 8 * NT * 4;
+    if (NT == 4 && smem > 200 * 1024) {
+        // 32 staged rows of K = 4096 (the down projection) do not fit in shared memory: two passes of 16 rows.  The second
+        // pass finds the weights in L2 (8 MB against 126 MB), so HBM still streams them once.
+        CBX_REQUIRE(p.epi != GEMV_STORE || p.out, "gemv: split pass needs row-addressed outputs");
+        GemvParams a = p, b = p;
+        a.rows = 16; b.rows = p.rows - 16; b.row_map = p.row_map + 16;
+        launch_gemv(a, nwarps, st);
+        launch_gemv(b, nwarps, st);
+        return;
+    }
     int grid = cdiv(p.n_strips, S);
     ProfScope ps(PC_GEMV, (double)p.n_strips * 16 * p.K * 2 + (double)p.rows * (p.K + p.N) * 4, st);
     CBX_REQUIRE(smem <= 200 * 1024, "gemv: staging exceeds shared memory");
     if (NT == 1) launch_pdl(gemv_kernel<1>, dim3(grid), dim3(nwarps * 32), smem, st, p);
-    else launch_pdl(gemv_kernel<2>, dim3(grid), dim3(nwarps * 32), smem, st, p);
+    else if (NT == 2) launch_pdl(gemv_kernel<2>, dim3(grid), dim3(nwarps * 32), smem, st, p);
+    else launch_pdl(gemv_kernel<4>, dim3(grid), dim3(nwarps * 32), smem, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st) {

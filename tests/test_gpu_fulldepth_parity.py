@@ -60,7 +60,7 @@ def full():
     dev = torch.device("cuda", 0)
     cfg = ModelConfig()
     sd = bf16_round(random_state_dict(cfg, 0))
-    eng = NativeEngine(cfg, max_streams=8, n_lanes=1, max_text=512)
+    eng = NativeEngine(cfg, max_streams=16, n_lanes=1, max_text=512)
     eng.load_state_dict(sd)
     conds = synthetic_conditionals(cfg)              # trump.wav shapes: 194 prompt tokens, 388 mel frames
     conds["gen"]["prompt_feat"] = conds["gen"]["prompt_feat"].to(torch.bfloat16).float()
@@ -144,6 +144,12 @@ def test_t3_logits_one_stream_64_steps(full):
 def test_t3_logits_eight_streams_64_steps(full):
     """configs[2] shape: 8 streams = 16 rows in one batched pass, ragged text lengths."""
     _check_t3(full, [_text(60 + 12 * i, i) for i in range(8)], 64, "gemv_8streams")
+
+
+def test_t3_logits_sixteen_streams_one_pass(full):
+    """16 streams = 32 rows decode in ONE pass over the weights (the 32-row GEMV instance; the down projection as two
+    16-row passes over L2-resident weights), ragged text lengths."""
+    _check_t3(full, [_text(40 + 9 * i, i + 5) for i in range(16)], 24, "gemv_16streams")
 
 
 def test_t3_logits_persistent_kernel(full):

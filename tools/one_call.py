@@ -20,7 +20,16 @@ conds = synthetic_conditionals(cfg)
 v = eng.voice_put("default", conds["t3"], conds["gen"])
 toks = [(i * 37) % 6561 for i in range(n)]
 text = [255] + [(7 * i) % 700 + 1 for i in range(145)] + [0]
-if what == "s3gen":
+if what == "s3batch":        # one batched call of B x n tokens (argv: s3batch n B)
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    calls = [(v, [(i * 37 + 11 * b) % 6561 for i in range(n)], None, 1 + b) for b in range(B)]
+    eng.s3gen_infer_batch(calls)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    eng.s3gen_infer_batch(calls)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+elif what == "s3gen":
     mel = eng.flow_infer(v, toks)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()

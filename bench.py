@@ -261,6 +261,37 @@ def t3_step_leg(eng, pk):
 
 
 # ------------------------------------------------------------------------------------------------ B200 leg
+def conditioning_leg(eng, with_cpu):
+    """configs[4]'s per-request extra: voice-cloning conditioning computed from a clip (reference prepare_conditionals :357-384) --
+    10 s of synthetic 24 kHz audio through the GPU encoders (host waveform in, host conditioning tensors out), median of 3; the
+    oracle port on the host cores beside it when the CPU baseline is on."""
+    import numpy as np
+    import torch
+    t = np.arange(24000 * 10) / 24000.0
+    rng = np.random.default_rng(0)
+    wav = (0.3 * np.sin(2 * np.pi * 170 * t) * np.clip(np.sin(2 * np.pi * 1.3 * t), 0, None) + 0.03 * rng.standard_normal(t.shape[0])).astype(np.float32)
+    enc = eng.conditioning_encoders()
+    ts = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        c = enc.prepare_conditionals(wav, 24000)
+        ts.append((time.time() - t0) * 1e3)
+    out = {"workload": "prepare_conditionals on a 10 s clip (24 kHz): mel, S3Tokenizer-v2, CAMPPlus, VoiceEncoder", "clip_s": 10.0,
+           "gpu_ms": statistics.median(ts[1:]), "prompt_tokens": int(c["gen"]["prompt_token"].shape[1]), "dtype": "f32"}
+    if with_cpu:
+        from oracle import cond as OC
+        from cbx_b200.config import ModelConfig
+        from cbx_b200.weights import random_state_dict
+        sd = random_state_dict(ModelConfig(), 0, parts=("cond",))
+        with torch.no_grad():
+            t0 = time.time()
+            OC.prepare_conditionals(sd, torch.from_numpy(wav))
+            out["cpu_port_ms"] = (time.time() - t0) * 1e3
+            out["cpu_cores"] = host_threads()
+    return out
+
+
 def run_b200(args):
     import ctypes as C
     import torch
@@ -278,7 +309,7 @@ def run_b200(args):
     sampling = SamplingDefaults(tokens_per_word=TOK_PER_WORD)
     # BASELINE.json configs: random-init Chatterbox weights (seed 0), passed explicitly -- the engine refuses to invent weights
     eng = TextToSpeechEngine(f"cuda:{local}", state_dict=random_state_dict(ModelConfig(), 0), concurrent_requests=int(os.environ.get("BENCH_CONCURRENT", "8")),
-                             sampling=sampling, seed=0)
+                             sampling=sampling, seed=0, encoder_state_dict=random_state_dict(ModelConfig(), 0, parts=("cond",)))
     lib = L.load()
 
     def barrier():
@@ -471,6 +502,8 @@ def run_b200(args):
             line["cpu_baseline"] = cpu
         if world == 1 and not args.no_concurrent:
             line["concurrent8"] = await concurrent_leg()
+        if world == 1:
+            line["conditioning"] = conditioning_leg(eng, cpu is not None)
         if mixed is not None:
             line["mixed_streams"] = mixed
         line["s3gen_batch_sizes"] = {str(k): int(v) for k, v in sorted(eng.s3gen.batches.items())}

@@ -27,7 +27,8 @@ from .config import ModelConfig
 from .weights import schema, random_state_dict
 
 MERGED = "cbx_b200.safetensors"
-UPSTREAM_T3, UPSTREAM_S3GEN, UPSTREAM_CONDS = "t3_cfg.safetensors", "s3gen.safetensors", "conds.pt"
+UPSTREAM_T3, UPSTREAM_S3GEN, UPSTREAM_CONDS, UPSTREAM_VE = "t3_cfg.safetensors", "s3gen.safetensors", "conds.pt", "ve.safetensors"
+COND_PREFIXES = ("tokenizer.", "speaker_encoder.", "ve.")
 
 
 class CheckpointError(RuntimeError):
@@ -113,14 +114,20 @@ def load_checkpoint(model_path: str, cfg: ModelConfig = None, seed: int = 0):
     from safetensors.torch import load_file
     merged = os.path.join(model_path or "", MERGED)
     if os.path.exists(merged):
-        return load_file(merged), None, "merged"
+        sd = load_file(merged)
+        enc = OrderedDict((k, v) for k, v in sd.items() if k.startswith(COND_PREFIXES))
+        return OrderedDict((k, v) for k, v in sd.items() if not k.startswith(COND_PREFIXES)), (enc or None), "merged"
     t3p, s3p = os.path.join(model_path or "", UPSTREAM_T3), os.path.join(model_path or "", UPSTREAM_S3GEN)
     if os.path.exists(t3p) and os.path.exists(s3p):
         sd, extra = convert_upstream(load_file(t3p), load_file(s3p), cfg)
+        vep = os.path.join(model_path or "", UPSTREAM_VE)
+        if os.path.exists(vep):          # VoiceEncoder state dict (lstm.*, proj.*): merged under "ve."
+            for k, v in load_file(vep).items():
+                extra["ve." + k] = v
         return sd, extra, "upstream"
     if os.environ.get("CBX_ALLOW_RANDOM_WEIGHTS", "0") == "1":
         warnings.warn(f"no checkpoint under {model_path!r}: using seeded RANDOM weights (CBX_ALLOW_RANDOM_WEIGHTS=1) -- the audio is noise")
-        return random_state_dict(cfg, seed), None, "random"
+        return random_state_dict(cfg, seed), random_state_dict(cfg, seed, parts=("cond",)), "random"
     raise CheckpointError(
         f"no checkpoint under MODEL_PATH={model_path!r}: expected {MERGED}, or the upstream {UPSTREAM_T3} + {UPSTREAM_S3GEN} "
         f"(reference: ChatterboxTTS.from_local, src/tts_streaming.py:252-258).  Benchmarks / tests pass a state dict explicitly; "

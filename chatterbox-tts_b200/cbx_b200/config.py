@@ -112,14 +112,38 @@ class HiFTConfig:
 
 
 @dataclass
+class CondConfig:
+    """Voice-conditioning encoders (reference src/tts_streaming.py:357-384; upstream S3TokenizerV2, CAMPPlus, VoiceEncoder)."""
+    tok_mels: int = 128
+    tok_dim: int = 1280
+    tok_heads: int = 20
+    tok_layers: int = 6
+    tok_fsmn_kernel: int = 31
+    xv_feat: int = 80
+    xv_dim: int = 192
+    xv_growth: int = 32
+    xv_init: int = 128
+    xv_blocks: tuple = ((12, 3, 1), (24, 3, 2), (16, 3, 2))    # (layers, kernel, dilation) of the three dense TDNN blocks
+    ve_mels: int = 40
+    ve_hidden: int = 256
+    ve_layers: int = 3
+    ve_embed: int = 256
+
+    @staticmethod
+    def tiny() -> "CondConfig":
+        return CondConfig(tok_layers=2, xv_blocks=((3, 3, 1), (4, 3, 2), (2, 3, 2)))
+
+
+@dataclass
 class ModelConfig:
     t3: T3Config = field(default_factory=T3Config)
     flow: FlowConfig = field(default_factory=FlowConfig)
     hift: HiFTConfig = field(default_factory=HiFTConfig)
+    cond: CondConfig = field(default_factory=CondConfig)
 
     @staticmethod
     def tiny() -> "ModelConfig":
-        return ModelConfig(t3=T3Config.tiny(), flow=FlowConfig.tiny(), hift=HiFTConfig())
+        return ModelConfig(t3=T3Config.tiny(), flow=FlowConfig.tiny(), hift=HiFTConfig(), cond=CondConfig.tiny())
 
     def to_dict(self):
         return asdict(self)

@@ -447,7 +447,7 @@ class TextToSpeechEngine:
 
     def __init__(self, device: str, cfg: ModelConfig = None, state_dict=None, concurrent_requests: int = None,
                  sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0, device_sink: bool = False,
-                 backend=None):
+                 backend=None, encoder_state_dict=None):
         """`backend` injects an object with NativeEngine's interface (host-logic tests only); the product path
         always builds a NativeEngine on `device` and refuses anything that is not cuda:N."""
         self.device = device
@@ -495,7 +495,8 @@ class TextToSpeechEngine:
         self.tokenizer = None
         self.seed = seed
         self.weights_source = None
-        self._encoder_sd = None
+        self._encoder_sd = encoder_state_dict     # tokenizer.* / speaker_encoder.* / ve.* (conditioning encoders), else from the checkpoint
+        self._cond, self._cond_lock = None, threading.Lock()
         self.device_sink = device_sink   # bench `value` leg: PCM stays in HBM, emit() receives sample counts
         self._seq = 0
         self._seq_lock = threading.Lock()
@@ -529,7 +530,9 @@ class TextToSpeechEngine:
             # merged file, or the upstream t3_cfg / s3gen files converted on the fly; a missing checkpoint is an ERROR as in
             # the reference (from_local, :252-258) unless CBX_ALLOW_RANDOM_WEIGHTS=1 (checkpoint.py)
             from .checkpoint import load_checkpoint
-            sd, self._encoder_sd, self.weights_source = load_checkpoint(model_path, self.cfg, self.seed)
+            sd, enc_sd, self.weights_source = load_checkpoint(model_path, self.cfg, self.seed)
+            if self._encoder_sd is None:
+                self._encoder_sd = enc_sd
         self.native.load_state_dict(sd)
         self._state_dict = None
         tj = os.path.join(model_path, "tokenizer.json")
@@ -575,25 +578,38 @@ class TextToSpeechEngine:
     def put_conditionals(self, voice_id: str, t3_cond: dict, gen: dict):
         self.voice_cache[voice_id] = self.native.voice_put(voice_id, t3_cond, gen)
 
+    def conditioning_encoders(self):
+        """The GPU conditioning encoders (S3Tokenizer-v2, CAMPPlus, VoiceEncoder, mel front ends), built on first use from the
+        checkpoint's `tokenizer.*` / `speaker_encoder.*` / `ve.*` tensors.  Raises when the checkpoint has none: a voice is
+        never invented."""
+        with self._cond_lock:
+            if self._cond is None:
+                if self._backend is not None:
+                    raise RuntimeError("prepare_conditionals needs the CUDA engine")
+                if not self._encoder_sd:
+                    raise RuntimeError("prepare_conditionals: the checkpoint holds no conditioning-encoder weights (tokenizer.*, speaker_encoder.*, "
+                                       "ve.*); pass them (encoder_state_dict=) or use put_conditionals() with tensors computed elsewhere")
+                from .conditioning import ConditioningEncoders
+                self._cond = ConditioningEncoders(self._encoder_sd, self.cfg.cond, device=self.gpu_id)
+                self._encoder_sd = None
+            return self._cond
+
     def prepare_conditionals(self, wav_fpath: str):
-        """Reference :357-384 runs the conditioning encoders (S3Tokenizer, CAMPPlus, VoiceEncoder, mel) on
-        the reference clip.  Those encoders are the next scope row; until they exist on the
-        GPU the clip only determines the *shapes*: 25 prompt tokens and 50 mel frames per second of the
-        first 10 s, contents seeded from the file name."""
-        from .weights import synthetic_conditionals
-        import zlib
-        import scipy.io.wavfile as wavfile
-        if self.weights_source in ("merged", "upstream"):
-            # a real checkpoint with seeded stand-in conditioning would silently speak in a random voice
-            raise RuntimeError("prepare_conditionals: the conditioning encoders (S3Tokenizer, CAMPPlus, VoiceEncoder) are not "
-                               "built yet (SURVEY 8f.1); with a real checkpoint use put_conditionals() with tensors computed upstream")
-        sr, data = wavfile.read(wav_fpath)
-        secs = min(data.shape[0] / float(sr), 10.0)
-        ntok = max(3, min(int(secs * 25), 250))
-        voice_id = Path(wav_fpath).name
-        c = synthetic_conditionals(self.cfg, seed=zlib.crc32(voice_id.encode()) & 0x7FFFFFFF, prompt_tokens=ntok)
-        c["t3"]["emotion_adv"] = float(os.environ.get("TTS_VOICE_EXAGGERATION_FACTOR", "0.5")) * torch.ones(1, 1, 1)
-        self.put_conditionals(voice_id, c["t3"], c["gen"])
+        """Reference :357-384: read the clip, run the conditioning encoders on it (24 kHz prompt mel, S3Tokenizer prompt tokens,
+        CAMPPlus x-vector, VoiceEncoder speaker embedding -- all on the GPU, cbx_b200/conditioning.py) and cache the result
+        under the file's base name."""
+        from .conditioning import load_wav
+        wav, sr = load_wav(wav_fpath)
+        if self._backend is not None and hasattr(self._backend, "prepare_conditionals"):
+            # host-logic tests only (injected fake backend): the fake supplies its own deterministic conditioning
+            c = self._backend.prepare_conditionals(wav, sr)
+            self.put_conditionals(Path(wav_fpath).name, c["t3"], c["gen"])
+            return
+        enc = self.conditioning_encoders()
+        with torch.cuda.device(self.gpu_id):
+            c = enc.prepare_conditionals(wav, sr, speech_cond_prompt_len=self.cfg.t3.speech_cond_prompt_len,
+                                         exaggeration=float(os.environ.get("TTS_VOICE_EXAGGERATION_FACTOR", "0.5")))
+        self.put_conditionals(Path(wav_fpath).name, c["t3"], c["gen"])
 
     # ------------------------------------------------------------------ helpers
     def _pinned_get(self):

@@ -20,6 +20,18 @@ class S3GenCall(C.Structure):
                 ("wav_out_d", C.c_void_p), ("source_out_d", C.c_void_p), ("mel_out_d", C.c_void_p), ("seed", C.c_uint64)]
 
 
+class SgemmArgs(C.Structure):
+    """cbx_sgemm_args of include/cbx_b200.h"""
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("a_bs", C.c_int64), ("kc", C.c_int), ("a_stride", C.c_int), ("a_dil", C.c_int), ("a_pad", C.c_int),
+                ("a_rows", C.c_int64), ("a_scale", C.c_void_p), ("a_shift", C.c_void_p), ("a_relu", C.c_int),
+                ("W", C.c_void_p), ("ldw", C.c_int64), ("w_bs", C.c_int64), ("w_trans", C.c_int),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("alpha", C.c_float),
+                ("bias", C.c_void_p), ("o_scale", C.c_void_p), ("o_shift", C.c_void_p), ("act", C.c_int),
+                ("mul", C.c_void_p), ("ldm", C.c_int64), ("mul_bs", C.c_int64), ("mul_div", C.c_int),
+                ("res", C.c_void_p), ("res2", C.c_void_p), ("ldr", C.c_int64), ("res_bs", C.c_int64),
+                ("C", C.c_void_p), ("ldc", C.c_int64), ("c_bs", C.c_int64)]
+
+
 # every exported symbol of include/cbx_b200.h: name -> (restype, argtypes)
 _P, _I, _F, _L, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 SIGNATURES = {
@@ -65,6 +77,20 @@ SIGNATURES = {
     "cbx_cfm_tail_launches": (C.c_longlong, []),
     "cbx_cfm_tail_trace": (_I, [_P]),
     "cbx_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "cbx_cond_sgemm": (_I, [C.POINTER(SgemmArgs), _P]),
+    "cbx_cond_frames_dft": (_I, [_P, _L, _I, _I, _I, _I, _P, _I, _F, _I, _I, _P, _I, _P]),
+    "cbx_cond_resample": (_I, [_P, _L, _P, _L, _I, _I, _P, _I, _I, _P]),
+    "cbx_cond_layernorm": (_I, [_P, _L, _P, _L, _I, _I, _P, _P, _F, _P]),
+    "cbx_cond_softmax": (_I, [_P, _L, _L, _I, _I, _I, _P]),
+    "cbx_cond_rotary": (_I, [_P, _L, _I, _I, _I, _F, _P]),
+    "cbx_cond_dwconv_add": (_I, [_P, _L, _P, _I, _P, _L, _I, _I, _P]),
+    "cbx_cond_fsq": (_I, [_P, _P, _I, _P]),
+    "cbx_cond_mel_log": (_I, [_P, _L, _I, _F, _P, _P]),
+    "cbx_cond_col_stats": (_I, [_P, _L, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "cbx_cond_l2norm_rows": (_I, [_P, _I, _I, _I, _P]),
+    "cbx_cond_mean_rows": (_I, [_P, _I, _I, _P, _P]),
+    "cbx_cond_conv2d": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "cbx_cond_lstm_layer": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -14,7 +14,7 @@ from collections import OrderedDict
 
 import torch
 
-from .config import ModelConfig, T3Config, FlowConfig, HiFTConfig
+from .config import ModelConfig, T3Config, FlowConfig, HiFTConfig, CondConfig
 
 # init kinds: ("w", fan_in, gain) normal(0, gain/sqrt(fan_in)); ("b",) small bias;
 # ("g",) norm gain 1+0.1n; ("n", std) normal; ("alpha",) positive snake alpha
@@ -200,6 +200,89 @@ def _hift_schema(c: HiFTConfig, S):
     S[m + "f0_predictor.classifier.bias"] = ((1,), ("n", 0.0))
 
 
+def _bn_schema(S, p, ch, affine=True):
+    if affine:
+        S[p + "weight"] = ((ch,), ("g",))
+        S[p + "bias"] = ((ch,), ("b",))
+    S[p + "running_mean"] = ((ch,), ("n", 0.1))
+    S[p + "running_var"] = ((ch,), ("var",))
+
+
+def _cond_schema(c: CondConfig, S):
+    """Upstream key names: `tokenizer.*` and `speaker_encoder.*` live in s3gen.safetensors, the VoiceEncoder in ve.safetensors
+    (merged here under `ve.`)."""
+    D = c.tok_dim
+    t = "tokenizer.encoder."
+    S[t + "conv1.weight"] = ((D, c.tok_mels, 3), ("w", 3 * c.tok_mels, 1.0))
+    S[t + "conv1.bias"] = ((D,), ("b",))
+    S[t + "conv2.weight"] = ((D, D, 3), ("w", 3 * D, 1.4))
+    S[t + "conv2.bias"] = ((D,), ("b",))
+    for i in range(c.tok_layers):
+        b = t + f"blocks.{i}."
+        for ln in ("attn_ln", "mlp_ln"):
+            S[b + ln + ".weight"] = ((D,), ("g",))
+            S[b + ln + ".bias"] = ((D,), ("b",))
+        for n in ("query", "key", "value", "out"):
+            S[b + f"attn.{n}.weight"] = ((D, D), ("w", D, 0.5 if n == "out" else 1.0))
+            if n != "key":
+                S[b + f"attn.{n}.bias"] = ((D,), ("b",))
+        S[b + "attn.fsmn_block.weight"] = ((D, 1, c.tok_fsmn_kernel), ("w", c.tok_fsmn_kernel, 0.5))
+        S[b + "mlp.0.weight"] = ((4 * D, D), ("w", D, 1.0))
+        S[b + "mlp.0.bias"] = ((4 * D,), ("b",))
+        S[b + "mlp.2.weight"] = ((D, 4 * D), ("w", 4 * D, 0.5))
+        S[b + "mlp.2.bias"] = ((D,), ("b",))
+    S["tokenizer.quantizer._codebook.project_down.weight"] = ((8, D), ("w", D, 1.5))
+    S["tokenizer.quantizer._codebook.project_down.bias"] = ((8,), ("b",))
+    h = "speaker_encoder.head."
+    S[h + "conv1.weight"] = ((32, 1, 3, 3), ("w", 9, 1.4))
+    _bn_schema(S, h + "bn1.", 32)
+    for layer in ("layer1", "layer2"):
+        for j in range(2):
+            r = h + f"{layer}.{j}."
+            S[r + "conv1.weight"] = ((32, 32, 3, 3), ("w", 288, 1.4))
+            _bn_schema(S, r + "bn1.", 32)
+            S[r + "conv2.weight"] = ((32, 32, 3, 3), ("w", 288, 1.0))
+            _bn_schema(S, r + "bn2.", 32)
+            if j == 0:
+                S[r + "shortcut.0.weight"] = ((32, 32, 1, 1), ("w", 32, 1.0))
+                _bn_schema(S, r + "shortcut.1.", 32)
+    S[h + "conv2.weight"] = ((32, 32, 3, 3), ("w", 288, 1.4))
+    _bn_schema(S, h + "bn2.", 32)
+    x = "speaker_encoder.xvector."
+    ch = c.xv_init
+    S[x + "tdnn.linear.weight"] = ((ch, 32 * (c.xv_feat // 8), 5), ("w", 5 * 32 * (c.xv_feat // 8), 1.4))
+    _bn_schema(S, x + "tdnn.nonlinear.batchnorm.", ch)
+    bn_ch = 4 * c.xv_growth
+    for bi, (n_layers, k, _dil) in enumerate(c.xv_blocks):
+        for li in range(n_layers):
+            l = x + f"block{bi + 1}.tdnnd{li + 1}."
+            cin = ch + li * c.xv_growth
+            _bn_schema(S, l + "nonlinear1.batchnorm.", cin)
+            S[l + "linear1.weight"] = ((bn_ch, cin, 1), ("w", cin, 1.4))
+            _bn_schema(S, l + "nonlinear2.batchnorm.", bn_ch)
+            S[l + "cam_layer.linear_local.weight"] = ((c.xv_growth, bn_ch, k), ("w", k * bn_ch, 1.4))
+            S[l + "cam_layer.linear1.weight"] = ((bn_ch // 2, bn_ch, 1), ("w", bn_ch, 1.4))
+            S[l + "cam_layer.linear1.bias"] = ((bn_ch // 2,), ("b",))
+            S[l + "cam_layer.linear2.weight"] = ((c.xv_growth, bn_ch // 2, 1), ("w", bn_ch // 2, 1.4))
+            S[l + "cam_layer.linear2.bias"] = ((c.xv_growth,), ("b",))
+        ch += n_layers * c.xv_growth
+        _bn_schema(S, x + f"transit{bi + 1}.nonlinear.batchnorm.", ch)
+        S[x + f"transit{bi + 1}.linear.weight"] = ((ch // 2, ch, 1), ("w", ch, 1.4))
+        ch //= 2
+    _bn_schema(S, x + "out_nonlinear.batchnorm.", ch)
+    S[x + "dense.linear.weight"] = ((c.xv_dim, 2 * ch, 1), ("w", 2 * ch, 1.0))
+    _bn_schema(S, x + "dense.nonlinear.batchnorm.", c.xv_dim, affine=False)
+    H = c.ve_hidden
+    for l in range(c.ve_layers):
+        I = c.ve_mels if l == 0 else H
+        S[f"ve.lstm.weight_ih_l{l}"] = ((4 * H, I), ("w", I, 1.0))
+        S[f"ve.lstm.weight_hh_l{l}"] = ((4 * H, H), ("w", H, 1.0))
+        S[f"ve.lstm.bias_ih_l{l}"] = ((4 * H,), ("b",))
+        S[f"ve.lstm.bias_hh_l{l}"] = ((4 * H,), ("b",))
+    S["ve.proj.weight"] = ((c.ve_embed, H), ("w", H, 1.0))
+    S["ve.proj.bias"] = ((c.ve_embed,), ("b",))
+
+
 def schema(cfg: ModelConfig, parts=("t3", "flow", "hift")) -> "OrderedDict[str, tuple]":
     """name -> (shape, init) for every tensor the hot path reads."""
     S = OrderedDict()
@@ -209,6 +292,8 @@ def schema(cfg: ModelConfig, parts=("t3", "flow", "hift")) -> "OrderedDict[str, 
         _flow_schema(cfg.flow, S)
     if "hift" in parts:
         _hift_schema(cfg.hift, S)
+    if "cond" in parts:
+        _cond_schema(cfg.cond, S)
     return S
 
 
@@ -224,6 +309,8 @@ def _draw(name, shape, init, seed):
         return torch.randn(shape, generator=g) * 0.02
     if kind == "g":
         return 1.0 + 0.1 * torch.randn(shape, generator=g)
+    if kind == "var":
+        return 0.5 + torch.rand(shape, generator=g)
     if kind == "alpha":
         return (1.0 + 0.2 * torch.randn(shape, generator=g)).abs() + 0.1
     raise ValueError(kind)

@@ -33,6 +33,7 @@ class Backend:
         self.weights_source, self.encoder_sd = "injected", None
         if _factory is not None:
             self.native = _factory(ckpt_dir, device)
+            self.encoder_sd = getattr(self.native, "encoder_sd", None)      # tests may hang conditioning-encoder weights on the injected engine
         else:
             if "cuda" not in str(device):
                 raise RuntimeError("the B200-native chatterbox shim needs a cuda:N device; there is no CPU fallback")
@@ -71,12 +72,19 @@ class Backend:
             return slot
 
 
-    def require_synthetic(self, what: str):
-        """The conditioning encoders are seeded stand-ins: fine on random-init weights, an error on a real
-        checkpoint, where they would silently produce a random voice."""
-        if self.weights_source in ("merged", "upstream"):
-            raise RuntimeError(f"{what}: the conditioning encoders are not built on the B200 path yet (SURVEY 8f.1); "
-                               "with a real checkpoint pass conditioning tensors computed upstream")
+    def encoders(self, what: str):
+        """The GPU conditioning encoders (cbx_b200/conditioning.py), built on first use from the checkpoint's tokenizer.* /
+        speaker_encoder.* / ve.* tensors.  A checkpoint without them is an error: a voice is never invented."""
+        with self.lock:
+            if getattr(self, "_enc", None) is None:
+                if _factory is not None and not self.encoder_sd:
+                    raise RuntimeError(f"{what}: the injected test backend has no conditioning-encoder weights")
+                if not self.encoder_sd:
+                    raise RuntimeError(f"{what}: the checkpoint holds no conditioning-encoder weights (tokenizer.*, speaker_encoder.*, ve.*)")
+                from cbx_b200.conditioning import ConditioningEncoders
+                gpu = int(str(self.device).split(":")[-1]) if ":" in str(self.device) else 0
+                self._enc = ConditioningEncoders(self.encoder_sd, self.cfg.cond, device=gpu)
+            return self._enc
 
 
 def new_key(prefix: str) -> str:

@@ -2,23 +2,21 @@
 import numpy as np
 import torch
 
-from ..._backend import seed_of
-
 
 class VoiceEncoder(torch.nn.Module):
-    """Speaker embedding (k, 256), L2-normalised.  Seeded from the clip until the encoder of SURVEY 8f.1 exists on the GPU."""
+    """Speaker embedding (k, 256), L2-normalised: 40-mel partials through the 3 x LSTM-256 on the GPU (cbx_b200/conditioning.py)."""
 
     def __init__(self, backend=None):
         super().__init__()
         self._b = backend
 
     def embeds_from_wavs(self, wavs, sample_rate=16000, as_spk=False, **kw):
-        if self._b is not None:
-            self._b.require_synthetic("ve.embeds_from_wavs")
+        if self._b is None:
+            raise RuntimeError("VoiceEncoder needs the engine backend (ChatterboxTTS.from_local builds it)")
+        enc = self._b.encoders("ve.embeds_from_wavs")
         out = []
         for w in wavs:
-            w = np.asarray(w, dtype=np.float32).reshape(-1)
-            g = torch.Generator().manual_seed(seed_of(w[:4000], [len(w)]))
-            e = torch.randn(256, generator=g)
-            out.append((e / e.norm()).numpy())
+            w = np.asarray(w.detach().cpu().numpy() if torch.is_tensor(w) else w, dtype=np.float32).reshape(-1)
+            x = enc.resample(enc._dev_wave(w), int(sample_rate), 16000)
+            out.append(enc.voice_embed(x.contiguous()).cpu().numpy())
         return np.stack(out).astype(np.float32)

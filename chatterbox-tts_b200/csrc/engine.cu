@@ -18,6 +18,8 @@ static thread_local std::string g_err;
         return 1;                                    \
     }
 
+void cbx_set_error(const char* msg) { g_err = msg ? msg : ""; }     // other translation units of the C-ABI (cond.cu)
+
 namespace {
 
 struct StreamBridge {   // order engine-internal stream `in` after the caller's stream and back

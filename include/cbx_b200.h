@@ -119,6 +119,58 @@ int cbx_hift_source(cbx_engine* e, const float* f0_d, int frames, const float* p
 int cbx_crossfade_pcm(cbx_engine* e, const float* cur_d, int64_t n_out, const float* prev_tail_d, int fade_len,
                       const float* fade_in_d, const float* fade_out_d, int16_t* out_d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Voice-conditioning encoders (reference src/tts_streaming.py:357-384: `s3gen.embed_ref` :366, `s3gen.tokenizer.forward`
+ * :370-372, `ve.embeds_from_wavs` :374).  fp32 building blocks on device pointers (time-major, channels-last); the host
+ * side (cbx_b200/conditioning.py) strings them together as the upstream modules do.  All take the caller's stream.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cbx_sgemm_args {
+    /* C[b][m][n] = epilogue(alpha * sum_kk A'(b,m,kk) * W(b,n,kk)), kk = tap * kc + c:
+     *   A'(b,m,kk) = in(A[b*a_bs + t*lda + c]) with t = m*a_stride + tap*a_dil - a_pad (0 outside [0, a_rows));
+     *   in(v) = relu?(v * a_scale[c] + a_shift[c]) when a_scale is given (BatchNorm + ReLU in front of a conv);
+     *   W(b,n,kk) = W[b*w_bs + n*ldw + kk], or W[b*w_bs + kk*ldw + n] when w_trans;
+     *   epilogue: + bias[n]; * o_scale[n] + o_shift[n]; act (0 none, 1 relu, 2 erf-gelu, 3 sigmoid, 4 tanh);
+     *             * mul[b*mul_bs + (m / mul_div)*ldm + n]; + res[b*res_bs + m*ldr + n] (+ res2, same strides). */
+    const float* A; int64_t lda; int64_t a_bs; int kc; int a_stride; int a_dil; int a_pad; int64_t a_rows;
+    const float* a_scale; const float* a_shift; int a_relu;
+    const float* W; int64_t ldw; int64_t w_bs; int w_trans;
+    int M, N, K, batch;
+    float alpha;
+    const float* bias; const float* o_scale; const float* o_shift; int act;
+    const float* mul; int64_t ldm; int64_t mul_bs; int mul_div;
+    const float* res; const float* res2; int64_t ldr; int64_t res_bs;
+    float* C; int64_t ldc; int64_t c_bs;
+} cbx_sgemm_args;
+int cbx_cond_sgemm(const cbx_sgemm_args* a, void* stream);
+/* framing + window + |DFT| by direct summation: frame f = samples f*hop - pad .. (+ frame_len), reflected at the clip edges;
+ * remove_dc / preemph: Kaldi's per-frame mean removal and pre-emphasis; mode 0 magnitude, 1 power, 2 sqrt(power + 1e-9);
+ * out[f*ld_out + bin], bins = n_fft/2 + 1 */
+int cbx_cond_frames_dft(const float* wav, int64_t n, int n_fft, int hop, int pad, int frame_len, const float* window, int remove_dc, float preemph,
+                        int mode, int n_frames, float* out, int ld_out, void* stream);
+/* polyphase windowed-sinc resampler (torchaudio.functional.resample): kern [up][klen] */
+int cbx_cond_resample(const float* x, int64_t n_in, float* y, int64_t n_out, int down, int up, const float* kern, int klen, int width, void* stream);
+int cbx_cond_layernorm(const float* x, int64_t ld_in, float* y, int64_t ld_out, int rows, int C, const float* g, const float* b, float eps, void* stream);
+int cbx_cond_softmax(float* x, int64_t ld, int64_t bs, int rows, int cols, int batch, void* stream);
+/* rotate-half rotary embedding (theta 10000, angles repeated over both halves) in place on [T][H][hd], then * scale */
+int cbx_cond_rotary(float* x, int64_t ld, int T, int H, int hd, float scale, void* stream);
+/* y = x + depthwise_conv_k(x) along time (zero padding (k-1)/2): the FSMN memory block of S3Tokenizer-v2 */
+int cbx_cond_dwconv_add(const float* x, int64_t ld, const float* w, int k, float* y, int64_t ld_out, int T, int C, void* stream);
+/* FSQ codebook of S3Tokenizer-v2: h [T][8] -> tanh * 0.999 -> round -> + 1 -> base-3 digits -> ids in [0, 6561) */
+int cbx_cond_fsq(const float* h, int* out, int T, void* stream);
+/* mode 0: x = log(max(x, floor_v)); mode 1: whisper log-mel (log10, clip to global max - 8, (x + 4) / 4; scratch1 = 1 float) */
+int cbx_cond_mel_log(float* x, int64_t n, int mode, float floor_v, float* scratch1, void* stream);
+/* per-column statistics over time of [T][C]: mode 0 subtract the mean in place; 1: out = [mean | unbiased std] of
+ * relu(x*a_scale + a_shift) (statistics pooling); 2: out = mean, seg_out[i][c] = mean of segment i (seg frames) + mean */
+int cbx_cond_col_stats(float* x, int64_t ld, int T, int C, int mode, const float* a_scale, const float* a_shift, float* out, int seg, float* seg_out, void* stream);
+int cbx_cond_l2norm_rows(float* x, int rows, int C, int relu, void* stream);
+int cbx_cond_mean_rows(const float* x, int rows, int C, float* out, void* stream);
+/* 3x3 (pad 1) / 1x1 conv2d over [Cin][F][T], stride (stride_f, 1), folded BatchNorm, optional residual and ReLU; t_major
+ * writes [T][Cout * F'] (CAMPPlus FCM head -> TDNN) */
+int cbx_cond_conv2d(const float* x, const float* w, const float* scale, const float* shift, const float* res, float* y, int Cin, int Cout, int F, int T,
+                    int ks, int stride_f, int relu, int t_major, void* stream);
+/* one LSTM layer over B sequences: xp [B][T][4H] = x W_ih^T + b_ih + b_hh, w_hh_t [H][4H]; h_seq [B][T][H] and / or h_last [B][H] */
+int cbx_cond_lstm_layer(const float* xp, const float* w_hh_t, float* h_seq, float* h_last, int B, int T, int H, void* stream);
+
 /* counters for bench.py: kernels launched by this library since engine creation */
 int64_t cbx_gpu_launches(cbx_engine* e);
 /* GEMM launches that took the tcgen05/TMA path (process-wide; 0 means the mma.sync fallback served everything) */

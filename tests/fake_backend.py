@@ -87,6 +87,18 @@ class FakeNative:
     def voice_put(self, key, t3, gen):
         return 0
 
+    def prepare_conditionals(self, wav, sr):
+        """Deterministic stand-in conditioning of the right shapes (host-logic tests only: the real encoders are CUDA kernels,
+        tests/test_gpu_conditioning.py)."""
+        import numpy as np
+        n = max(3, min(int(len(wav) / float(sr) * 25), 250))
+        g = torch.Generator().manual_seed(int(np.abs(np.asarray(wav[:4000], dtype=np.float64)).sum() * 1e3) & 0x7FFFFFFF)
+        spk = torch.randn(1, 256, generator=g)
+        return {"t3": {"speaker_emb": spk / spk.norm(), "cond_prompt_speech_tokens": torch.randint(0, 6561, (1, min(n, 150)), generator=g),
+                       "emotion_adv": 0.5 * torch.ones(1, 1, 1)},
+                "gen": {"prompt_token": torch.randint(0, 6561, (1, n), generator=g), "prompt_token_len": torch.tensor([n]),
+                        "prompt_feat": torch.randn(1, 2 * n, 80, generator=g), "prompt_feat_len": None, "embedding": torch.randn(1, 192, generator=g)}}
+
     def voice_drop(self, key):
         pass
 

@@ -93,14 +93,14 @@ def test_unmodified_reference_engine_runs_on_the_shim(ref_engine_module, tmp_pat
         for name in ("full_fade30", "zero_fade30", "trims_slice20", "long_eos"):
             sc = next(s for s in SCENARIOS if s["name"] == name)
             res[name] = await _collect(M, eng, sc, scenario_text(sc["words"]))
-        # voice conditioning through the shim's embed_ref / tokenizer / voice encoder (reference prepare_conditionals :357-384)
+        # voice conditioning (reference prepare_conditionals :357-384) runs the GPU encoders behind embed_ref / tokenizer.forward /
+        # embeds_from_wavs: on this CPU-only fake backend it must fail loudly, never invent a voice (GPU: tests/test_gpu_shim.py)
         import scipy.io.wavfile as wavfile
         wav = tmp_path / "bob.wav"
         wavfile.write(str(wav), 24000, (np.sin(np.arange(24000 * 3) * 0.03) * 9000).astype(np.int16))
-        eng.prepare_conditionals(str(wav))
-        c = eng.voice_cache["bob.wav"]
-        assert c.t3.speaker_emb.shape == (1, 256) and c.t3.cond_prompt_speech_tokens.shape[0] == 1 and c.gen["prompt_feat"].shape[-1] == 80
-        assert c.gen["prompt_feat"].shape[1] == 2 * c.gen["prompt_token"].shape[1]
+        with pytest.raises(RuntimeError, match="conditioning-encoder weights"):
+            eng.prepare_conditionals(str(wav))
+        assert "bob.wav" not in eng.voice_cache
         return res
 
     res = asyncio.run(run())

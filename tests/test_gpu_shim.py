@@ -21,6 +21,7 @@ def test_shim_over_native_engine(tiny_cfg):
     def factory(ckpt, device):
         eng = NativeEngine(tiny_cfg, max_streams=4, max_s3_tokens=200, n_lanes=1, n_voices=8)
         eng.load_state_dict(bf16_round(random_state_dict(tiny_cfg, 0)))
+        eng.encoder_sd = random_state_dict(tiny_cfg, 0, parts=("cond",))
         return eng
 
     chatterbox.set_backend_factory(factory)
@@ -53,6 +54,20 @@ def test_shim_over_native_engine(tiny_cfg):
         wav2, src2 = tts.s3gen.inference(speech_tokens=sp, ref_dict=conds.gen, cache_source=src)
         torch.cuda.synchronize()
         assert torch.equal(src2, src) and torch.allclose(wav2, wav, atol=1e-6)
+        # the three conditioning call sites of prepare_conditionals (:366, :370-372, :374) run the GPU encoders and agree with the oracle
+        from oracle import cond as OC
+        enc_sd = nat.encoder_sd
+        tw = torch.arange(24000 * 3) / 24000.0
+        w24 = (0.3 * torch.sin(2 * np.pi * 200 * tw) * torch.clamp(torch.sin(2 * np.pi * 2 * tw), min=0) + 0.02 * torch.randn(tw.shape[0], generator=torch.Generator().manual_seed(1))).float()
+        w16 = OC.resample(w24, 24000, 16000)
+        ref = tts.s3gen.embed_ref(w24.numpy(), 24000, device="cuda:0")
+        oref = OC.embed_ref(enc_sd, w24)
+        assert ref["prompt_feat"].shape == (1, 150, 80) and torch.equal(ref["prompt_token"][0], oref["prompt_token"])
+        assert float((ref["embedding"][0] - oref["embedding"]).norm() / oref["embedding"].norm()) < 2e-4
+        tk, ln = tts.s3gen.tokenizer.forward([w16.numpy()[: 6 * 16000]], max_len=150)
+        assert int(ln[0]) == tk.shape[1] == 75 and torch.equal(tk[0], OC.s3_tokens_from_wav(enc_sd, w16[: 6 * 16000], max_len=150))
+        ve = tts.ve.embeds_from_wavs([w16.numpy()], sample_rate=16000)
+        assert ve.shape == (1, 256) and float(np.linalg.norm(ve[0] - OC.voice_embed(enc_sd, w16).numpy())) < 2e-4
         # an abandoned generator gives its KV pages back
         gen = tts.t3.inference_stream(t3_cond=conds.t3, text_tokens=text2, max_new_tokens=50)
         next(gen)

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libcbx_b200.so")
-SOURCES = ["engine.cu", "t3.cu", "flow.cu", "hift.cu", "gemm.cu", "attention.cu", "norm_act.cu", "t3_kernels.cu", "hift_kernels.cu", "profiler.cu", "gemm_tc.cu", "t3_mega.cu", "attention_tc.cu", "cfm_tail.cu", "attention_fa.cu", "cond.cu"]
+SOURCES = ["engine.cu", "t3.cu", "flow.cu", "hift.cu", "gemm.cu", "attention.cu", "norm_act.cu", "t3_kernels.cu", "hift_kernels.cu", "profiler.cu", "gemm_tc.cu", "t3_mega.cu", "attention_tc.cu", "cfm_tail.cu", "attention_fa.cu", "cond.cu", "t3_gemv_tc.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "cbx_attn_tc_launches": (C.c_longlong, []),
     "cbx_attn_fa_launches": (C.c_longlong, []),
     "cbx_attn_fa_trace": (_I, [_P]),
+    "cbx_t3_tc_launches": (C.c_longlong, []),
     "cbx_gemm_tc_trace": (_I, [_P]),
     "cbx_t3_mega_trace": (_I, [_P]),
     "cbx_t3_mega_prof": (_I, [_P]),

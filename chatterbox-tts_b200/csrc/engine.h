@@ -29,7 +29,10 @@ constexpr int H_BASE = 512, H_NSRC = 18, H_NSRC_PAD = 24, H_HALO = 32, H_UP = 48
 struct Lin { bf16* w = nullptr; float* b = nullptr; int N = 0, K = 0; };
 struct LNp { float* g = nullptr; float* b = nullptr; };
 
-struct T3Layer { float *ln1, *ln2; bf16 *wqkv, *wo, *wgu, *wd; bf16 *wqkv_f, *wo_f, *wgu_f, *wd_f; };
+struct T3Layer {
+    float *ln1, *ln2; bf16 *wqkv, *wo, *wgu, *wd; bf16 *wqkv_f, *wo_f, *wgu_f, *wd_f;
+    alignas(64) unsigned char tm_qkv[128], tm_o[128], tm_gu[128], tm_d[128];     // TMA descriptors of the row-major weights (batched decode on tcgen05)
+};
 struct T3Model {
     float *text_emb, *speech_emb, *text_pos, *speech_pos, *final_norm, *inv_freq;
     bf16* head_f;

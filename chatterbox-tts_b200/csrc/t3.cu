@@ -104,6 +104,11 @@ void t3_alloc(cbx_engine* e) {
     // otherwise share the GPU with T3 on other streams have to wait (measured on the pipelined 200-word paragraph: 3.64 s
     // vs 3.17 s), and with 16 rows the GEMV kernels are faster (1.55 ms vs 2.35 ms).  See DESIGN.md section 6.
     m.mega_ok = t3_mega_init(m.max_pages, hl, m.head_f, T3_VPAD / 16, &m.mega_state);
+    if (gemv_tc_available())
+        for (auto& l : m.layers) {
+            gemv_tc_weight_map(l.tm_qkv, l.wqkv, 3 * T3_D, T3_D); gemv_tc_weight_map(l.tm_o, l.wo, T3_D, T3_D);
+            gemv_tc_weight_map(l.tm_gu, l.wgu, 2 * T3_FFN, T3_D); gemv_tc_weight_map(l.tm_d, l.wd, T3_D, T3_FFN);
+        }
     const char* en = getenv("CBX_T3_MEGA");
     m.mega = m.mega_ok && en && en[0] == '1';
 }
@@ -250,6 +255,13 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
     // of squares, the consuming projection scales its outputs by the row's RMS factor.  Layer 0 reads the fp32 row the
     // sampler wrote.
     static const int gu_strips = [] { const char* v = getenv("CBX_T3_GU_STRIPS"); return v ? atoi(v) : 2; }();
+    // batched rows: the projections run on tcgen05 (swap-AB: weight tile = M operand, rows = N), one wave of <= 128 CTAs each
+    static const int tc_min_rows = [] { const char* v = getenv("CBX_T3_TC_MIN_ROWS"); return v ? atoi(v) : 17; }();
+    const bool tc = gemv_tc_available() && rows >= tc_min_rows;
+    auto gemv = [&](const GemvParams& g, const unsigned char (&map)[128], int nwarps) {
+        if (tc && g.xb && launch_gemv_tc(g, map, st)) return;
+        launch_gemv(g, nwarps, st);
+    };
     const int n_layers = e->cfg.t3_layers;
     for (int li = 0; li < n_layers; li++) {
         const T3Layer& l = m.layers[li];
@@ -257,22 +269,22 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         q.row_map = m.d_rowmap; q.rows = rows; q.eps = 1e-5f; q.out = m.qkv; q.ld_out = 3 * T3_D; q.epi = GEMV_STORE;
         if (li == 0) { q.x = m.x; q.ldx_in = T3_D; q.gain = l.ln1; }
         else { q.xb = m.xb; q.ldxb = T3_D; q.ss_in = m.ss; q.n_ss = T3_D / 16; }
-        launch_gemv(q, 8, st);
+        gemv(q, l.tm_qkv, 8);
         DecodeAttnParams a; a.qkv = m.qkv; a.out_b = m.attn_b; a.kv = m.kv + li * m.kv_layer_stride; a.kv_half = m.kv_half; a.page_table = m.page_table;
         a.max_pages = m.max_pages; a.slot_pos = m.slot_pos; a.row_map = m.d_rowmap; a.inv_freq = m.inv_freq; a.H = T3_H;
         launch_decode_attn(a, rows, e->cfg.max_seq, st);
         GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.xb = m.attn_b; o.ldxb = T3_D;
         o.row_map = m.d_rowmap; o.rows = rows; o.out = m.x; o.ld_out = T3_D; o.epi = GEMV_RESID;
         o.out_b = m.xb; o.ld_out_b = T3_D; o.next_gain = l.ln2; o.ss_out = m.ss;
-        launch_gemv(o, 16, st);
+        gemv(o, l.tm_o, 16);
         GemvParams gu; gu.Wf = l.wgu_f; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.n_strips = 2 * T3_FFN / 16; gu.strips_per_cta = gu_strips;
         gu.xb = m.xb; gu.ldxb = T3_D; gu.ss_in = m.ss; gu.n_ss = T3_D / 16;
         gu.row_map = m.d_rowmap; gu.rows = rows; gu.eps = 1e-5f; gu.out_b = m.act_b; gu.ld_out_b = T3_FFN; gu.epi = GEMV_GLU;
-        launch_gemv(gu, 8, st);
+        gemv(gu, l.tm_gu, 8);
         GemvParams d; d.Wf = l.wd_f; d.N = T3_D; d.K = T3_FFN; d.n_strips = T3_D / 16; d.strips_per_cta = 1; d.xb = m.act_b; d.ldxb = T3_FFN;
         d.row_map = m.d_rowmap; d.rows = rows; d.out = m.x; d.ld_out = T3_D; d.epi = GEMV_RESID;
         d.out_b = m.xb; d.ld_out_b = T3_D; d.next_gain = li + 1 < n_layers ? m.layers[li + 1].ln1 : m.final_norm; d.ss_out = m.ss;
-        launch_gemv(d, 16, st);
+        gemv(d, l.tm_d, 16);
     }
     static const int head_strips = [] { const char* v = getenv("CBX_T3_HEAD_STRIPS"); return v ? atoi(v) : 1; }();
     GemvParams h; h.Wf = m.head_f; h.N = T3_V; h.K = T3_D; h.n_strips = T3_VPAD / 16; h.strips_per_cta = head_strips;

@@ -577,6 +577,7 @@ __global__ void scale_vec_kernel(float* out, const float* __restrict__ w, float 
 }  // namespace
 
 void t3_kernels_init() {
+    gemv_tc_init();
     CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CBX_CHECK(cudaFuncSetAttribute(gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

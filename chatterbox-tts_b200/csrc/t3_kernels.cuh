@@ -20,6 +20,11 @@ struct GemvParams {
     float* ss_out = nullptr;                      // RESID: [rows_total][n_strips] sum of squares of this strip's 16 new values
 };
 void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st);
+// tcgen05 form for batched rows (t3_gemv_tc.cu): row-major weights through a TMA descriptor built once per weight
+void gemv_tc_init();
+bool gemv_tc_available();
+void gemv_tc_weight_map(unsigned char (&map)[128], const bf16* w, int N, int K);
+bool launch_gemv_tc(const GemvParams& p, const unsigned char (&map)[128], cudaStream_t st);
 
 struct T3SlotState {   // device-resident per-stream decode state
     int pos;        // KV length (positions already cached) of both rows

@@ -181,6 +181,8 @@ long long cbx_attn_tc_launches(void);
 long long cbx_attn_fa_launches(void);
 /* debug (CBX_ATTN_FA_DBG=4): %globaltimer stamps of the first CTA of the last launch (MMA issuer and softmax row 0 per key block) */
 int cbx_attn_fa_trace(unsigned long long* out_h);
+/* T3 decode projections launched on the tcgen05 path (batched rows, t3_gemv_tc.cu; process-wide) */
+long long cbx_t3_tc_launches(void);
 /* debug: %globaltimer stamps (ns) of the last tcgen05 GEMM's CTA 0: start, setup done, first TMA landed, MMAs issued,
  * accumulator ready, epilogue done, teardown */
 int cbx_gemm_tc_trace(unsigned long long* out_h);

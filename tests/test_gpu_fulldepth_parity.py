@@ -149,7 +149,12 @@ def test_t3_logits_eight_streams_64_steps(full):
 def test_t3_logits_sixteen_streams_one_pass(full):
     """16 streams = 32 rows decode in ONE pass over the weights (the 32-row GEMV instance; the down projection as two
     16-row passes over L2-resident weights), ragged text lengths."""
+    from cbx_b200 import lib as L
+    lib = L.load()
+    before = lib.cbx_t3_tc_launches()
     _check_t3(full, [_text(40 + 9 * i, i + 5) for i in range(16)], 24, "gemv_16streams")
+    # batched rows take the tcgen05 projections (swap-AB, t3_gemv_tc.cu): every layer but the first QKV, every step
+    assert lib.cbx_t3_tc_launches() - before >= 24 * (4 * 30 - 1)
 
 
 def test_t3_logits_persistent_kernel(full):

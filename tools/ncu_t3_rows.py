@@ -14,7 +14,7 @@ from cbx_b200.weights import random_state_dict, synthetic_conditionals
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cfg = ModelConfig()
-eng = NativeEngine(cfg, max_streams=8, n_lanes=1)
+eng = NativeEngine(cfg, max_streams=max(8, n), n_lanes=1)
 eng.load_state_dict(random_state_dict(cfg, 0))
 conds = synthetic_conditionals(cfg)
 v = eng.voice_put("default", conds["t3"], conds["gen"])

@@ -78,6 +78,7 @@ SIGNATURES = {
     "cbx_cfm_tail_launches": (C.c_longlong, []),
     "cbx_cfm_tail_trace": (_I, [_P]),
     "cbx_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "cbx_op_attention_bias": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "cbx_cond_sgemm": (_I, [C.POINTER(SgemmArgs), _P]),
     "cbx_cond_frames_dft": (_I, [_P, _L, _I, _I, _I, _I, _P, _I, _F, _I, _I, _P, _I, _P]),
     "cbx_cond_resample": (_I, [_P, _L, _P, _L, _I, _I, _P, _I, _I, _P]),

@@ -117,6 +117,7 @@ struct AttnFaArgs {
     bf16* o; long ldo, o_bs;
     int T, H, causal; float sl2;   // sl2 = scale * log2(e): scores are kept in the log2 domain
     int kv_len[16]; int kv_div; int dbg;
+    const float* relbias; long rb_ld, rb_hs, rb_bs;      // additive score bias (ESPnet relative position): bias[b][h][i][T - 1 - i + j]
 };
 
 __global__ void __launch_bounds__(THREADS, 1) attn_fa_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -233,6 +234,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fa_kernel(const __grid_consta
                 mbar_arrive(s_free + 8 * g);                                              // the tensor core may overwrite S_g
                 FA_TRACE(j < 8 && qr == 0, 128 + (j * 2 + g) * 4 + 2);
                 const int kbase = j * BK;
+                if (p.relbias && qi < p.T) {          // rel-pos term (q + v) P^T, rel-shifted by the index: consecutive keys are consecutive floats
+                    const float* br = p.relbias + (long)b * p.rb_bs + (long)h * p.rb_hs + (long)qi * p.rb_ld + (p.T - 1 - qi + kbase);
+                    const int nk = min(BK, Tk - kbase);
+#pragma unroll
+                    for (int i = 0; i < 128; i++) if (i < nk) s[i] += __ldg(br + i);
+                }
                 const bool masked = kbase + BK > Tk || (p.causal && kbase + BK - 1 > q0 + g * BQ);      // block with masked keys (CTA-group-uniform)
                 if (masked) {
                     const int lim = p.causal ? min(Tk, qi + 1) : Tk;                      // keys < lim are visible to this row
@@ -351,9 +358,9 @@ void attention_fa_init() {
     g_ok = true;
 }
 
-// returns false when the problem does not fit this kernel (additive bias / alignment): the caller falls back to the older kernels
+// returns false when the problem does not fit this kernel (alignment): the caller falls back to the older kernels
 bool launch_attention_fa(const AttnParams& p, cudaStream_t st) {
-    if (!g_ok || p.relbias) return false;
+    if (!g_ok) return false;
     if (p.ldq % 8 || p.ldk % 8 || p.ldv % 8 || p.q_bs % 8 || p.k_bs % 8 || p.v_bs % 8 || p.ldo % 8 || p.o_bs % 8) return false;
     if (((uintptr_t)p.q & 15) || ((uintptr_t)p.k & 15) || ((uintptr_t)p.v & 15) || ((uintptr_t)p.o & 15)) return false;
     alignas(64) CUtensorMap tq, tk, tv;
@@ -363,6 +370,7 @@ bool launch_attention_fa(const AttnParams& p, cudaStream_t st) {
     a.o = p.o; a.ldo = p.ldo; a.o_bs = p.o_bs; a.T = p.T; a.H = p.H; a.causal = p.causal; a.sl2 = p.scale * 1.4426950408889634f;
     for (int i = 0; i < 16; i++) a.kv_len[i] = p.kv_len[i];
     a.kv_div = p.kv_div;
+    a.relbias = p.relbias; a.rb_ld = p.rb_ld; a.rb_hs = p.rb_hs; a.rb_bs = p.rb_bs;
     { static const int dbg = [] { const char* e = getenv("CBX_ATTN_FA_DBG"); return e ? atoi(e) : 0; }(); a.dbg = dbg; }
     ProfScope ps(PC_ATTN, 4.0 * p.T * p.T * D * p.H * p.batch * (p.causal ? 0.5 : 1.0), st);
     launch_pdl(attn_fa_kernel, dim3(cdiv(p.T, 2 * BQ), p.H, p.batch), dim3(THREADS), SMEM, st, tq, tk, tv, a);

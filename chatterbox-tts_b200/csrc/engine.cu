@@ -540,4 +540,16 @@ int cbx_op_attention(const void* qkv, void* out, int T, int H, int batch, int ca
     CBX_API_END
 }
 
+// attention with an additive relative-position bias (flow encoder): bias fp32 [batch][H][T][2T], entry (i, j) at column T - 1 - i + j
+int cbx_op_attention_bias(const void* qkv, const float* bias, void* out, int T, int H, int batch, void* stream) {
+    CBX_API_BEGIN
+    ops_init_once();
+    const long ld = 3L * H * 64;
+    AttnParams a; a.q = (const bf16*)qkv; a.k = a.q + H * 64; a.v = a.q + 2 * H * 64; a.ldq = a.ldk = a.ldv = ld; a.q_bs = a.k_bs = a.v_bs = (long)T * ld;
+    a.o = (bf16*)out; a.ldo = H * 64; a.o_bs = (long)T * H * 64; a.T = T; a.H = H; a.batch = batch; a.causal = 0; a.scale = 0.125f;
+    a.relbias = bias; a.rb_ld = 2L * T; a.rb_hs = (long)T * 2 * T; a.rb_bs = (long)H * T * 2 * T;
+    launch_attention(a, (cudaStream_t)stream);
+    CBX_API_END
+}
+
 }  // extern "C"

@@ -217,6 +217,8 @@ long long cbx_cfm_tail_launches(void);
 /* debug: %globaltimer stamps (ns) of CTA 0 of the last fused-tail launch (9 phase boundaries, see cfm_tail.cu) */
 int cbx_cfm_tail_trace(unsigned long long* out_h);
 int cbx_op_attention(const void* qkv_bf16_d, void* out_bf16_d, int T, int H, int batch, int causal, void* stream);
+/* the same with the flow encoder's additive relative-position bias: bias fp32 [batch][H][T][2T], entry (i, j) read at column T - 1 - i + j */
+int cbx_op_attention_bias(const void* qkv_bf16_d, const float* bias_d, void* out_bf16_d, int T, int H, int batch, void* stream);
 
 #ifdef __cplusplus
 }

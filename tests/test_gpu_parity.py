@@ -85,6 +85,27 @@ def test_attention_op(dev, T, H, B, causal):
     assert torch.equal(out, out2), "run-to-run determinism"
 
 
+@pytest.mark.parametrize("T,H,B", [(100, 8, 2), (388, 8, 3), (668, 8, 1)])
+def test_attention_op_with_relative_position_bias(dev, T, H, B):
+    """The flow encoder's attention: scores = (q k^T + bd) / 8 with the rel-shifted bias read at column T - 1 - i + j; served by
+    the tcgen05 kernel (no mma.sync attention left on the S3Gen path)."""
+    from cbx_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(T)
+    qkv = torch.randn(B, T, 3 * H * 64, generator=g).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(B, H, T, 2 * T, generator=g) * 3).to(dev)
+    out = torch.empty(B, T, H * 64, device=dev, dtype=torch.bfloat16)
+    before = lib.cbx_attn_fa_launches()
+    L.check(lib.cbx_op_attention_bias(qkv.data_ptr(), bias.data_ptr(), out.data_ptr(), T, H, B, None))
+    torch.cuda.synchronize()
+    assert lib.cbx_attn_fa_launches() == before + 1
+    q, k, v = (t.float().view(B, T, H, 64).transpose(1, 2) for t in qkv.split(H * 64, dim=-1))
+    idx = (T - 1 - torch.arange(T, device=dev)[:, None] + torch.arange(T, device=dev)[None]).expand(B, H, T, T)
+    sc = (q @ k.transpose(-1, -2) + bias.gather(-1, idx)) * 0.125
+    ref = (torch.softmax(sc, dim=-1) @ v).transpose(1, 2).reshape(B, T, H * 64)
+    assert _rel(out.float(), ref) < 1e-2
+
+
 @pytest.mark.parametrize("M,mode", [(128, 7), (300, 7), (1000, 3), (1000, 4), (5000, 7), (77, 1), (2049, 6)])
 def test_cfm_tail_op(dev, M, mode):
     """Fused tail of a CFM transformer block (cfm_tail.cu) against plain fp32 torch with bf16 rounding at the same hand-over

@@ -447,7 +447,7 @@ def run_b200(args):
         n = 8
         counts, pms, work = (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
         lib.cbx_profile_end(counts, pms, work, n)
-        names = ["gemm_tc_kernel class (tcgen05 GEMM + implicit conv: CFM / HiFT / encoder / T3 prefill)", "attn_tc_kernel class (tcgen05 flash attention: CFM / encoder / T3 prefill)",
+        names = ["gemm_tc_kernel class (tcgen05 GEMM + implicit conv: CFM / HiFT / encoder / T3 prefill)", "attn_fa_kernel class (tcgen05 flash attention, P and O in tensor memory: CFM / encoder / T3 prefill)",
                  "t3_decode_step (GEMV projections + decode attention + sampler of one step, graph replay)", "decode_attn_kernel", "sampler_kernel", "norm_kernel", "elementwise", "hift misc"]
         kern = []
         for i in range(n):
@@ -472,12 +472,18 @@ def run_b200(args):
             roof["t3_decode_step_in_workload"] = {"bound": "hbm", "achieved": gv["rate"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gv["rate"] / pk["hbm_gbs"]}
         # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), when there is one
         try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")) as fh:
                 tr = json.load(fh)
-            key = "gemm_tc_kernel" if dom == 0 else ("attn_tc_kernel" if dom == 1 else ("t3_decode_step" if dom == 2 else None))
+            key = "gemm_tc_kernel" if dom == 0 else ("attn_fa_kernel" if dom == 1 else None)
             if key in tr:
                 roof["traffic"] = tr[key]["dram_bytes_per_launch"]
-                roof["traffic_note"] = tr[key].get("note", "")
+                roof["traffic_note"] = ("ncu --set full --clock-control none (tools/ncu_capture_r2.sh: one batched S3Gen call of 8 x 140 tokens; cold-cache, "
+                                        "serialised); dram read + write bytes averaged over the captured launches of " + key + "; profiles/ncu_traffic_r2.json")
+            elif dom == 2:      # one decode step = 30 x (QKV + O + gate/up + down) captured launches + the head: weights once (the KV cache is extra)
+                g = tr.get("gemv_kernel", {}).get("dram_bytes_per_launch")
+                if g:
+                    roof["traffic"] = g * 4 * 30 + 16.8e6
+                    roof["traffic_note"] = "30 x 4 captured gemv_kernel launches (2 rows) + the 16.8 MB head; decode attention's KV reads are not in this figure"
         except Exception:
             pass
         # T3 decode step alone, both implementations (200 steps of one stream, CUDA events): bytes = weights + KV read

@@ -117,6 +117,8 @@ class T3Scheduler(threading.Thread):
         self.lock = threading.Condition()
         self.running = True
         self.rounds = 0
+        self.busy_s = 0.0                              # wall time inside decode rounds (stats)
+        self.row_hist = collections.Counter()          # rows per decode round -> count
         # CBX_T3_ALIGN_OPENS_MS (default 30, 0 = off): while every open stream is still at token 0 and other streams are being
         # opened (their prefills run one after the other, ~3 ms each), the first decode round waits up to this long, so that
         # requests that arrive together decode in lockstep and their first slices share ONE S3Gen batch instead of "first
@@ -185,6 +187,7 @@ class T3Scheduler(threading.Thread):
             if not live:
                 continue
             try:
+                t_busy = time.time()
                 with self._ctx():
                     self.native.t3_step([s.slot for s in live], self.k)
                     for s in live:
@@ -198,6 +201,8 @@ class T3Scheduler(threading.Thread):
                         if done:
                             self._retire(s)
                 self.rounds += 1
+                self.busy_s += time.time() - t_busy
+                self.row_hist[2 * len(live)] += 1
             except BaseException as ex:  # surface engine failures to every waiting request
                 for s in live:
                     with s.cv:
@@ -278,6 +283,7 @@ class S3GenBatcher:
         self.cv = threading.Condition()
         self.running = True
         self.batches = collections.Counter()   # batch size -> count (bench / tests)
+        self.busy_s = 0.0                      # wall time inside batched calls, including the stream sync (stats)
         self.pad_stats = [0, 0]                # new tokens requested, new tokens computed after padding to the batch maximum
         n = workers or int(os.environ.get("CBX_S3GEN_WORKERS", "1"))
         # after the first pending job shows up, wait this long for companions (slices of concurrent requests become ready
@@ -357,6 +363,7 @@ class S3GenBatcher:
                 else:
                     live.append(j)
             if live:
+                t_busy = time.time()
                 try:
                     with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
                         def cache_of(j, pos):
@@ -380,6 +387,7 @@ class S3GenBatcher:
                         if st is not None:
                             st.synchronize()
                     with self.cv:
+                        self.busy_s += time.time() - t_busy
                         self.batches[len(live)] += 1
                         lens = [len(j.toks) for j in live]
                         self.pad_stats[0] += sum(lens)

@@ -221,11 +221,25 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fa_kernel(const __grid_consta
             float m = -INFINITY, l = 0.f;
             const bool pingpong = ngroups == 2 && !(p.dbg & 8);
             if (pingpong && g == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");      // group A goes first
+            // a warp whose 32 query rows all lie beyond the sequence (the tail of the last query tile: 668 rows = 5.2 tiles) only
+            // keeps the barrier protocol going: no TMEM traffic, no exponentials.  Its P / O rows hold garbage that is never stored.
+            const bool dead = q0 + g * BQ + (warp & 3) * 32 >= Tk;
             for (int j = 0; j < nkv; j++) {
                 FA_TRACE(j < 8 && qr == 0 , 128 + (j * 2 + g) * 4);
                 mbar_wait(s_full + 8 * g, j & 1);
                 tc_fence_after();
                 FA_TRACE(j < 8 && qr == 0, 128 + (j * 2 + g) * 4 + 1);
+                if (dead) {
+                    tc_fence_before();
+                    mbar_arrive(s_free + 8 * g);
+                    if (j > 0) mbar_wait(o_done + 8 * g, (j - 1) & 1);
+                    if (pingpong) {
+                        if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+                        if (!(g == 1 && j == nkv - 1)) { if (g == 0) asm volatile("bar.arrive 2, 256;" ::: "memory"); else asm volatile("bar.arrive 1, 256;" ::: "memory"); }
+                    }
+                    mbar_arrive(p_ready + 8 * g);
+                    continue;
+                }
                 float s[128];
 #pragma unroll
                 for (int c = 0; c < 4; c++) tmem_ld32_nowait(scol + c * 32, s + c * 32);
@@ -284,10 +298,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fa_kernel(const __grid_consta
                 if (pingpong) { if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory"); }
                 FA_TRACE(j < 8 && qr == 0, 192 + (j * 2 + g) * 4 + 2);
                 float l0 = 0.f, l1 = 0.f;
+                // 32-key chunks of the last key block that lie wholly beyond the sequence get P = 0 without an exponential
+                const int live_chunks = (masked && !p.causal) ? (min(BK, Tk - kbase) + 31) >> 5 : 4;
                 auto exp_pass = [&](auto use_poly) {         // masked blocks (exact zeros wanted) take the MUFU for every element
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         uint32_t pk[16];
+                        if (c >= live_chunks) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) pk[i] = 0u;
+                        } else
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
                             const float x0 = fmaf(s[c * 32 + i], p.sl2, neg_m), x1 = fmaf(s[c * 32 + i + 1], p.sl2, neg_m);
@@ -311,6 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fa_kernel(const __grid_consta
             }
             mbar_wait(o_done + 8 * g, (nkv - 1) & 1);
             tc_fence_after();
+            if (!dead) {                  // (dead warps: nothing to store, rows beyond the sequence are never consumed)
             float o[64];
             tmem_ld32_nowait(ocol, o);
             tmem_ld32_nowait(ocol + 32, o + 32);
@@ -322,6 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fa_kernel(const __grid_consta
                 for (int i = 0; i < 64; i += 8)
                     *reinterpret_cast<uint4*>(orow + i) = make_uint4(pack_bf16(o[i] * inv, o[i + 1] * inv), pack_bf16(o[i + 2] * inv, o[i + 3] * inv),
                                                                      pack_bf16(o[i + 4] * inv, o[i + 5] * inv), pack_bf16(o[i + 6] * inv, o[i + 7] * inv));
+            }
             }
         }
     }

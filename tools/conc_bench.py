@@ -36,6 +36,8 @@ for lanes in lanes_list:
             return nb, first
         await asyncio.gather(*[one(i) for i in range(streams)])
         torch.cuda.synchronize()
+        b0, r0, n0 = eng.s3gen.busy_s, eng.scheduler.busy_s, dict(eng.s3gen.batches)
+        eng.scheduler.row_hist.clear()
         t0 = time.time()
         res = await asyncio.gather(*[one(i) for i in range(streams)])
         torch.cuda.synchronize()
@@ -43,7 +45,9 @@ for lanes in lanes_list:
         audio = sum(r[0] for r in res) / 2 / 24000.0
         firsts = sorted(r[1] for r in res)
         print(json.dumps({"streams": streams, "lanes": lanes, "audio_s_per_s": audio / dt, "seconds": dt, "first_chunk_ms_p50": firsts[len(firsts) // 2], "first_chunk_ms_all": [round(f, 1) for f in firsts], "s3gen_batches": dict(sorted(eng.s3gen.batches.items())),
-                          "t3_rounds": eng.scheduler.rounds}), flush=True)
+                          "t3_rounds": eng.scheduler.rounds,
+                          "s3gen_busy_s": eng.s3gen.busy_s - b0, "t3_busy_s": eng.scheduler.busy_s - r0, "t3_rows_hist": dict(sorted(eng.scheduler.row_hist.items())),
+                          "s3gen_batches_this_wave": {k: v - n0.get(k, 0) for k, v in sorted(eng.s3gen.batches.items()) if v - n0.get(k, 0)}}), flush=True)
     asyncio.run(main())
     eng.shutdown()
     del eng

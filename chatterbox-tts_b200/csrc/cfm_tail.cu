@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TM;
     const bool do_out = p.mode & CFM_TAIL_OUT, do_ff = p.mode & CFM_TAIL_FF, do_qkv = p.mode & CFM_TAIL_QKV;
+    if (p.seq_T > 0) {      // a tile wholly inside one slab's padding: nothing to do (before any barrier / TMEM state exists)
+        const int s0 = m0 / p.seq_T, s1 = min(m0 + TM - 1, p.M - 1) / p.seq_T;
+        if (s0 == s1 && m0 - s0 * p.seq_T >= p.seq_len[(s0 >> 1) & 15]) { pdl_launch_dependents(); return; }
+    }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NST; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }

@@ -13,6 +13,9 @@ struct CfmTailArgs {
     const float *b0 = nullptr, *b2 = nullptr;                // [1024], [256]
     const float *ln1_g = nullptr, *ln1_b = nullptr;          // [256] LayerNorm1 of the NEXT block
     bf16* qkv = nullptr;                                     // [M][1536] bf16 out
+    // ragged batches: rows are [slab][seq_T] (two slabs per call); a tile that lies wholly in a slab's padding (row index inside
+    // the slab >= seq_len[slab / 2]) is skipped -- its rows are never consumed (causal convs, masked attention keys).  0 = off
+    int seq_T = 0; int seq_len[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // TMA descriptors of one block's weights (static for the life of the engine): 128-byte opaque CUtensorMaps

@@ -195,6 +195,9 @@ struct GemmParams {
     const float* ln_gamma = nullptr; const float* ln_beta = nullptr; float ln_eps = 1e-5f;
     // transposed-conv scatter mask: column n belongs to phase n/ct_cout; output time = m*ct_u + phase - ct_pad must be in [0, ct_len)
     int ct_u = 0, ct_cout = 0, ct_pad = 0, ct_len = 0;
+    // ragged batches of slabs (batch = slab index): row tiles that start at or beyond row_len[b / row_div] lie in the slab's padding
+    // and are skipped by the tcgen05 kernel (their rows are never consumed).  row_div == 0: off
+    int row_len[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int row_div = 0;
 };
 void launch_gemm(const GemmParams& p, cudaStream_t st);
 void gemm_init();

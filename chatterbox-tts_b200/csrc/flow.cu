@@ -289,6 +289,9 @@ static void tfm_stage(cbx_engine* e, Lane& L, int j0, int nb, int T, cudaStream_
     if (flow_tail_path(M)) {
         // stage opener: LayerNorm1 + QKV of the first block; then per block: attention, fused tail (+ next block's LN1 / QKV)
         CfmTailArgs a; a.M = M; a.h = L.c_h; a.qkv = L.c_qkv;
+        bool ragged = false;
+        for (int b = 0; b < L.nb; b++) ragged = ragged || L.call[b].Tt != L.Ttm;
+        if (ragged && L.nb <= 16) { a.seq_T = T; for (int b = 0; b < L.nb; b++) a.seq_len[b] = 2 * L.call[b].Tt; }
         a.mode = CFM_TAIL_QKV; a.ln1_g = f.tfms[j0].n1.g; a.ln1_b = f.tfms[j0].n1.b;
         launch_cfm_tail(a, nullptr, nullptr, &f.tfms[j0].tw, st);
         for (int j = 0; j < nb; j++) {
@@ -298,7 +301,8 @@ static void tfm_stage(cbx_engine* e, Lane& L, int j0, int nb, int T, cudaStream_
             set_kv_len(at, L, 2, 2);
             launch_attention(at, st);
             const bool more = j + 1 < nb;
-            CfmTailArgs b; b.M = M; b.h = L.c_h; b.qkv = L.c_qkv; b.mode = CFM_TAIL_OUT | CFM_TAIL_FF | (more ? CFM_TAIL_QKV : 0);
+            CfmTailArgs b; b.M = M; b.h = L.c_h; b.qkv = L.c_qkv; b.seq_T = a.seq_T; for (int i = 0; i < 16; i++) b.seq_len[i] = a.seq_len[i];
+            b.mode = CFM_TAIL_OUT | CFM_TAIL_FF | (more ? CFM_TAIL_QKV : 0);
             b.b_out = t.out.b; b.ln3_g = t.n3.g; b.ln3_b = t.n3.b; b.b0 = t.ff0.b; b.b2 = t.ff2.b;
             if (more) { b.ln1_g = f.tfms[j0 + j + 1].n1.g; b.ln1_b = f.tfms[j0 + j + 1].n1.b; }
             launch_cfm_tail(b, L.c_o, &t.tw, more ? &f.tfms[j0 + j + 1].tw : nullptr, st);
@@ -310,19 +314,28 @@ static void tfm_stage(cbx_engine* e, Lane& L, int j0, int nb, int T, cudaStream_
         tfm_block(e, L, f.tfms[j0 + j], T, fuse_ln() && j > 0, (fuse_ln() && j + 1 < nb) ? &f.tfms[j0 + j + 1].n1 : nullptr, st);
 }
 
+// slab GEMMs of the estimator (batch = 2 x calls slabs of T frames): row tiles in a slab's padding are skipped
+static void set_row_len(GemmParams& g, const Lane& L) {
+    bool ragged = false;
+    for (int b = 0; b < L.nb; b++) ragged = ragged || L.call[b].Tt != L.Ttm;
+    if (!ragged || L.nb > 16) return;
+    g.row_div = 2;
+    for (int b = 0; b < L.nb; b++) g.row_len[b] = 2 * L.call[b].Tt;
+}
+
 // resnet: in = haloed bf16 [2nb][CH+T][cin] -> L.c_h fp32 [2nb][T][256]
 static void resnet(cbx_engine* e, Lane& L, const ResnetP& r, const float* tproj, const bf16* in, int T, cudaStream_t st) {
     const int NB = 2 * L.nb;
     const long TH = T + CH, bs = (long)T * C_CH;
-    GemmParams g = mk(r.c1, in, r.cin, T, r.cin, r.cin); g.batch = NB; g.a_bs = TH * r.cin; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    GemmParams g = mk(r.c1, in, r.cin, T, r.cin, r.cin); g.batch = NB; g.a_bs = TH * r.cin; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; set_row_len(g, L); launch_gemm(g, st);
     NormParams n; n.in = L.c_tmp; n.ld_in = C_CH; n.in_bs = bs; n.rows = T; n.batch = NB; n.C = C_CH; n.gain = r.n1.g; n.bias = r.n1.b; n.eps = 1e-5f; n.act = ACT_MISH;
     n.add = tproj; n.add_bs = 0; n.outB = L.c_hb + CH * C_CH; n.ld_outB = C_CH; n.outB_bs = TH * C_CH;
     launch_norm(n, st);
-    g = mk(r.c2, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; launch_gemm(g, st);
+    g = mk(r.c2, L.c_hb, C_CH, T, C_CH, C_CH); g.batch = NB; g.a_bs = TH * C_CH; g.outF = L.c_tmp; g.ldc = C_CH; g.c_bs = bs; set_row_len(g, L); launch_gemm(g, st);
     NormParams n2; n2.in = L.c_tmp; n2.ld_in = C_CH; n2.in_bs = bs; n2.rows = T; n2.batch = NB; n2.C = C_CH; n2.gain = r.n2.g; n2.bias = r.n2.b; n2.eps = 1e-5f; n2.act = ACT_MISH;
     n2.outF = L.c_tmp2; n2.ld_outF = C_CH; n2.outF_bs = bs;
     launch_norm(n2, st);
-    g = mk(r.res, in + CH * r.cin, r.cin, T, r.cin, 0); g.batch = NB; g.a_bs = TH * r.cin; g.res = L.c_tmp2; g.ldr = C_CH; g.r_bs = bs; g.outF = L.c_h; g.ldc = C_CH; g.c_bs = bs;
+    g = mk(r.res, in + CH * r.cin, r.cin, T, r.cin, 0); g.batch = NB; g.a_bs = TH * r.cin; g.res = L.c_tmp2; g.ldr = C_CH; g.r_bs = bs; g.outF = L.c_h; g.ldc = C_CH; g.c_bs = bs; set_row_len(g, L);
     launch_gemm(g, st);
     e->gpu_launches += 5;
 }

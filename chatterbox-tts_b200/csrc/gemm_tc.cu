@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256, 2) gemm_tc_kernel(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN, b = blockIdx.z;
     const int KB = p.K / TK;
+    if (!LN && p.row_div > 0 && m0 >= p.row_len[(b / p.row_div) & 15]) { pdl_launch_dependents(); return; }     // tile in a slab's padding
 
     if (threadIdx.x == 0) TC_TRACE(0);
     if (warp == 0 && lane == 0) {

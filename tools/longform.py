@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[4]-style robustness run on one GPU: a 2000-word document streamed through the engine
-(about 80 text chunks, 20 000 speech tokens, ~13 minutes of audio): checks slot / KV-page recycling and ordering at length."""
+"""BASELINE.json configs[4] on one GPU: a 2000-word document with VOICE-CLONING CONDITIONING COMPUTED FOR THE REQUEST (a 10 s clip in
+VOICES_DIR, not cached: prepare_conditionals runs the GPU encoders inside the timed request) streamed through the engine (about 80
+text chunks, 20 000 speech tokens, ~13 minutes of audio): also checks slot / KV-page recycling and ordering at length."""
 import asyncio, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "chatterbox-tts_b200")):
@@ -12,11 +13,23 @@ from cbx_b200.engine import TextToSpeechEngine, SamplingDefaults
 
 async def main():
     words = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    eng = TextToSpeechEngine("cuda:0", concurrent_requests=8, sampling=SamplingDefaults(tokens_per_word=bench.TOK_PER_WORD), seed=0)
+    import tempfile
+    from scipy.io import wavfile
+    from cbx_b200.config import ModelConfig
+    from cbx_b200.weights import random_state_dict
+    vdir = tempfile.mkdtemp()
+    os.environ["VOICES_DIR"] = vdir
+    t = np.arange(24000 * 10) / 24000.0
+    clip = 0.3 * np.sin(2 * np.pi * 170 * t) * np.clip(np.sin(2 * np.pi * 1.3 * t), 0, None) + 0.03 * np.random.default_rng(0).standard_normal(t.shape[0])
+    wavfile.write(os.path.join(vdir, "speaker.wav"), 24000, (clip * 32767).astype(np.int16))
+    cfg = ModelConfig()
+    eng = TextToSpeechEngine("cuda:0", concurrent_requests=8, sampling=SamplingDefaults(tokens_per_word=bench.TOK_PER_WORD), seed=0,
+                             state_dict=random_state_dict(cfg, 0), encoder_state_dict=random_state_dict(cfg, 0, parts=("cond",)))
     await eng.ainit()
+    eng.conditioning_encoders()          # weights resident (the reference loads its encoders in from_local as well)
     text = bench.synthetic_text(words)
     t0 = time.time(); first = None; nbytes = 0; peak = 0
-    async for chunk in eng.stream(text=text, output_format="raw_pcm", voice_id=None, request_id="long", cancellation_token=None, **bench.REQ):
+    async for chunk in eng.stream(text=text, output_format="raw_pcm", voice_id="speaker.wav", request_id="long", cancellation_token=None, **bench.REQ):
         if first is None and len(chunk):
             first = (time.time() - t0) * 1e3
         if len(chunk):

@@ -63,6 +63,7 @@ SIGNATURES = {
     "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P, _P, _P]),
     "cbx_gpu_launches": (_L, [_P]),
     "cbx_gemm_tc_launches": (C.c_longlong, []),
+    "cbx_gemm_mma_launches": (C.c_longlong, []),
     "cbx_attn_tc_launches": (C.c_longlong, []),
     "cbx_attn_fa_launches": (C.c_longlong, []),
     "cbx_attn_fa_trace": (_I, [_P]),

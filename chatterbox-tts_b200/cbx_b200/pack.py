@@ -167,7 +167,7 @@ def pack_state_dict(sd, cfg: ModelConfig):
     # ------------------------------------------------------------------ HiFT
     hc = cfg.hift
     m = "mel2wav."
-    conv("hift.conv_pre", m + "conv_pre")
+    conv("hift.conv_pre", m + "conv_pre", cin_pad=128)       # mel channels 80 -> 128: whole K tiles for the tcgen05 conv
     conv("hift.conv_post", m + "conv_post")
     nk = len(hc.resblock_kernels)
 
@@ -181,12 +181,12 @@ def pack_state_dict(sd, cfg: ModelConfig):
     for i, u in enumerate(hc.upsample_rates):
         w, b = convT_pack(sd[m + f"ups.{i}.weight"], sd[m + f"ups.{i}.bias"], u)
         P[f"hift.ups{i}.w"], P[f"hift.ups{i}.b"] = bf(w), f32(b)
-        conv(f"hift.sdown{i}", m + f"source_downs.{i}", cin_pad=24)
+        conv(f"hift.sdown{i}", m + f"source_downs.{i}", cin_pad=64)
         resblock(f"hift.sres{i}.", m + f"source_resblocks.{i}.")
         for k in range(nk):
             resblock(f"hift.res{i * nk + k}.", m + f"resblocks.{i * nk + k}.")
     for l in range(hc.f0_layers):
-        conv(f"hift.f0c{l}", m + f"f0_predictor.condnet.{2 * l}")
+        conv(f"hift.f0c{l}", m + f"f0_predictor.condnet.{2 * l}", cin_pad=128 if l == 0 else None)
     P["hift.f0w"] = f32(sd[m + "f0_predictor.classifier.weight"][0])
     P["hift.f0b"] = f32(sd[m + "f0_predictor.classifier.bias"])
     P["hift.lw"] = f32(sd[m + "m_source.l_linear.weight"][0])

@@ -23,7 +23,7 @@ constexpr int T3_D = 1024, T3_H = 16, T3_FFN = 4096, T3_V = 8194, T3_VPAD = 8208
               T3_SPEECH_POS = 4100, T3_SPK = 256, T3_PQ = 32, T3_PH = 4, T3_COND = 34, T3_BOS = 6561, T3_EOS = 6562, PAGE = 16;
 constexpr int F_V = 6561, F_D = 512, F_H = 8, F_FFN = 2048, F_SPK = 192, MEL = 80, C_IN = 320, C_CH = 256, C_INNER = 512,
               C_FF = 1024, C_TDIM = 1024, NOISE_LEN = 15000;
-constexpr int H_BASE = 512, H_NSRC = 18, H_NSRC_PAD = 24, H_HALO = 32, H_UP = 480, H_NHARM = 9, H_F0CH = 512;
+constexpr int H_BASE = 512, H_NSRC = 18, H_NSRC_PAD = 64, MEL_PAD = 128, H_HALO = 32, H_UP = 480, H_NHARM = 9, H_F0CH = 512;
 }  // namespace dims
 
 struct Lin { bf16* w = nullptr; float* b = nullptr; int N = 0, K = 0; };

@@ -143,7 +143,7 @@ void lane_alloc(cbx_engine* e, Lane& L, int bmax) {
     }
     // hift (one call at a time)
     const long HH = H_HALO;
-    L.mel = e->scratch<float>(Tg * MEL); L.h_mel = e->scratch<bf16>((Tg + 2 * HH) * MEL);
+    L.mel = e->scratch<float>(Tg * MEL); L.h_mel = e->scratch<bf16>((Tg + 2 * HH) * MEL_PAD);     // channels 80..127 stay zero: K tiles of 64 for the tcgen05 conv
     L.h_f0a = e->scratch<bf16>((Tg + 2 * HH) * H_F0CH); L.h_f0b = e->scratch<bf16>((Tg + 2 * HH) * H_F0CH);
     L.h_f0 = e->scratch<float>(Tg); L.h_cum = e->scratch<double>(Tg * H_NHARM); L.h_s = e->scratch<float>(Tg * H_UP);
     const long F = 120 * Tg + 1;

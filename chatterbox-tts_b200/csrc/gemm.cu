@@ -182,6 +182,9 @@ void gemm_init() {
     init_cfg<64, 64, 2, 4>();
 }
 
+static long g_mma_launches = 0;
+extern "C" long long cbx_gemm_mma_launches(void) { return g_mma_launches; }
+
 void launch_gemm(const GemmParams& p, cudaStream_t st) {
     CBX_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.batch > 0, "gemm: empty problem");
     CBX_REQUIRE(p.kc % 8 == 0 && p.K % 8 == 0 && p.lda % 8 == 0 && p.ldw % 8 == 0 && p.tap_stride % 8 == 0 &&
@@ -192,6 +195,7 @@ void launch_gemm(const GemmParams& p, cudaStream_t st) {
     ProfScope ps(PC_GEMM, 2.0 * p.M * p.N * p.K * p.batch, st);
     if (launch_gemm_tc(p, st)) return;
     CBX_REQUIRE(!p.ln_gamma, "gemm: the fused LayerNorm epilogue exists only on the tcgen05 path (N must be 1..4 tiles, no activation)");
+    g_mma_launches++;       // mma.sync fallback (shapes TMA cannot describe): none is left on the S3Gen / T3 paths
     long big = (long)cdiv(p.M, 128) * cdiv(p.N, 128) * p.batch;
     if (big >= 296) launch_cfg<128, 128, 4, 4>(p, st);
     else launch_cfg<64, 64, 2, 4>(p, st);

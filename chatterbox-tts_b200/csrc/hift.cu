@@ -28,7 +28,7 @@ static ResBlockP reg_resblock(cbx_engine* e, const std::string& p, int ch, int k
 
 void hift_build(cbx_engine* e) {
     HiftModel& h = e->hift;
-    h.conv_pre = reg_lin(e, "hift.conv_pre", H_BASE, 7 * MEL);
+    h.conv_pre = reg_lin(e, "hift.conv_pre", H_BASE, 7 * MEL_PAD);
     for (int i = 0; i < 3; i++) {
         int cin = H_BASE >> i, ch = H_BASE >> (i + 1), taps = (UPS_K[i] + UPS_U[i] - 1) / UPS_U[i];
         std::string s = std::to_string(i);
@@ -38,7 +38,7 @@ void hift_build(cbx_engine* e) {
         for (int k = 0; k < 3; k++) h.res[i * 3 + k] = reg_resblock(e, "hift.res" + std::to_string(i * 3 + k) + ".", ch, RES_K[k]);
     }
     h.conv_post = reg_lin(e, "hift.conv_post", H_NSRC, 7 * (H_BASE >> 3));
-    for (int l = 0; l < 5; l++) h.f0c[l] = reg_lin(e, "hift.f0c" + std::to_string(l), H_F0CH, 3 * (l == 0 ? MEL : H_F0CH));
+    for (int l = 0; l < 5; l++) h.f0c[l] = reg_lin(e, "hift.f0c" + std::to_string(l), H_F0CH, 3 * (l == 0 ? MEL_PAD : H_F0CH));
     h.f0w = e->reg<float>("hift.f0w", DT_F32, H_F0CH);
     h.f0b = e->reg<float>("hift.f0b", DT_F32, 1);
     h.lw = e->reg<float>("hift.lw", DT_F32, H_NHARM);
@@ -84,10 +84,10 @@ static void resblock(cbx_engine* e, const ResBlockP& r, const float* x_in, float
 void hift_f0(cbx_engine* e, Lane& L, int Tg, cudaStream_t st) {
     HiftModel& h = e->hift;
     auto zero_tail = [&](bf16* buf, long T, int C) { CBX_CHECK(cudaMemsetAsync(buf + (H_HALO + T) * C, 0, (size_t)H_HALO * C * 2, st)); };
-    zero_tail(L.h_mel, Tg, MEL); zero_tail(L.h_f0a, Tg, H_F0CH); zero_tail(L.h_f0b, Tg, H_F0CH);
-    launch_f32_to_bf16_rows(L.mel, MEL, L.h_mel + (long)H_HALO * MEL, MEL, Tg, MEL, ACT_NONE, 0.f, st);
+    zero_tail(L.h_mel, Tg, MEL_PAD); zero_tail(L.h_f0a, Tg, H_F0CH); zero_tail(L.h_f0b, Tg, H_F0CH);
+    launch_f32_to_bf16_rows(L.mel, MEL, L.h_mel + (long)H_HALO * MEL_PAD, MEL_PAD, Tg, MEL, ACT_NONE, 0.f, st);     // 80 of 128 columns; the rest stay zero
     // F0 predictor: 5 x (conv k3 + ELU) -> |linear|
-    const bf16* fin = L.h_mel; int cin = MEL;
+    const bf16* fin = L.h_mel; int cin = MEL_PAD;
     bf16* pp[2] = {L.h_f0a, L.h_f0b};
     for (int l = 0; l < 5; l++) {
         GemmParams g = conv(h.f0c[l], fin, cin, 3, 1, Tg);
@@ -131,7 +131,7 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
     launch_stft16(src_out, Ls, L.h_stft + (long)H_HALO * H_NSRC_PAD, H_NSRC_PAD, (int)F, st);
     // ---- conv_pre (+ the leaky_relu that precedes ups[0])
     {
-        GemmParams g = conv(h.conv_pre, L.h_mel, MEL, 7, 1, Tg);
+        GemmParams g = conv(h.conv_pre, L.h_mel, MEL_PAD, 7, 1, Tg);
         g.act = ACT_LRELU; g.act_param = 0.1f; g.outB = L.h_xb[0] + (long)H_HALO * H_BASE; g.ldc = H_BASE;
         launch_gemm(g, st);
     }

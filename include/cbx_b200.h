@@ -175,6 +175,8 @@ int cbx_cond_lstm_layer(const float* xp, const float* w_hh_t, float* h_seq, floa
 int64_t cbx_gpu_launches(cbx_engine* e);
 /* GEMM launches that took the tcgen05/TMA path (process-wide; 0 means the mma.sync fallback served everything) */
 long long cbx_gemm_tc_launches(void);
+/* GEMM launches that fell back to the mma.sync kernel (shapes TMA cannot describe); 0 on the T3 / S3Gen paths */
+long long cbx_gemm_mma_launches(void);
 /* attention launches served by the tcgen05 flash-attention kernels (process-wide; both generations) */
 long long cbx_attn_tc_launches(void);
 /* of those, the launches of the second-generation kernel (P and O in tensor memory, attention_fa.cu) */

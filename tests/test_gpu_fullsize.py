@@ -83,3 +83,23 @@ def test_s3gen_ragged_batch_is_exact_full_depth(full):
         assert m1.shape == m0.shape and torch.isfinite(m1).all()
         assert _rel(m1, m0) < 1e-4
         assert w1.shape == w0.shape and w1.abs().max() <= 0.99 + 1e-6
+
+
+def test_hot_path_runs_only_blackwell_contraction_kernels(full):
+    """T3 prefill + decode, the flow encoder / estimator and the vocoder launch no mma.sync GEMM and no mma.sync attention: every
+    contraction goes through the tcgen05 kernels (GEMM + implicit conv, flash attention, fused CFM tail) or, for decode rows, the
+    HBM-bound GEMV."""
+    from cbx_b200 import lib as L
+    lib = L.load()
+    eng, voice = full
+    mma0, fa0, tc0 = lib.cbx_gemm_mma_launches(), lib.cbx_attn_fa_launches(), lib.cbx_attn_tc_launches()
+    slot = eng.t3_open(voice, _text(50, 1), seed=3, max_new=8)
+    eng.t3_step([slot], 4)
+    eng.t3_close(slot)
+    calls = [(voice, [(i * 37 + 11 * b) % 6561 for i in range(20 + 9 * b)], None, 1 + b) for b in range(3)]      # ragged batch, plain launches
+    eng.s3gen_infer_batch(calls)
+    torch.cuda.synchronize()
+    assert lib.cbx_gemm_mma_launches() == mma0, "a GEMM fell back to the mma.sync kernel"
+    d_fa, d_all = lib.cbx_attn_fa_launches() - fa0, lib.cbx_attn_tc_launches() - tc0
+    # 30 causal prefill launches + 10 rel-pos encoder launches + 56 x 10 estimator launches, all on the second-generation kernel
+    assert d_fa == d_all == 30 + 10 + 560

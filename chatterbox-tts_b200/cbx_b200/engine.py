@@ -248,10 +248,11 @@ class T3Scheduler(threading.Thread):
 class _S3Job:
     """One S3Gen call in flight: `dep` is the job whose source output is this call's cache_source (the previous slice of
     the same text chunk under the "full" overlap strategy), or None."""
-    __slots__ = ("voice", "toks", "dep", "seed", "done", "out", "err", "dropped", "urgent", "consumed")
+    __slots__ = ("voice", "toks", "dep", "seed", "done", "out", "err", "dropped", "urgent", "consumed", "emit_from")
 
-    def __init__(self, voice, toks, dep, seed, urgent=False):
+    def __init__(self, voice, toks, dep, seed, urgent=False, emit_from=0):
         self.voice, self.toks, self.dep, self.seed = voice, toks, dep, seed
+        self.emit_from = emit_from      # samples: the consumer reads wav[emit_from:] only ("full" overlap), the vocoder may decode a window
         self.done, self.out, self.err, self.dropped = threading.Event(), None, None, False
         # urgent: the first audio of a request.  The batcher gives its consumer a short exclusive window before it starts the
         # next batch: the PCM kernel + D2H of the emitter otherwise queue inside the driver behind the ~5 000-launch burst of the
@@ -289,13 +290,15 @@ class S3GenBatcher:
         # after the first pending job shows up, wait this long for companions (slices of concurrent requests become ready
         # within a decode round of each other): one batch of 8 beats a single call followed by a batch of 7
         self.gather_s = float(os.environ.get("CBX_S3GEN_GATHER_MS", "3")) * 1e-3
+        # "full" overlap emits wav[previous_length:] only: the vocoder decodes a window that ends the call (exact from emit_from on)
+        self.window = os.environ.get("CBX_HIFT_WINDOW", "1") != "0"
         self.urgent_window_s = float(os.environ.get("CBX_S3GEN_URGENT_MS", "15")) * 1e-3   # upper bound; the emitter ends it
         self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
         for t in self.threads:
             t.start()
 
-    def submit(self, voice, toks, dep: Optional[_S3Job], seed, urgent=False) -> _S3Job:
-        job = _S3Job(voice, toks, dep, seed, urgent)
+    def submit(self, voice, toks, dep: Optional[_S3Job], seed, urgent=False, emit_from=0) -> _S3Job:
+        job = _S3Job(voice, toks, dep, seed, urgent, emit_from if self.window else 0)
         with self.cv:
             self.jobs.append(job)
             self.cv.notify_all()
@@ -381,7 +384,7 @@ class S3GenBatcher:
                             # capturing a graph for a token count it has not seen yet
                             pos, calls = {}, []
                             for i, j in enumerate(live):
-                                calls.append((j.voice, j.toks, cache_of(j, pos), j.seed))
+                                calls.append((j.voice, j.toks, cache_of(j, pos), j.seed, j.emit_from))
                                 pos[id(j)] = i
                             outs = self.native.s3gen_infer_batch(calls)
                         if st is not None:
@@ -794,7 +797,8 @@ class TextToSpeechEngine:
                             if self.hold_until == "tokens" or (self.hold_until == "auto" and self._inflight > 1):
                                 first_slice_ready.set()
                         job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx,
-                                                urgent=(ci == 0 and first_slice))
+                                                urgent=(ci == 0 and first_slice),
+                                                emit_from=960 * len(prev_job.toks) if (overlap == "full" and prev_job is not None) else 0)
                         prev_job = job
                         jobs.append(job)
                         outq[ci].put((job, first_slice, last))

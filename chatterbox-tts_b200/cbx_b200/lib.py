@@ -17,7 +17,7 @@ class CbxConfig(C.Structure):
 class S3GenCall(C.Structure):
     """cbx_s3gen_call of include/cbx_b200.h"""
     _fields_ = [("voice", C.c_int), ("tokens_h", C.c_void_p), ("n", C.c_int), ("cache_source_d", C.c_void_p), ("m", C.c_int64),
-                ("wav_out_d", C.c_void_p), ("source_out_d", C.c_void_p), ("mel_out_d", C.c_void_p), ("seed", C.c_uint64)]
+                ("wav_out_d", C.c_void_p), ("source_out_d", C.c_void_p), ("mel_out_d", C.c_void_p), ("seed", C.c_uint64), ("emit_from", C.c_int64)]
 
 
 class SgemmArgs(C.Structure):
@@ -58,6 +58,7 @@ SIGNATURES = {
     "cbx_s3gen_infer_batch": (_I, [_P, C.POINTER(S3GenCall), _I, _P]),
     "cbx_flow_infer": (_I, [_P, _I, _P, _I, _P, _P]),
     "cbx_hift_infer": (_I, [_P, _P, _I, _P, _L, _P, _P, _P, _P, _U64, _P]),
+    "cbx_hift_infer_window": (_I, [_P, _P, _I, _P, _L, _P, _P, _U64, _I, _P]),
     "cbx_hift_f0": (_I, [_P, _P, _I, _P, _P]),
     "cbx_hift_source": (_I, [_P, _P, _I, _P, _P, _U64, _P, _P]),
     "cbx_crossfade_pcm": (_I, [_P, _P, _L, _P, _I, _P, _P, _P, _P]),

@@ -236,14 +236,17 @@ class NativeEngine:
         return (wav, src, mel) if return_mel else (wav, src)
 
     def s3gen_infer_batch(self, calls, return_mel=False):
-        """calls: list of (voice, tokens, cache_source, seed) -> list of (wav, source[, mel]); one batched token->mel pass
+        """calls: list of (voice, tokens, cache_source, seed[, emit_from]) -> list of (wav, source[, mel]); one batched token->mel pass
         for all calls (cbx_s3gen_infer_batch), results equal s3gen_infer call by call.  cache_source is a tensor, None, or
         the index of an EARLIER call of this batch whose source output is the cache (the vocoder runs call by call in
-        order, so consecutive slices of one text chunk can share a batch)."""
+        order, so consecutive slices of one text chunk can share a batch).  emit_from > 0: only wav[..., emit_from:] is valid
+        (the vocoder decodes a window; the samples before it are uninitialised)."""
         dev = torch.device("cuda", self.device)
         arr = (L.S3GenCall * len(calls))()
         keep, outs = [], []
-        for i, (voice, tokens, cache_source, seed) in enumerate(calls):
+        for i, call in enumerate(calls):
+            voice, tokens, cache_source, seed = call[:4]
+            emit_from = int(call[4]) if len(call) > 4 else 0
             tok = _i32(tokens).reshape(-1)
             n = len(tok)
             wav = torch.empty(1, 960 * n, device=dev, dtype=torch.float32)
@@ -258,7 +261,7 @@ class NativeEngine:
                 cs = cache_source.contiguous() if m else None
             keep.append((tok, cs))
             arr[i] = L.S3GenCall(voice, tok.ctypes.data, n, cs.data_ptr() if m else None, m, wav.data_ptr(), src.data_ptr(),
-                                 mel.data_ptr() if return_mel else None, seed)
+                                 mel.data_ptr() if return_mel else None, seed, emit_from)
             outs.append((wav, src, mel) if return_mel else (wav, src))
         L.check(self.lib.cbx_s3gen_infer_batch(self.h, arr, len(calls), _stream_ptr()))
         return outs
@@ -281,6 +284,18 @@ class NativeEngine:
         L.check(self.lib.cbx_hift_infer(self.h, C.c_void_p(mel.data_ptr()), T, cptr, m, C.c_void_p(wav.data_ptr()), C.c_void_p(src.data_ptr()),
                                         ph.ctypes.data if ph is not None else None,
                                         C.c_void_p(noise.data_ptr()) if noise is not None else None, seed, _stream_ptr()))
+        return wav, src
+
+    def hift_infer_window(self, mel, w0, cache_source=None, seed=0):
+        """hift_infer with the convolution stack over mel frames [w0, T) only: samples before (w0 + 20) * 480 are not valid."""
+        mel = mel.contiguous().float()
+        T = mel.shape[0]
+        wav = torch.zeros(1, 480 * T, device=mel.device, dtype=torch.float32)
+        src = torch.empty(1, 1, 480 * T, device=mel.device, dtype=torch.float32)
+        m = 0 if cache_source is None else cache_source.shape[-1]
+        cptr = C.c_void_p(cache_source.contiguous().data_ptr()) if m else None
+        L.check(self.lib.cbx_hift_infer_window(self.h, C.c_void_p(mel.data_ptr()), T, cptr, m, C.c_void_p(wav.data_ptr()), C.c_void_p(src.data_ptr()),
+                                               seed, int(w0), _stream_ptr()))
         return wav, src
 
     def hift_f0(self, mel):

@@ -466,7 +466,10 @@ int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_call
                 if (c.cache_source_d && c.cache_source_d == calls[a].source_out_d) CBX_CHECK(cudaStreamWaitEvent(hs, L.ev_call[a], 0));
         }
         CBX_CHECK(cudaMemcpyAsync(S.mel, L.melb + b * mel_bs, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, hs));
-        hift_infer(e, S, 2 * c.n, c.cache_source_d, c.m > Ls ? Ls : c.m, c.wav_out_d, c.source_out_d, nullptr, nullptr, c.seed, hs);
+        // decode window: the caller only consumes wav_out[emit_from:] ("full" overlap: the audio of earlier slices has been sent)
+        int w0 = 0;
+        if (c.emit_from > 0) { w0 = (int)(std::min<int64_t>(c.emit_from, Ls) / H_UP) - HIFT_WINDOW_MARGIN; if (w0 < 0) w0 = 0; if (w0 >= 2 * c.n) w0 = 2 * c.n - 1; }
+        hift_infer(e, S, 2 * c.n, c.cache_source_d, c.m > Ls ? Ls : c.m, c.wav_out_d, c.source_out_d, nullptr, nullptr, c.seed, hs, nullptr, w0);
         if (c.mel_out_d) CBX_CHECK(cudaMemcpyAsync(c.mel_out_d, S.mel, (size_t)2 * c.n * MEL * 4, cudaMemcpyDeviceToDevice, hs));
         if (!prof_enabled()) CBX_CHECK(cudaEventRecord(L.ev_call[b], hs));
     }
@@ -537,6 +540,22 @@ int cbx_op_attention(const void* qkv, void* out, int T, int H, int batch, int ca
     AttnParams a; a.q = (const bf16*)qkv; a.k = a.q + H * 64; a.v = a.q + 2 * H * 64; a.ldq = a.ldk = a.ldv = ld; a.q_bs = a.k_bs = a.v_bs = (long)T * ld;
     a.o = (bf16*)out; a.ldo = H * 64; a.o_bs = (long)T * H * 64; a.T = T; a.H = H; a.batch = batch; a.causal = causal; a.scale = 0.125f;
     launch_attention(a, (cudaStream_t)stream);
+    CBX_API_END
+}
+
+// windowed vocoder decode (tests): as cbx_hift_infer, the convolution stack over mel frames [w0, frames) only
+int cbx_hift_infer_window(cbx_engine* e, const float* mel_d, int frames, const float* cache_source_d, int64_t m, float* wav_out_d, float* source_out_d,
+                          uint64_t seed, int w0, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && mel_d && wav_out_d && source_out_d, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    Lane& L = pick_lane(e);
+    std::lock_guard<std::mutex> g(L.lock);
+    StreamBridge br((cudaStream_t)stream, L.st, L.ev_in, L.ev_out);
+    CBX_REQUIRE(frames >= 1 && frames <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
+    CBX_CHECK(cudaMemcpyAsync(L.mel, mel_d, (size_t)frames * MEL * 4, cudaMemcpyDeviceToDevice, L.st));
+    hift_infer(e, L, frames, cache_source_d, m, wav_out_d, source_out_d, nullptr, nullptr, seed, L.st, nullptr, w0);
+    br.finish();
     CBX_API_END
 }
 

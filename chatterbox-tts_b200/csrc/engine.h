@@ -136,7 +136,8 @@ void flow_infer(cbx_engine* e, Lane& L, const Voice& v, const int* tokens_h, int
 
 void hift_build(cbx_engine* e);
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
-                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr);
+                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn = nullptr, int w0 = 0);
+constexpr int HIFT_WINDOW_MARGIN = 20;     // mel frames between the start of a decode window and the first sample that equals the full decode
 void flow_stage(cbx_engine* e, Lane& L, const int* const* tokens_h, cudaStream_t st);   // L.nb / L.call[] set by the caller
 bool flow_tail_path(long rows);                                                          // fused block-tail kernels for a call of this many estimator rows?
 void flow_run(cbx_engine* e, Lane& L, cudaStream_t st);                                  // -> L.melb

@@ -114,14 +114,24 @@ void hift_source(cbx_engine* e, Lane& L, const float* f0, int Tg, const float* c
     e->gpu_launches += 2;
 }
 
+// Decode window.  The reference's "full" overlap strategy re-synthesises every accumulated token of a text chunk for each slice and
+// then emits only wav[previous_length:] (src/tts_streaming.py:694-699).  The vocoder is LOCAL: apart from the sine source (whose
+// phase accumulates from the first frame -- F0 predictor, source and its STFT are therefore always computed in full, they are
+// cheap), an output sample depends on mel frames within the receptive field of conv_pre, the three upsample stages and their
+// resblocks (kernel 11, dilations 1 / 3 / 5: 60 samples at the stage's rate) -- under 20 mel frames in total.  With `w0` > 0 the
+// convolution stack runs on mel frames [w0, Tg) only; rows left of the window are read as context (real data for conv_pre, stale
+// but finite data deeper in the stack), so samples from (w0 + HIFT_WINDOW_MARGIN) * 480 on are IDENTICAL to the full decode
+// (tests/test_gpu_parity.py::test_hift_window_is_exact); earlier samples of wav_out are left untouched.
 void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long m, float* wav_out, float* src_out,
-                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn) {
+                const float* phase_h, const float* noise_dev, unsigned long long seed, cudaStream_t st, const SourceDyn* dyn, int w0) {
     HiftModel& h = e->hift;
     CBX_REQUIRE(Tg >= 1 && Tg <= 2 * e->cfg.max_s3_tokens, "hift: mel length out of range");
+    CBX_REQUIRE(w0 >= 0 && w0 < Tg, "hift: decode window starts beyond the mel");
     const long Ls = (long)Tg * H_UP, F = 120L * Tg + 1;
     CBX_REQUIRE(m >= 0, "hift: negative cache_source length");
     if (m > Ls) m = Ls;
     const long tlen[4] = {Tg, 8L * Tg, 40L * Tg, F};
+    const long off[4] = {w0, 8L * w0, 40L * w0, 120L * w0};        // first row of the window at every stage's rate
     auto zero_tail = [&](bf16* buf, long T, int C) { CBX_CHECK(cudaMemsetAsync(buf + (H_HALO + T) * C, 0, (size_t)H_HALO * C * 2, st)); };
     zero_tail(L.h_stft, F, H_NSRC_PAD);
     for (int i = 0; i < 4; i++) zero_tail(L.h_xb[i], tlen[i], H_BASE >> i);
@@ -131,41 +141,44 @@ void hift_infer(cbx_engine* e, Lane& L, int Tg, const float* cache_src_dev, long
     launch_stft16(src_out, Ls, L.h_stft + (long)H_HALO * H_NSRC_PAD, H_NSRC_PAD, (int)F, st);
     // ---- conv_pre (+ the leaky_relu that precedes ups[0])
     {
-        GemmParams g = conv(h.conv_pre, L.h_mel, MEL_PAD, 7, 1, Tg);
-        g.act = ACT_LRELU; g.act_param = 0.1f; g.outB = L.h_xb[0] + (long)H_HALO * H_BASE; g.ldc = H_BASE;
+        GemmParams g = conv(h.conv_pre, L.h_mel + off[0] * MEL_PAD, MEL_PAD, 7, 1, (int)(Tg - off[0]));
+        g.act = ACT_LRELU; g.act_param = 0.1f; g.outB = L.h_xb[0] + (H_HALO + off[0]) * H_BASE; g.ldc = H_BASE;
         launch_gemm(g, st);
     }
     e->gpu_launches += 2;
     for (int i = 0; i < 3; i++) {
         const int cin_i = H_BASE >> i, ch = H_BASE >> (i + 1), u = UPS_U[i], k = UPS_K[i], p = (k - u) / 2, taps = (k + u - 1) / u;
-        const long Tin = tlen[i], Tout = tlen[i + 1];
+        const long Tin = tlen[i] - off[i], Tout = tlen[i + 1] - off[i + 1], oi = off[i], oo = off[i + 1];
         const int shift = (i == 2) ? 1 : 0;   // ReflectionPad1d((1,0)) after the last upsample
         // transposed conv as one GEMM over all u phases; row q covers outputs q*u - p + [0,u)
         GemmParams g;
-        g.A = L.h_xb[i] + (long)(H_HALO - (taps - 1)) * cin_i; g.lda = cin_i; g.kc = cin_i; g.tap_stride = cin_i;
+        g.A = L.h_xb[i] + (H_HALO - (taps - 1) + oi) * cin_i; g.lda = cin_i; g.kc = cin_i; g.tap_stride = cin_i;
         g.W = h.ups[i].w; g.ldw = h.ups[i].K; g.M = (int)Tin + 1; g.N = u * ch; g.K = taps * cin_i; g.bias = h.ups[i].b;
-        g.outF = L.h_x[i] + (long)(shift - p) * ch; g.ldc = (long)u * ch;
+        g.outF = L.h_x[i] + (shift - p + oo) * ch; g.ldc = (long)u * ch;
         g.ct_u = u; g.ct_cout = ch; g.ct_pad = p; g.ct_len = (int)(Tin * u);
         launch_gemm(g, st);
-        if (shift) launch_copy_row(L.h_x[i], L.h_x[i] + 2L * ch, ch, st);
+        if (shift && w0 == 0) launch_copy_row(L.h_x[i], L.h_x[i] + 2L * ch, ch, st);
         // source fusion: strided conv of the source STFT, source resblock, x += si
         GemmParams s;
-        s.A = L.h_stft + (long)(H_HALO - SD_PAD[i]) * H_NSRC_PAD; s.lda = (long)SD_STRIDE[i] * H_NSRC_PAD; s.kc = H_NSRC_PAD; s.tap_stride = H_NSRC_PAD;
-        s.W = h.sdown[i].w; s.ldw = h.sdown[i].K; s.M = (int)Tout; s.N = ch; s.K = h.sdown[i].K; s.bias = h.sdown[i].b; s.outF = L.h_si[i]; s.ldc = ch;
+        s.A = L.h_stft + (H_HALO - SD_PAD[i] + oo * SD_STRIDE[i]) * H_NSRC_PAD; s.lda = (long)SD_STRIDE[i] * H_NSRC_PAD; s.kc = H_NSRC_PAD; s.tap_stride = H_NSRC_PAD;
+        s.W = h.sdown[i].w; s.ldw = h.sdown[i].K; s.M = (int)Tout; s.N = ch; s.K = h.sdown[i].K; s.bias = h.sdown[i].b; s.outF = L.h_si[i] + oo * ch; s.ldc = ch;
         launch_gemm(s, st);
-        resblock(e, h.sres[i], L.h_si[i], L.h_si[i], L.h_a[i], L.h_b[i], (int)Tout, RbOut{L.h_x[i], 1, 1.f, nullptr, 0, 0.f}, st);
+        bf16 *ha = L.h_a[i] + oo * ch, *hb = L.h_b[i] + oo * ch;      // haloed buffers: the "halo" left of the window is earlier rows
+        float *x = L.h_x[i] + oo * ch, *si = L.h_si[i] + oo * ch, *acc = L.h_acc[i] + oo * ch, *r = L.h_r[i] + oo * ch;
+        resblock(e, h.sres[i], si, si, ha, hb, (int)Tout, RbOut{x, 1, 1.f, nullptr, 0, 0.f}, st);
         for (int kk = 0; kk < 3; kk++) {
-            RbOut fo{L.h_acc[i], kk > 0, 1.f / 3.f, nullptr, 0, 0.f};
-            if (kk == 2) { fo.outB2 = L.h_xb[i + 1] + (long)H_HALO * ch; fo.act2 = ACT_LRELU; fo.act2_param = (i == 2) ? 0.01f : 0.1f; }
-            resblock(e, h.res[i * 3 + kk], L.h_x[i], L.h_r[i], L.h_a[i], L.h_b[i], (int)Tout, fo, st);
+            RbOut fo{acc, kk > 0, 1.f / 3.f, nullptr, 0, 0.f};
+            if (kk == 2) { fo.outB2 = L.h_xb[i + 1] + (H_HALO + oo) * ch; fo.act2 = ACT_LRELU; fo.act2_param = (i == 2) ? 0.01f : 0.1f; }
+            resblock(e, h.res[i * 3 + kk], x, r, ha, hb, (int)Tout, fo, st);
         }
         e->gpu_launches += 3;
     }
     {
-        GemmParams g = conv(h.conv_post, L.h_xb[3], H_BASE >> 3, 7, 1, (int)F);
-        g.outF = L.h_post; g.ldc = H_NSRC;
+        GemmParams g = conv(h.conv_post, L.h_xb[3] + off[3] * (H_BASE >> 3), H_BASE >> 3, 7, 1, (int)(F - off[3]));
+        g.outF = L.h_post + off[3] * H_NSRC; g.ldc = H_NSRC;
         launch_gemm(g, st);
     }
-    launch_istft16(L.h_post, H_NSRC, (int)F, wav_out, Ls, 0.99f, h.fade, 960, st);
+    // frames left of the window hold stale rows: start far enough inside it that every frame a sample reads has been computed
+    launch_istft16(L.h_post, H_NSRC, (int)F, wav_out, Ls, 0.99f, h.fade, 960, w0 > 0 ? 4 * (off[3] + 4) : 0, st);
     e->gpu_launches += 2;
 }

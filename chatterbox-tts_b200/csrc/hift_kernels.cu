@@ -100,9 +100,9 @@ __global__ void stft16_kernel(const float* __restrict__ s, long L, bf16* out, lo
 }
 
 // y[F][18] (fp32: 9 log-magnitudes, 9 phase pre-activations) -> wav[4*(F-1)], with clamp and leading trim-fade
-__global__ void istft16_kernel(const float* __restrict__ y, long ldy, int F, float* wav, long L, float limit, const float* __restrict__ fade, int fade_len) {
+__global__ void istft16_kernel(const float* __restrict__ y, long ldy, int F, float* wav, long L, float limit, const float* __restrict__ fade, int fade_len, long n0) {
     pdl_prologue();
-    long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long n = n0 + (long)blockIdx.x * blockDim.x + threadIdx.x;      // samples [n0, L): a decode window leaves the earlier ones alone
     if (n >= L) return;
     // frames f with 0 <= n + 8 - 4f < 16
     int fhi = (int)((n + 8) >> 2);
@@ -209,9 +209,10 @@ void launch_stft16(const float* s, long L, bf16* out, long ld, int F, cudaStream
     launch_pdl(stft16_kernel, g1(F, 128), dim3(128), 0, st, s, L, out, ld, F);
     CBX_CHECK(cudaGetLastError());
 }
-void launch_istft16(const float* y, long ldy, int F, float* wav, long L, float limit, const float* fade, int fade_len, cudaStream_t st) {
+void launch_istft16(const float* y, long ldy, int F, float* wav, long L, float limit, const float* fade, int fade_len, long n0, cudaStream_t st) {
     ProfScope ps(PC_HIFT_MISC, (double)F * ldy * 4 + (double)L * 4, st);
-    launch_pdl(istft16_kernel, dim3(g1(L)), dim3(256), 0, st, y, ldy, F, wav, L, limit, fade, fade_len);
+    if (n0 >= L) return;
+    launch_pdl(istft16_kernel, dim3(g1(L - n0)), dim3(256), 0, st, y, ldy, F, wav, L, limit, fade, fade_len, n0);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_snake_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, const float* alpha, cudaStream_t st) {

@@ -18,7 +18,7 @@ void hift_init_constants();
 void launch_f0_classifier(const bf16* x, long ld, const float* w, const float* b, float* f0, int T, int C, cudaStream_t st);
 void launch_source(const SourceParams& p, int T, cudaStream_t st);
 void launch_stft16(const float* s, long L, bf16* out, long ld, int F, cudaStream_t st);
-void launch_istft16(const float* y, long ldy, int F, float* wav, long L, float limit, const float* fade, int fade_len, cudaStream_t st);
+void launch_istft16(const float* y, long ldy, int F, float* wav, long L, float limit, const float* fade, int fade_len, long n0, cudaStream_t st);
 void launch_snake_rows(const float* in, long ld_in, bf16* out, long ld_out, int rows, int C, const float* alpha, cudaStream_t st);
 void launch_relpos_table(bf16* out, int T, int D, cudaStream_t st);
 void launch_copy_row(float* dst, const float* src, int C, cudaStream_t st);

@@ -99,12 +99,20 @@ typedef struct cbx_s3gen_call {
     const float* cache_source_d; int64_t m;
     float* wav_out_d; float* source_out_d; float* mel_out_d /* optional */;
     uint64_t seed;
+    /* The caller only reads wav_out_d[emit_from:] (the reference's "full" overlap emits wav[previous_length:], :694-699): the
+     * vocoder's convolution stack then runs on a window that starts a receptive field before that sample; samples from emit_from
+     * on equal the full decode exactly, earlier ones are left untouched.  source_out_d is always complete.  0 = everything. */
+    int64_t emit_from;
 } cbx_s3gen_call;
 int cbx_s3gen_infer_batch(cbx_engine* e, const cbx_s3gen_call* calls, int n_calls, void* stream);
 /* the two halves of the call above, for teacher-forced parity checks */
 int cbx_flow_infer(cbx_engine* e, int voice, const int32_t* tokens_h, int n, float* mel_out_d, void* stream);
 int cbx_hift_infer(cbx_engine* e, const float* mel_d /*[frames][80]*/, int frames, const float* cache_source_d, int64_t m,
                    float* wav_out_d, float* source_out_d, const float* phase_h, const float* noise_d, uint64_t seed, void* stream);
+
+/* cbx_hift_infer with the convolution stack restricted to mel frames [w0, frames): samples from (w0 + 20) * 480 on equal the full decode */
+int cbx_hift_infer_window(cbx_engine* e, const float* mel_d, int frames, const float* cache_source_d, int64_t m, float* wav_out_d,
+                          float* source_out_d, uint64_t seed, int w0, void* stream);
 
 /* HiFT stages for parity tests: mel -> f0 (ConvRNNF0Predictor) and f0 -> source (SineGen + SourceModuleHnNSF) */
 int cbx_hift_f0(cbx_engine* e, const float* mel_d, int frames, float* f0_out_d, void* stream);

@@ -31,9 +31,9 @@ class BatchNative:
     def s3gen_infer_batch(self, calls):
         if self.gate is not None:
             self.gate.wait(5)
-        self.batches.append([(len(t), ("chain", c) if isinstance(c, int) else ("tensor" if c is not None else None)) for _, t, c, _ in calls])
+        self.batches.append([(len(t), ("chain", c) if isinstance(c, int) else ("tensor" if c is not None else None)) for _, t, c, *_ in calls])
         outs = []
-        for voice, toks, cache, seed in calls:
+        for voice, toks, cache, seed, *_ in calls:
             if isinstance(cache, int):
                 cache = outs[cache][1]            # the vocoder of a batch runs in call order: the earlier source exists
             outs.append(FakeModel.s3gen(toks, cache))

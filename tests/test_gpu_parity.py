@@ -425,3 +425,29 @@ def test_crossfade_pcm(tiny, dev):
     cur = (torch.rand(5000, generator=g) * 2.4 - 1.2).to(dev)
     out2 = eng.crossfade_pcm(cur, 5000)
     assert torch.equal(out2, (torch.clamp(cur, -1.0, 1.0) * 32767).to(torch.int16))
+
+
+@pytest.mark.parametrize("T,w0", [(140, 60), (280, 200), (280, 37), (70, 10), (380, 300), (64, 0)])
+def test_hift_window_is_exact(tiny, dev, T, w0):
+    """The vocoder's decode window ("full" overlap emits only wav[previous_length:], reference :694-699): with the convolution
+    stack run over mel frames [w0, T) only, every sample from (w0 + HIFT_WINDOW_MARGIN) * 480 on is BIT-IDENTICAL to the full
+    decode, and the source (whose phase accumulates from frame 0) is identical everywhere."""
+    eng = tiny[0]
+    g = torch.Generator().manual_seed(T + w0)
+    mel = (torch.randn(T, 80, generator=g) * 2.0 - 5.0).to(dev)
+    cache = (torch.randn(1, 1, 480 * (T // 2), generator=g) * 0.01).to(dev)
+    full, src_full = eng.hift_infer(mel, cache_source=cache, seed=9)
+    win, src_win = eng.hift_infer_window(mel, w0, cache_source=cache, seed=9)
+    torch.cuda.synchronize()
+    assert torch.equal(src_full, src_win)
+    first = (w0 + 20) * 480
+    assert torch.equal(full[0, first:], win[0, first:]), "window differs inside the guaranteed region"
+    if w0 == 0:
+        assert torch.equal(full, win)
+        return
+    # the margin is not vacuous: close to the window's left edge the stale context does show
+    assert not torch.equal(full[0, w0 * 480: (w0 + 2) * 480], win[0, w0 * 480: (w0 + 2) * 480])
+    # and how much margin is really needed (reported by the failure message if the guarantee ever breaks)
+    diff = (full[0] != win[0]).nonzero().flatten()
+    last_bad = int(diff[diff >= w0 * 480].max()) if (diff >= w0 * 480).any() else w0 * 480
+    assert last_bad < (w0 + 16) * 480, f"contamination reaches {(last_bad - w0 * 480) / 480:.1f} frames into the window"

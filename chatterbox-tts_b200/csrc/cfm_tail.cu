@@ -139,10 +139,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result): one
-// reciprocal and one exp2 on the SFU plus ten FMAs, branch-free -- libdevice's erff costs about three times as many issue
-// slots, and the GELU of a 128 x 1024 tile is what the element-wise warps spend most of their time on.
-__device__ __forceinline__ float gelu_fast(float x) {
+// GELU of the feed-forward's hidden units, written to tensor memory as bf16.  The reference applies the erf form; here
+// 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with ONE MUFU (tanh.approx) and four FMA-pipe instructions per element.  Its
+// distance to the erf form is at most 4.7e-4 ABSOLUTE (around |x| = 2.3), i.e. under a tenth of the bf16 rounding the value gets
+// right after (half an ulp at |x| = 2 is 7.8e-3), and the GELU of a 128 x 1024 tile is what the element-wise warps spend their
+// time on: the Abramowitz-Stegun erf used before (|error| 1.5e-7, a reciprocal and an exp2 on the XU pipe plus ten FMAs) made the
+// feed-forward loop XU-bound at 1.22 us per 64-unit chunk against 0.74 us of weight streaming.  CBX_CFM_TAIL_GELU_ERF=1 (read at
+// launch, mode bit 32) selects the erf form for A/B parity runs.
+__device__ __forceinline__ float gelu_erf_as(float x) {
     const float a = fabsf(x) * 0.70710678118654752f;
     float t;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.f)));
@@ -155,6 +159,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * a * a));
     const float e = 1.f - p * ex;                                       // erf(|x| / sqrt 2)
     return 0.5f * x * (1.f + copysignf(e, x));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 
 // A operand from tensor memory (rows = lanes, two bf16 per 32-bit column along K), B from shared memory
@@ -434,11 +445,20 @@ __global__ void __launch_bounds__(THREADS, 1) cfm_tail_kernel(const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) pk[i >> 1] = __uint_as_float(pack_bf16(v[i], v[i + 1]));
                 } else {
+                    if (p.mode & 32) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(b0 + i);
-                        pk[i >> 1] = __uint_as_float(pack_bf16(gelu_fast(v[i] + bb.x), gelu_fast(v[i + 1] + bb.y)));
-                        pk[(i >> 1) + 1] = __uint_as_float(pack_bf16(gelu_fast(v[i + 2] + bb.z), gelu_fast(v[i + 3] + bb.w)));
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(b0 + i);
+                            pk[i >> 1] = __uint_as_float(pack_bf16(gelu_erf_as(v[i] + bb.x), gelu_erf_as(v[i + 1] + bb.y)));
+                            pk[(i >> 1) + 1] = __uint_as_float(pack_bf16(gelu_erf_as(v[i + 2] + bb.z), gelu_erf_as(v[i + 3] + bb.w)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(b0 + i);
+                            pk[i >> 1] = __uint_as_float(pack_bf16(gelu_fast(v[i] + bb.x), gelu_fast(v[i + 1] + bb.y)));
+                            pk[(i >> 1) + 1] = __uint_as_float(pack_bf16(gelu_fast(v[i + 2] + bb.z), gelu_fast(v[i + 3] + bb.w)));
+                        }
                     }
                 }
                 tmem_st16(trow + SB + 64 * (j & 1) + hh * 32, pk);   // G_j overwrites the first half of this thread's own score columns
@@ -561,7 +581,10 @@ void launch_cfm_tail(const CfmTailArgs& a, const bf16* attn_o, const CfmTailWeig
     if (a.mode & CFM_TAIL_FF) flops += 4.0 * a.M * C * CF;
     if (a.mode & CFM_TAIL_QKV) flops += 2.0 * a.M * C * NQKV;
     ProfScope ps(PC_GEMM, flops, st);
-    launch_pdl(cfm_tail_kernel, dim3(cdiv(a.M, TM)), dim3(THREADS), SMEM, st, tmO, *mo, *m0, *m2, *mq, tmH, tmQ, a);
+    static const bool gelu_erf = [] { const char* e = getenv("CBX_CFM_TAIL_GELU_ERF"); return e && e[0] == '1'; }();
+    CfmTailArgs aa = a;
+    if (gelu_erf) aa.mode |= 32;
+    launch_pdl(cfm_tail_kernel, dim3(cdiv(a.M, TM)), dim3(THREADS), SMEM, st, tmO, *mo, *m0, *m2, *mq, tmH, tmQ, aa);
     CBX_CHECK(cudaGetLastError());
     g_launches++;
 }

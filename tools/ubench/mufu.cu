@@ -43,6 +43,8 @@ __global__ void k(float* out, long long* cyc, float a, float b, int iters) {
 #pragma unroll
         for (int i = 0; i < 64; i += 2) {
             if (MODE == 0) { s[i] = ex2(s[i]); s[i + 1] = ex2(s[i + 1]); }
+            else if (MODE == 3) { asm volatile("tanh.approx.f32 %0, %0;" : "+f"(s[i])); asm volatile("tanh.approx.f32 %0, %0;" : "+f"(s[i + 1])); }
+            else if (MODE == 4) { asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(s[i])); asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(s[i + 1])); }
             else {
                 float e0 = ex2(fmaf(s[i], a, b)), e1 = ex2(fmaf(s[i + 1], a, b));
                 l0 += e0; l1 += e1;
@@ -60,19 +62,21 @@ __global__ void k(float* out, long long* cyc, float a, float b, int iters) {
 int main() {
     float* out; long long* cyc; cudaMalloc(&out, 1 << 24); cudaMalloc(&cyc, 8);
     const int iters = 200;
-    for (int mode = 0; mode < 3; mode++)
+    for (int mode = 0; mode < 5; mode++)
         for (int threads : {128, 256, 512}) {
             long long c = 0;
             for (int rep = 0; rep < 2; rep++) {
                 if (mode == 0) k<0><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
                 if (mode == 1) k<1><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
                 if (mode == 2) k<2><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
+                if (mode == 3) k<3><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
+                if (mode == 4) k<4><<<148, threads>>>(out, cyc, -0.5f, -0.25f, iters);
                 cudaDeviceSynchronize();
             }
             cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
             const double per_sub = (double)iters * 64 * (threads / 128);      // warp-wide ex2 per sub-partition
             printf("mode %d (%s) warps/subpartition %d: %.2f cycles per warp-wide EX2 per sub-partition (%s)\n", mode,
-                   mode == 0 ? "ex2 only" : mode == 1 ? "ffma+ex2+fadd+fadd" : "ffma+ex2+fadd+fadd+pack", threads / 128, (double)c / per_sub, cudaGetErrorString(cudaGetLastError()));
+                   mode == 0 ? "ex2 only" : mode == 1 ? "ffma+ex2+fadd+fadd" : mode == 2 ? "ffma+ex2+fadd+fadd+pack" : mode == 3 ? "tanh.approx only" : "rcp.approx only", threads / 128, (double)c / per_sub, cudaGetErrorString(cudaGetLastError()));
         }
     for (int pk = 0; pk < 2; pk++)
         for (int threads : {128, 256}) {

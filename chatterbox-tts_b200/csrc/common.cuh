@@ -27,9 +27,21 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // ---------------------------------------------------------------- activations
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_LRELU = 4, ACT_ELU = 5, ACT_SNAKE = 6 };
 
+// GELU of a bf16-bound activation: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with tanh.approx (one MUFU).  The reference
+// applies the erf form; the two differ by at most 4.7e-4 absolute, a tenth of the bf16 rounding the value gets right after, and
+// libdevice's erff costs ~30 issue slots per element in the epilogue of the widest GEMM of a CFM block.  (The fp32 conditioning
+// encoders keep the exact erf form, cond.cu.)
+__device__ __forceinline__ float gelu_tanh_form(float x) {
+    const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+
 __device__ __forceinline__ float act_apply(int act, float v, float param) {
     switch (act) {
-        case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+        case ACT_GELU: return gelu_tanh_form(v);
         case ACT_SILU: return v / (1.f + expf(-v));
         case ACT_MISH: {
             float sp = v > 20.f ? v : log1pf(expf(v));
@@ -49,7 +61,7 @@ template <int ACT>
 __device__ __forceinline__ void act_apply8(float (&v)[8], const float (&alpha)[8] /*per-column parameter (snake alpha / lrelu slope)*/) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        if constexpr (ACT == ACT_GELU) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+        if constexpr (ACT == ACT_GELU) v[i] = gelu_tanh_form(v[i]);
         else if constexpr (ACT == ACT_SILU) v[i] = v[i] / (1.f + expf(-v[i]));
         else if constexpr (ACT == ACT_MISH) { float sp = v[i] > 20.f ? v[i] : log1pf(expf(v[i])); v[i] = v[i] * tanhf(sp); }
         else if constexpr (ACT == ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : v[i] * alpha[i];

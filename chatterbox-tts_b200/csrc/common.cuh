@@ -39,18 +39,22 @@ __device__ __forceinline__ float gelu_tanh_form(float x) {
     return fmaf(hx, t, hx);
 }
 
+// mish(x) = x tanh(softplus(x)) without log1p / tanh: with e = exp(x), tanh(log(1 + e)) = ((1 + e)^2 - 1) / ((1 + e)^2 + 1) = n / (n + 2),
+// n = e (e + 2).  One exp and one division on the fast paths; fp32-exact to rounding (x > 20: tanh(softplus) = 1 in fp32).
+__device__ __forceinline__ float mish_fast(float v) {
+    const float e = __expf(fminf(v, 20.f)), n = e * (e + 2.f);
+    return v > 20.f ? v : v * __fdividef(n, n + 2.f);
+}
+
 __device__ __forceinline__ float act_apply(int act, float v, float param) {
     switch (act) {
         case ACT_GELU: return gelu_tanh_form(v);
-        case ACT_SILU: return v / (1.f + expf(-v));
-        case ACT_MISH: {
-            float sp = v > 20.f ? v : log1pf(expf(v));
-            return v * tanhf(sp);
-        }
+        case ACT_SILU: return __fdividef(v, 1.f + __expf(-v));
+        case ACT_MISH: return mish_fast(v);
         case ACT_LRELU: return v > 0.f ? v : v * param;
         case ACT_ELU: return v > 0.f ? v : expm1f(v);
         case ACT_SNAKE: {
-            float s = sinf(v * param);
+            float s = __sinf(v * param);
             return v + s * s / (param + 1e-9f);
         }
         default: return v;
@@ -62,11 +66,11 @@ __device__ __forceinline__ void act_apply8(float (&v)[8], const float (&alpha)[8
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if constexpr (ACT == ACT_GELU) v[i] = gelu_tanh_form(v[i]);
-        else if constexpr (ACT == ACT_SILU) v[i] = v[i] / (1.f + expf(-v[i]));
-        else if constexpr (ACT == ACT_MISH) { float sp = v[i] > 20.f ? v[i] : log1pf(expf(v[i])); v[i] = v[i] * tanhf(sp); }
+        else if constexpr (ACT == ACT_SILU) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+        else if constexpr (ACT == ACT_MISH) v[i] = mish_fast(v[i]);
         else if constexpr (ACT == ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : v[i] * alpha[i];
         else if constexpr (ACT == ACT_ELU) v[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
-        else if constexpr (ACT == ACT_SNAKE) { float a = alpha[i]; float s = sinf(v[i] * a); v[i] = v[i] + s * s / (a + 1e-9f); }
+        else if constexpr (ACT == ACT_SNAKE) { float a = alpha[i]; float s = __sinf(v[i] * a); v[i] = v[i] + s * s / (a + 1e-9f); }
     }
 }
 

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) norm_kernel(NormParams p) {
         if (p.bias) { const float4 bb = *reinterpret_cast<const float4*>(p.bias + c); y[0] += bb.x; y[1] += bb.y; y[2] += bb.z; y[3] += bb.w; }
         if (ACT == ACT_MISH) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) { const float sp = y[j] > 20.f ? y[j] : log1pf(expf(y[j])); y[j] = y[j] * tanhf(sp); }
+            for (int j = 0; j < 4; j++) y[j] = mish_fast(y[j]);      // exp + division (common.cuh), not log1p + tanh: the Mish, not the 6 B/element, bounded this kernel
         }
         if (add) { const float4 aa = *reinterpret_cast<const float4*>(add + c); y[0] += aa.x; y[1] += aa.y; y[2] += aa.z; y[3] += aa.w; }
 #pragma unroll

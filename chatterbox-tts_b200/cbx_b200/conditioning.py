@@ -12,6 +12,7 @@ polyphase resampler as embed_ref's own 24 k -> 16 k step.
 """
 import ctypes as C
 import math
+import threading
 
 import numpy as np
 import torch
@@ -126,6 +127,10 @@ class ConditioningEncoders:
         self.kaldi80 = up(kaldi_mel_bank())
         self.eye80 = up(np.eye(80, dtype=np.float32))
         self._kern = {}
+        # one long-lived stream for every conditioning run: a request thread's fresh stream misses the caching allocator's
+        # per-stream pools, and each of the ~200 temporaries of a run would fall through to cudaMalloc
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.lock = threading.Lock()
         self.n_blocks = 0
         while f"tokenizer.encoder.blocks.{self.n_blocks}.attn_ln.weight" in self.w:
             self.n_blocks += 1
@@ -384,13 +389,14 @@ class ConditioningEncoders:
     def prepare_conditionals(self, wav, sr, speech_cond_prompt_len=150, exaggeration=0.5):
         """reference :357-384 from the decoded waveform on; returns host tensors in the layout voice_put / the reference's
         Conditionals use."""
-        x = self._dev_wave(wav)
-        wav24 = self.resample(x, sr, S3GEN_SR)
-        wav16 = self.resample(wav24, S3GEN_SR, S3_SR)
-        gen = self.embed_ref(wav24[:DEC_COND_LEN].contiguous())
-        t3_tok = self.s3_tokens_from_wav(wav16[:ENC_COND_LEN].contiguous(), max_len=speech_cond_prompt_len)
-        spk = self.voice_embed(wav16)
-        torch.cuda.current_stream(self.dev).synchronize()
+        with self.lock, torch.cuda.stream(self.stream):
+            x = self._dev_wave(wav)
+            wav24 = self.resample(x, sr, S3GEN_SR)
+            wav16 = self.resample(wav24, S3GEN_SR, S3_SR)
+            gen = self.embed_ref(wav24[:DEC_COND_LEN].contiguous())
+            t3_tok = self.s3_tokens_from_wav(wav16[:ENC_COND_LEN].contiguous(), max_len=speech_cond_prompt_len)
+            spk = self.voice_embed(wav16)
+            self.stream.synchronize()
         n = gen["prompt_token"].shape[0]
         return {"t3": {"speaker_emb": spk.cpu()[None], "cond_prompt_speech_tokens": t3_tok.cpu().long()[None], "emotion_adv": exaggeration * torch.ones(1, 1, 1)},
                 "gen": {"prompt_token": gen["prompt_token"].cpu().long()[None], "prompt_token_len": torch.tensor([n]),

@@ -603,6 +603,9 @@ class TextToSpeechEngine:
                 from .conditioning import ConditioningEncoders
                 self._cond = ConditioningEncoders(self._encoder_sd, self.cfg.cond, device=self.gpu_id)
                 self._encoder_sd = None
+                # one pass over a 10 s dummy clip (the longest the reference conditions on): the encoders' stream gets its pool of
+                # temporaries from the caching allocator now, not inside the first request that brings a new voice
+                self._cond.prepare_conditionals(np.zeros(10 * S3GEN_SR, dtype=np.float32) + 1e-3 * np.sin(np.arange(10 * S3GEN_SR) * 0.05).astype(np.float32), S3GEN_SR)
             return self._cond
 
     def prepare_conditionals(self, wav_fpath: str):

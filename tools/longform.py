@@ -28,6 +28,10 @@ async def main():
     await eng.ainit()
     eng.conditioning_encoders()          # weights resident (the reference loads its encoders in from_local as well)
     text = bench.synthetic_text(words)
+    # steady-state serving: one short request first (allocator pools, first-use sizes), as bench.py's warm-up steps do
+    async for _ in eng.stream(text=bench.synthetic_text(100, seed=7), output_format="raw_pcm", voice_id=None, request_id="warm", cancellation_token=None, **bench.REQ):
+        pass
+    torch.cuda.synchronize()
     t0 = time.time(); first = None; nbytes = 0; peak = 0
     async for chunk in eng.stream(text=text, output_format="raw_pcm", voice_id="speaker.wav", request_id="long", cancellation_token=None, **bench.REQ):
         if first is None and len(chunk):

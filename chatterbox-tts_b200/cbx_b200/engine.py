@@ -126,7 +126,11 @@ class T3Scheduler(threading.Thread):
         # chunk p50 468 ms without, 255 ms at 5 ms, 207 ms at 15 ms.  A lone request never waits (nothing else is opening).
         self.align_s = float(os.environ.get("CBX_T3_ALIGN_OPENS_MS", "30")) * 1e-3
         self.opening = 0
+        self.open_q = collections.deque()
+        self.open_gather_s = float(os.environ.get("CBX_T3_OPEN_GATHER_MS", "0.5")) * 1e-3
         self.unhealthy: Optional[BaseException] = None   # a native slot could not be closed: its pages are lost, refuse new work
+        self.opener = threading.Thread(target=self._opener, daemon=True, name="cbx-t3-opener")
+        self.opener.start()
         self.start()
 
     def open(self, voice, text_ids, cfg_w, temp, sd: SamplingDefaults, seed, max_new, on_closed=None) -> _T3Stream:
@@ -137,21 +141,69 @@ class T3Scheduler(threading.Thread):
             raise RuntimeError(f"T3 engine is unhealthy after an unrecoverable error: {self.unhealthy}")
         if not self.running:
             raise RuntimeError("engine is shutting down")
+        # Opens are handed to the opener thread: the ones that are pending at the same moment (8 requests arriving together, the
+        # text chunks of one request) are prefilled in ONE pass (cbx_t3_open_batch) instead of queueing behind each other.
+        req = {"args": (voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new), "max_new": max_new,
+               "on_closed": on_closed, "done": threading.Event(), "stream": None, "err": None}
         with self.lock:
             self.opening += 1
-        s = None
-        try:
-            with self._ctx():
-                slot = self.native.t3_open(voice, text_ids, cfg_w, temp, sd.repetition_penalty, sd.min_p, sd.top_p, seed, max_new)
-            s = _T3Stream(slot, max_new)
-            s.on_closed = on_closed
-        finally:
+            self.open_q.append(req)
+            self.lock.notify_all()
+        req["done"].wait()
+        if req["err"] is not None:
+            raise req["err"]
+        return req["stream"]
+
+    def _opener(self):
+        if self.on_gpu:
+            torch.cuda.set_device(self.native.device)
+        batchable = hasattr(self.native, "t3_open_batch")
+        while True:
             with self.lock:
-                self.opening -= 1
-                if s is not None:
-                    self.active.append(s)
+                while self.running and not self.open_q:
+                    self.lock.wait(0.5)
+                if not self.running:
+                    pend, self.open_q = list(self.open_q), collections.deque()
+                    self.opening -= len(pend)
+                    for r in pend:
+                        r["err"] = RuntimeError("engine is shutting down")
+                        r["done"].set()
+                    return
+                if batchable and self.open_gather_s > 0 and len(self.open_q) < 8:
+                    t_end = time.time() + self.open_gather_s       # companions of a burst arrive within a fraction of a millisecond
+                    while self.running and len(self.open_q) < 8:
+                        left = t_end - time.time()
+                        if left <= 0:
+                            break
+                        self.lock.wait(left)
+                batch = [self.open_q.popleft() for _ in range(min(8 if batchable else 1, len(self.open_q)))]
+            slots = None
+            if len(batch) > 1:
+                try:
+                    with self._ctx():
+                        slots = self.native.t3_open_batch([r["args"] for r in batch])
+                except BaseException:
+                    slots = None        # e.g. not enough slots / pages for all of them: open one by one, each with its own verdict
+            for i, r in enumerate(batch):
+                try:
+                    if slots is not None:
+                        slot = slots[i]
+                    else:
+                        with self._ctx():
+                            slot = self.native.t3_open(*r["args"])
+                    st = _T3Stream(slot, r["max_new"])
+                    st.on_closed = r["on_closed"]
+                    r["stream"] = st
+                except BaseException as ex:
+                    r["err"] = ex
+            with self.lock:
+                self.opening -= len(batch)
+                for r in batch:
+                    if r["stream"] is not None:
+                        self.active.append(r["stream"])
                 self.lock.notify_all()
-        return s
+            for r in batch:
+                r["done"].set()
 
     def cancel(self, s: _T3Stream):
         s.cancelled = True

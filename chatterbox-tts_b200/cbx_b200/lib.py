@@ -20,6 +20,12 @@ class S3GenCall(C.Structure):
                 ("wav_out_d", C.c_void_p), ("source_out_d", C.c_void_p), ("mel_out_d", C.c_void_p), ("seed", C.c_uint64), ("emit_from", C.c_int64)]
 
 
+class T3OpenReq(C.Structure):
+    """cbx_t3_open_req of include/cbx_b200.h"""
+    _fields_ = [("voice", C.c_int), ("text_ids_h", C.c_void_p), ("n_text", C.c_int), ("cfg_weight", C.c_float), ("temperature", C.c_float),
+                ("repetition_penalty", C.c_float), ("min_p", C.c_float), ("top_p", C.c_float), ("seed", C.c_uint64), ("max_new_tokens", C.c_int)]
+
+
 class SgemmArgs(C.Structure):
     """cbx_sgemm_args of include/cbx_b200.h"""
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("a_bs", C.c_int64), ("kc", C.c_int), ("a_stride", C.c_int), ("a_dil", C.c_int), ("a_pad", C.c_int),
@@ -47,6 +53,7 @@ SIGNATURES = {
     "cbx_voice_put": (_I, [_P, _I, _P, _P, _I, _F, _P, _I, _P, _I, _P, _P]),
     "cbx_voice_drop": (_I, [_P, _I]),
     "cbx_t3_open": (_I, [_P, _I, _P, _I, _F, _F, _F, _F, _F, _U64, _I, C.POINTER(_I), _P]),
+    "cbx_t3_open_batch": (_I, [_P, C.POINTER(T3OpenReq), _I, _P, _P]),
     "cbx_t3_step": (_I, [_P, _P, _I, _I, _P, _P]),
     "cbx_t3_set_persistent": (_I, [_P, _I]),
     "cbx_t3_poll": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), _P]),

@@ -184,6 +184,19 @@ class NativeEngine:
                                      seed, max_new, C.byref(slot), _stream_ptr()))
         return slot.value
 
+    def t3_open_batch(self, reqs):
+        """reqs: list of (voice, text_ids, cfg_weight, temperature, rep_penalty, min_p, top_p, seed, max_new) -> slots; ONE prefill
+        pass for all of them (cbx_t3_open_batch, at most 8), each stream identical to its own t3_open."""
+        arr = (L.T3OpenReq * len(reqs))()
+        keep = []
+        for i, (voice, text_ids, cfg_w, temp, rep, min_p, top_p, seed, max_new) in enumerate(reqs):
+            ids = _i32(text_ids).reshape(-1)
+            keep.append(ids)
+            arr[i] = L.T3OpenReq(voice, ids.ctypes.data, len(ids), cfg_w, temp, rep, min_p, top_p, seed, max_new)
+        slots = (C.c_int * len(reqs))()
+        L.check(self.lib.cbx_t3_open_batch(self.h, arr, len(reqs), slots, _stream_ptr()))
+        return [int(x) for x in slots]
+
     def t3_step(self, slots, n_steps=1, noise=None):
         s = _i32(slots)
         nptr = C.c_void_p(noise.data_ptr()) if noise is not None else None

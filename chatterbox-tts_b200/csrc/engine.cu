@@ -230,6 +230,24 @@ int cbx_t3_open(cbx_engine* e, int voice, const int32_t* text_ids_h, int n_text,
     CBX_API_END
 }
 
+int cbx_t3_open_batch(cbx_engine* e, const cbx_t3_open_req* reqs, int n, int* slots_out, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && e->finalized && reqs && slots_out && n >= 1 && n <= T3_PREFILL_BATCH, "bad argument");
+    T3OpenReq rq[T3_PREFILL_BATCH];
+    for (int i = 0; i < n; i++) {
+        CBX_REQUIRE(reqs[i].text_ids_h, "null text");
+        for (int k = 0; k < reqs[i].n_text; k++) CBX_REQUIRE(reqs[i].text_ids_h[k] >= 0 && reqs[i].text_ids_h[k] < T3_TEXT_V, "text id out of range");
+        rq[i] = T3OpenReq{reqs[i].voice, reqs[i].text_ids_h, reqs[i].n_text, reqs[i].cfg_weight, reqs[i].temperature, reqs[i].repetition_penalty,
+                          reqs[i].min_p, reqs[i].top_p, reqs[i].seed, reqs[i].max_new_tokens};
+    }
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    StreamBridge br((cudaStream_t)stream, e->t3_st, e->t3_ev_in, e->t3_ev_out);
+    t3_open_batch(e, rq, n, slots_out, e->t3_st);
+    br.finish();
+    CBX_API_END
+}
+
 int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps, const float* noise_d, void* stream) {
     CBX_API_BEGIN
     CBX_REQUIRE(e && e->finalized && slots_h && n_steps >= 1, "bad argument");

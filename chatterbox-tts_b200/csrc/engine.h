@@ -127,6 +127,9 @@ void t3_alloc(cbx_engine* e);
 void t3_voice_prefix(cbx_engine* e, Voice& v, const float* speaker_emb_h, const int* cond_tokens_h, int n_cond, float emotion, cudaStream_t st);
 int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w, float temp, float rep, float min_p, float top_p,
             unsigned long long seed, int max_new, cudaStream_t st);
+struct T3OpenReq { int voice; const int* text_ids_h; int L; float cfg_w, temp, rep, min_p, top_p; unsigned long long seed; int max_new; };
+constexpr int T3_PREFILL_BATCH = 8;      // requests prefilled in one pass (workspace is sized for this many)
+void t3_open_batch(cbx_engine* e, const T3OpenReq* reqs, int n, int* slots_out, cudaStream_t st);
 void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* noise_dev, cudaStream_t st);
 void t3_close(cbx_engine* e, int slot);
 

@@ -76,13 +76,13 @@ void t3_alloc(cbx_engine* e) {
     m.d_slots = e->scratch<int>(S);
     m.d_rowmap = e->scratch<int>(R);
     m.pf_max = T3_COND + c.max_text + 2;
-    const long M = 2L * m.pf_max;
+    const long M = 2L * m.pf_max * T3_PREFILL_BATCH;      // up to T3_PREFILL_BATCH requests, every sequence padded to the longest
     m.pf_x = e->scratch<float>(M * T3_D);
     m.pf_xn = e->scratch<bf16>(M * T3_D);
     m.pf_qkv = e->scratch<bf16>(M * 3 * T3_D);
     m.pf_att = e->scratch<bf16>(M * T3_D);
     m.pf_act = e->scratch<bf16>(M * T3_FFN);
-    m.pf_text = e->scratch<int>(c.max_text + 8);
+    m.pf_text = e->scratch<int>((long)(c.max_text + 8) * T3_PREFILL_BATCH);
     m.free_pages.clear();
     for (int i = m.total_pages - 1; i >= 0; i--) m.free_pages.push_back(i);
     m.slot_used.assign(S, 0);
@@ -167,64 +167,98 @@ void t3_voice_prefix(cbx_engine* e, Voice& v, const float* speaker_emb_h, const 
     e->gpu_launches += 16;
 }
 
-int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w, float temp, float rep, float min_p, float top_p,
-            unsigned long long seed, int max_new, cudaStream_t st) {
+// Prefill of n requests in ONE pass (reference: T3.inference_stream primes every generator on its own, :420-435; requests that
+// arrive together -- 8 concurrent streams, the text chunks of one request -- used to queue behind each other's ~240 launches of
+// ~10 us).  Sequences are padded to the longest (rows [2 i + cfg_row][Lmax]): norms and GEMMs are row-wise, attention is causal
+// with a key length per sequence, RoPE + KV append and the embedding assembly run per request, so every request's KV cache and
+// first logits are what its own t3_open produces (tests/test_gpu_parity.py::test_t3_open_batch_matches_single_opens).
+void t3_open_batch(cbx_engine* e, const T3OpenReq* reqs, int n, int* slots_out, cudaStream_t st) {
     T3Model& m = e->t3;
     const cbx_config& c = e->cfg;
-    CBX_REQUIRE(voice >= 0 && voice < c.n_voices && e->voices[voice].valid, "t3_open: voice slot is empty");
-    CBX_REQUIRE(L >= 1 && L <= c.max_text, "t3_open: text length out of range");
-    CBX_REQUIRE(max_new >= 1 && max_new <= m.out_stride, "t3_open: max_new_tokens out of range");
-    CBX_REQUIRE(temp > 0.f, "t3_open: temperature must be positive");
-    const int cfg_on = cfg_w > 0.f ? 1 : 0;
-    const int Lp = T3_COND + L + cfg_on;   // positions prefilled; the last BOS goes through the first decode step
-    CBX_REQUIRE(Lp + 1 + max_new <= c.max_seq, "t3_open: sequence exceeds max_seq");
-    int slot = -1;
-    for (int i = 0; i < c.max_streams; i++) if (!m.slot_used[i]) { slot = i; break; }
-    CBX_REQUIRE(slot >= 0, "t3_open: no free stream slot");
-    const int need = cdiv(Lp + 1 + max_new, PAGE);
-    CBX_REQUIRE((int)m.free_pages.size() >= 2 * need, "t3_open: KV page pool exhausted");
-    std::vector<int> pt(2 * m.max_pages, 0);
-    m.slot_pages[slot].clear();
-    for (int r = 0; r < 2; r++)
-        for (int i = 0; i < need; i++) {
-            int pg = m.free_pages.back(); m.free_pages.pop_back();
-            pt[r * m.max_pages + i] = pg; m.slot_pages[slot].push_back(pg);
-        }
-    m.slot_used[slot] = 1; m.slot_maxnew[slot] = max_new; m.slot_pos_h[slot] = Lp;
-    CBX_CHECK(cudaMemcpyAsync(m.page_table + (long)slot * 2 * m.max_pages, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, st));
-    CBX_CHECK(cudaMemcpyAsync(m.pf_text, text_ids_h, L * 4, cudaMemcpyHostToDevice, st));
-    CBX_CHECK(cudaStreamSynchronize(st));   // pt / text staging are host stack buffers
+    CBX_REQUIRE(n >= 1 && n <= T3_PREFILL_BATCH, "t3_open_batch: between 1 and 8 requests per pass");
+    int Lp[T3_PREFILL_BATCH], need[T3_PREFILL_BATCH], Lmax = 0, pages = 0, free_slots = 0;
+    for (int i = 0; i < c.max_streams; i++) free_slots += !m.slot_used[i];
+    CBX_REQUIRE(free_slots >= n, "t3_open: no free stream slot");
+    for (int i = 0; i < n; i++) {
+        const T3OpenReq& r = reqs[i];
+        CBX_REQUIRE(r.voice >= 0 && r.voice < c.n_voices && e->voices[r.voice].valid, "t3_open: voice slot is empty");
+        CBX_REQUIRE(r.L >= 1 && r.L <= c.max_text, "t3_open: text length out of range");
+        CBX_REQUIRE(r.max_new >= 1 && r.max_new <= m.out_stride, "t3_open: max_new_tokens out of range");
+        CBX_REQUIRE(r.temp > 0.f, "t3_open: temperature must be positive");
+        Lp[i] = T3_COND + r.L + (r.cfg_w > 0.f ? 1 : 0);   // positions prefilled; the last BOS goes through the first decode step
+        CBX_REQUIRE(Lp[i] + 1 + r.max_new <= c.max_seq, "t3_open: sequence exceeds max_seq");
+        need[i] = cdiv(Lp[i] + 1 + r.max_new, PAGE);
+        pages += 2 * need[i];
+        Lmax = std::max(Lmax, Lp[i]);
+    }
+    CBX_REQUIRE((int)m.free_pages.size() >= pages, "t3_open: KV page pool exhausted");
+    // nothing can fail from here on: take slots and pages
+    std::vector<int> pt((size_t)n * 2 * m.max_pages, 0), text((size_t)n * (c.max_text + 8), 0);
+    for (int i = 0, s0 = 0; i < n; i++) {
+        int slot = -1;
+        for (int k = s0; k < c.max_streams; k++) if (!m.slot_used[k]) { slot = k; break; }
+        s0 = slot + 1;
+        slots_out[i] = slot;
+        m.slot_pages[slot].clear();
+        for (int r = 0; r < 2; r++)
+            for (int k = 0; k < need[i]; k++) {
+                int pg = m.free_pages.back(); m.free_pages.pop_back();
+                pt[((size_t)i * 2 + r) * m.max_pages + k] = pg; m.slot_pages[slot].push_back(pg);
+            }
+        m.slot_used[slot] = 1; m.slot_maxnew[slot] = reqs[i].max_new; m.slot_pos_h[slot] = Lp[i];
+        std::copy(reqs[i].text_ids_h, reqs[i].text_ids_h + reqs[i].L, text.begin() + (size_t)i * (c.max_text + 8));
+        CBX_CHECK(cudaMemcpyAsync(m.page_table + (long)slot * 2 * m.max_pages, pt.data() + (size_t)i * 2 * m.max_pages, (size_t)2 * m.max_pages * 4, cudaMemcpyHostToDevice, st));
+    }
+    CBX_CHECK(cudaMemcpyAsync(m.pf_text, text.data(), text.size() * 4, cudaMemcpyHostToDevice, st));
+    CBX_CHECK(cudaStreamSynchronize(st));   // pt / text staging are host buffers of this call
 
-    AssembleParams a;
-    a.x = m.pf_x; a.prefix = e->voices[voice].prefix; a.text_emb = m.text_emb; a.text_pos = m.text_pos; a.speech_emb = m.speech_emb;
-    a.speech_pos = m.speech_pos; a.text_ids = m.pf_text; a.Lc = T3_COND; a.L = L; a.Lp = Lp; a.dim = T3_D; a.bos = T3_BOS; a.cfg_on = cfg_on;
-    launch_assemble_embeds(a, st);
-    const int M = 2 * Lp;
+    const long slab2 = 2L * Lmax;           // rows of one request (both CFG rows)
+    for (int i = 0; i < n; i++) {
+        AssembleParams a;
+        a.x = m.pf_x + i * slab2 * T3_D; a.prefix = e->voices[reqs[i].voice].prefix; a.text_emb = m.text_emb; a.text_pos = m.text_pos; a.speech_emb = m.speech_emb;
+        a.speech_pos = m.speech_pos; a.text_ids = m.pf_text + (long)i * (c.max_text + 8); a.Lc = T3_COND; a.L = reqs[i].L; a.Lp = Lp[i]; a.dim = T3_D; a.bos = T3_BOS;
+        a.cfg_on = reqs[i].cfg_w > 0.f ? 1 : 0; a.slab = Lmax;
+        launch_assemble_embeds(a, st);
+    }
+    const int M = (int)(n * slab2);
     for (int li = 0; li < c.t3_layers; li++) {
         const T3Layer& l = m.layers[li];
-        NormParams n; n.in = m.pf_x; n.ld_in = T3_D; n.rows = M; n.C = T3_D; n.gain = l.ln1; n.rms = 1; n.eps = 1e-5f; n.outB = m.pf_xn; n.ld_outB = T3_D;
-        launch_norm(n, st);
+        NormParams nn; nn.in = m.pf_x; nn.ld_in = T3_D; nn.rows = M; nn.C = T3_D; nn.gain = l.ln1; nn.rms = 1; nn.eps = 1e-5f; nn.outB = m.pf_xn; nn.ld_outB = T3_D;
+        launch_norm(nn, st);
         GemmParams g; g.A = m.pf_xn; g.lda = T3_D; g.kc = T3_D; g.W = l.wqkv; g.ldw = T3_D; g.M = M; g.N = 3 * T3_D; g.K = T3_D; g.outB = m.pf_qkv; g.ldc = 3 * T3_D;
         launch_gemm(g, st);
-        RopeKvParams r; r.qkv = m.pf_qkv; r.Lp = Lp; r.H = T3_H; r.kv = m.kv + li * m.kv_layer_stride; r.kv_half = m.kv_half;
-        r.page_table = m.page_table; r.max_pages = m.max_pages; r.row0 = slot * 2; r.inv_freq = m.inv_freq;
-        launch_rope_kv_prefill(r, st);
+        for (int i = 0; i < n; i++) {
+            RopeKvParams r; r.qkv = m.pf_qkv + i * slab2 * 3 * T3_D; r.Lp = Lp[i]; r.slab = Lmax; r.H = T3_H; r.kv = m.kv + li * m.kv_layer_stride; r.kv_half = m.kv_half;
+            r.page_table = m.page_table; r.max_pages = m.max_pages; r.row0 = slots_out[i] * 2; r.inv_freq = m.inv_freq;
+            launch_rope_kv_prefill(r, st);
+        }
         AttnParams at; at.q = m.pf_qkv; at.k = m.pf_qkv + T3_D; at.v = m.pf_qkv + 2 * T3_D; at.ldq = at.ldk = at.ldv = 3 * T3_D;
-        at.q_bs = at.k_bs = at.v_bs = (long)Lp * 3 * T3_D; at.o = m.pf_att; at.ldo = T3_D; at.o_bs = (long)Lp * T3_D; at.T = Lp; at.H = T3_H; at.batch = 2;
+        at.q_bs = at.k_bs = at.v_bs = (long)Lmax * 3 * T3_D; at.o = m.pf_att; at.ldo = T3_D; at.o_bs = (long)Lmax * T3_D; at.T = Lmax; at.H = T3_H; at.batch = 2 * n;
         at.causal = 1; at.scale = 0.125f;
+        if (n > 1) { at.kv_div = 2; for (int i = 0; i < n; i++) at.kv_len[i] = Lp[i]; }
         launch_attention(at, st);
         GemmParams o; o.A = m.pf_att; o.lda = T3_D; o.kc = T3_D; o.W = l.wo; o.ldw = T3_D; o.M = M; o.N = T3_D; o.K = T3_D; o.res = m.pf_x; o.ldr = T3_D; o.outF = m.pf_x; o.ldc = T3_D;
         launch_gemm(o, st);
-        n.gain = l.ln2; launch_norm(n, st);
+        nn.gain = l.ln2; launch_norm(nn, st);
         GemmParams gu; gu.A = m.pf_xn; gu.lda = T3_D; gu.kc = T3_D; gu.W = l.wgu; gu.ldw = T3_D; gu.M = M; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.glu = 1; gu.outB = m.pf_act; gu.ldc = T3_FFN;
         launch_gemm(gu, st);
         GemmParams d; d.A = m.pf_act; d.lda = T3_FFN; d.kc = T3_FFN; d.W = l.wd; d.ldw = T3_FFN; d.M = M; d.N = T3_D; d.K = T3_FFN; d.res = m.pf_x; d.ldr = T3_D; d.outF = m.pf_x; d.ldc = T3_D;
         launch_gemm(d, st);
     }
-    T3SlotState s{};
-    s.pos = Lp; s.step = 0; s.max_new = max_new; s.done = 0; s.cfg_w = cfg_w; s.temp = temp; s.rep_pen = rep; s.min_p = min_p; s.top_p = top_p; s.seed = seed;
-    launch_init_slot(m.slot_state, s, m.slot_pos, slot, m.seen, T3_VPAD, T3_BOS, m.x, m.speech_emb, m.speech_pos, T3_D, st);
-    e->gpu_launches += 2 + 8L * c.t3_layers;
+    for (int i = 0; i < n; i++) {
+        const T3OpenReq& r = reqs[i];
+        T3SlotState s{};
+        s.pos = Lp[i]; s.step = 0; s.max_new = r.max_new; s.done = 0; s.cfg_w = r.cfg_w; s.temp = r.temp; s.rep_pen = r.rep; s.min_p = r.min_p; s.top_p = r.top_p; s.seed = r.seed;
+        launch_init_slot(m.slot_state, s, m.slot_pos, slots_out[i], m.seen, T3_VPAD, T3_BOS, m.x, m.speech_emb, m.speech_pos, T3_D, st);
+    }
+    e->gpu_launches += 2L * n + (7L + n) * c.t3_layers;
+}
+
+int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w, float temp, float rep, float min_p, float top_p,
+            unsigned long long seed, int max_new, cudaStream_t st) {
+    T3OpenReq r{voice, text_ids_h, L, cfg_w, temp, rep, min_p, top_p, seed, max_new};
+    int slot = -1;
+    t3_open_batch(e, &r, 1, &slot, st);
     return slot;
 }
 

@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
 __global__ void assemble_embeds_kernel(const AssembleParams p) {
     pdl_prologue();
     const int t = blockIdx.x, b = blockIdx.y;
-    float* out = p.x + ((long)b * p.Lp + t) * p.dim;
+    float* out = p.x + ((long)b * (p.slab ? p.slab : p.Lp) + t) * p.dim;
     for (int d = threadIdx.x; d < p.dim; d += blockDim.x) {
         float v;
         if (t < p.Lc) v = p.prefix[(long)t * p.dim + d];
@@ -530,7 +530,7 @@ __global__ void assemble_embeds_kernel(const AssembleParams p) {
 __global__ void rope_kv_prefill_kernel(const RopeKvParams p) {
     pdl_prologue();
     const int t = blockIdx.x, b = blockIdx.y;
-    bf16* row = p.qkv + ((long)b * p.Lp + t) * (3 * p.H * HD);
+    bf16* row = p.qkv + ((long)b * (p.slab ? p.slab : p.Lp) + t) * (3 * p.H * HD);
     const int* pt = p.page_table + (long)(p.row0 + b) * p.max_pages;
     bf16* kpool = p.kv; bf16* vpool = p.kv + p.kv_half;
     for (int i = threadIdx.x; i < p.H * 32; i += blockDim.x) {

@@ -70,11 +70,12 @@ struct AssembleParams {
     const float* speech_emb = nullptr; const float* speech_pos = nullptr;
     const int* text_ids = nullptr;       // [L] device
     int Lc = 0, L = 0, Lp = 0, dim = 0, bos = 0, cfg_on = 0;
+    int slab = 0;                        // rows between the two CFG rows' sequences (0: Lp; a batched prefill pads every sequence to the longest)
 };
 void launch_assemble_embeds(const AssembleParams& p, cudaStream_t st);
 
 struct RopeKvParams {
-    bf16* qkv = nullptr; int Lp = 0; int H = 16;
+    bf16* qkv = nullptr; int Lp = 0; int H = 16; int slab = 0;     // slab: as in AssembleParams
     bf16* kv = nullptr; long kv_half = 0;
     const int* page_table = nullptr; int max_pages = 0; int row0 = 0;
     const float* inv_freq = nullptr;

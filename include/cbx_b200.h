@@ -68,6 +68,16 @@ int cbx_voice_drop(cbx_engine* e, int voice);
 int cbx_t3_open(cbx_engine* e, int voice, const int32_t* text_ids_h, int n_text, float cfg_weight, float temperature,
                 float repetition_penalty, float min_p, float top_p, uint64_t seed, int max_new_tokens, int* slot_out,
                 void* stream);
+/* Several cbx_t3_open calls as ONE prefill pass (requests that arrive together: concurrent streams, the text chunks of one
+ * request): sequences padded to the longest, causal attention with a key length per sequence.  Every stream's KV cache, first
+ * logits and sampled ids equal what its own cbx_t3_open yields.  n <= 8. */
+typedef struct cbx_t3_open_req {
+    int voice; const int32_t* text_ids_h; int n_text;
+    float cfg_weight, temperature, repetition_penalty, min_p, top_p;
+    uint64_t seed; int max_new_tokens;
+} cbx_t3_open_req;
+int cbx_t3_open_batch(cbx_engine* e, const cbx_t3_open_req* reqs, int n, int* slots_out, void* stream);
+
 /* next() on up to max_streams generators at once: n_steps decode steps for the given slots (batched rows).
  * noise_d: optional explicit Exp(1) sampling noise [n_steps][n_slots][8194] (parity tests); NULL = Philox(seed). */
 int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps, const float* noise_d, void* stream);

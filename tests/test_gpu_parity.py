@@ -451,3 +451,35 @@ def test_hift_window_is_exact(tiny, dev, T, w0):
     diff = (full[0] != win[0]).nonzero().flatten()
     last_bad = int(diff[diff >= w0 * 480].max()) if (diff >= w0 * 480).any() else w0 * 480
     assert last_bad < (w0 + 16) * 480, f"contamination reaches {(last_bad - w0 * 480) / 480:.1f} frames into the window"
+
+
+def test_t3_open_batch_matches_single_opens(tiny, tiny_cfg, dev):
+    """cbx_t3_open_batch prefills several requests in one pass (sequences padded to the longest, causal attention with a key
+    length per sequence): every stream's first logits and sampled ids must be exactly what its own cbx_t3_open produces."""
+    from cbx_b200.weights import synthetic_conditionals
+    eng, sd_dev, conds, voice = tiny
+    c2 = synthetic_conditionals(tiny_cfg, 91, prompt_tokens=17)
+    v2 = eng.voice_put("w2", c2["t3"], c2["gen"])
+    texts = [[255] + [(5 * i + 3 * k) % 700 + 1 for i in range(n)] + [0] for k, n in enumerate((9, 40, 23, 3))]
+    voices = [voice, v2, voice, v2]
+    steps = 5
+    g = torch.Generator().manual_seed(4)
+    noise = torch.empty(steps, 1, 8194).exponential_(generator=g).to(dev)
+
+    def run(slot):
+        lg = []
+        for i in range(steps):
+            eng.t3_step([slot], 1, noise=noise[i].contiguous())
+            lg.append(torch.from_numpy(eng.t3_logits(slot)).clone())
+        toks = eng.t3_tokens(slot, 0, steps).tolist()
+        eng.t3_close(slot)
+        return torch.stack(lg), toks
+
+    single = [run(eng.t3_open(v, t, 0.5 if k != 2 else 0.0, 0.8, 1.2, 0.05, 0.95, 100 + k, 16)) for k, (v, t) in enumerate(zip(voices, texts))]
+    slots = eng.t3_open_batch([(v, t, 0.5 if k != 2 else 0.0, 0.8, 1.2, 0.05, 0.95, 100 + k, 16) for k, (v, t) in enumerate(zip(voices, texts))])
+    assert len(set(slots)) == 4
+    batch = [run(s) for s in slots]
+    for k in range(4):
+        assert batch[k][1] == single[k][1], f"stream {k}: sampled ids differ"
+        assert torch.equal(batch[k][0], single[k][0]), f"stream {k}: logits differ by {float((batch[k][0] - single[k][0]).abs().max())}"
+    eng.voice_drop("w2")

@@ -344,6 +344,7 @@ class S3GenBatcher:
         self.gather_s = float(os.environ.get("CBX_S3GEN_GATHER_MS", "3")) * 1e-3
         # "full" overlap emits wav[previous_length:] only: the vocoder decodes a window that ends the call (exact from emit_from on)
         self.window = os.environ.get("CBX_HIFT_WINDOW", "1") != "0"
+        self.gather_always = os.environ.get("CBX_S3GEN_GATHER_ALWAYS", "0") == "1"      # experiment: also gather when jobs were already pending
         self.urgent_window_s = float(os.environ.get("CBX_S3GEN_URGENT_MS", "15")) * 1e-3   # upper bound; the emitter ends it
         self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
         for t in self.threads:
@@ -390,7 +391,7 @@ class S3GenBatcher:
         while True:
             with self.cv:
                 batch = []
-                idle = not self.jobs      # nothing accumulated while the previous batch ran: the next job opens a gather window
+                idle = (not self.jobs) or self.gather_always      # nothing accumulated while the previous batch ran: the next job opens a gather window
                 while self.running:
                     if idle and self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch:
                         # every submit wakes this wait: keep gathering until the window (counted from the first job) closes

@@ -95,3 +95,45 @@ def test_wav_header_and_empty_text():
     assert len(h) == 44 and h[:4] == b"RIFF" and h[8:12] == b"WAVE" and h[4:8] == b"\xff\xff\xff\xff"   # reference audio_encoding.py:97-115
     assert int.from_bytes(h[24:28], "little") == 24000 and int.from_bytes(h[34:36], "little") == 16
     assert empty == [b""]
+
+
+def test_opens_pending_together_are_prefilled_in_one_pass():
+    """The scheduler's opener thread hands opens that are pending at the same moment to ONE t3_open_batch call (8 requests arriving
+    together, chunks 1.. of a request): the audio is what one-by-one opens produce, and a batch that cannot be opened as a whole
+    falls back to individual opens, each with its own verdict."""
+    class BatchNative(FakeNative):
+        def __init__(self, fail_batches=False):
+            super().__init__()
+            self.batch_sizes, self.fail_batches = [], fail_batches
+
+        def t3_open_batch(self, reqs):
+            self.batch_sizes.append(len(reqs))
+            if self.fail_batches:
+                raise RuntimeError("not enough pages for the whole batch")
+            return [self.t3_open(*r) for r in reqs]
+
+    async def many(native):
+        from cbx_b200.engine import TextToSpeechEngine
+        eng = TextToSpeechEngine("cpu", backend=native, concurrent_requests=4)
+        await eng.ainit()
+        eng.scheduler.open_gather_s = 0.05          # a wide window: the four requests below must meet in it
+
+        async def one(sc):
+            out = b""
+            async for c in eng.stream(text=scenario_text(sc["words"]), output_format="raw_pcm", voice_id=None, cfg_guidance_weight=0.5,
+                                      synthesis_temperature=0.8, text_processing_chunk_size=sc["chunk"], audio_tokens_per_slice=sc["slice"],
+                                      remove_trailing_milliseconds=sc["trail"], remove_leading_milliseconds=sc["lead"],
+                                      chunk_overlap_strategy=sc["overlap"], crossfade_duration_milliseconds=sc["fade"], request_id=sc["name"]):
+                out += c
+            return np.frombuffer(out, dtype=np.int16)
+        scs = [SCENARIOS[0], SCENARIOS[3], SCENARIOS[1], SCENARIOS[0]]
+        r = await asyncio.gather(*[one(sc) for sc in scs])
+        eng.shutdown()
+        return scs, r
+
+    for fail in (False, True):
+        native = BatchNative(fail_batches=fail)
+        scs, res = asyncio.run(many(native))
+        for sc, pcm in zip(scs, res):
+            assert zlib.crc32(pcm.tobytes()) == int(GOLD[sc["name"] + "_crc"][0]), (sc["name"], fail)
+        assert max(native.batch_sizes) >= 2, native.batch_sizes

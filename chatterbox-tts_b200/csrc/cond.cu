@@ -41,13 +41,41 @@ __device__ __forceinline__ float act_f(int act, float v) {
 // ------------------------------------------------------------------------------------------------------------ sgemm
 constexpr int GT = 64, GK = 16;
 __global__ void __launch_bounds__(256) sgemm_kernel(const cbx_sgemm_args p) {
-    __shared__ float As[GK][GT + 4], Ws[GK][GT + 4];
+    __shared__ __align__(16) float As[GK][GT + 4], Ws[GK][GT + 4];
     const int b = blockIdx.z, m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const float* A = p.A + (long)b * p.a_bs;
     const float* W = p.W + (long)b * p.w_bs;
     float acc[4][4] = {};
+    // fast path: every 16-wide K tile lies inside one conv tap and all operand rows are 16-byte aligned -> one float4 per thread
+    // and tile for A and for W (no per-element index arithmetic), float4 reads of the tiles in the inner loop
+    const bool vec = (p.kc % GK == 0) && (p.K % GK == 0) && (p.lda % 4 == 0) && (p.ldw % 4 == 0) && (p.a_bs % 4 == 0) && (p.w_bs % 4 == 0) && !p.w_trans &&
+                     ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
     for (int k0 = 0; k0 < p.K; k0 += GK) {
+        if (vec) {
+            const int r = threadIdx.x >> 2, q4 = (threadIdx.x & 3) * 4;       // 64 rows x 4 float4 columns
+            const int tap = k0 / p.kc, c0 = k0 - tap * p.kc + q4;
+            {
+                const int m = m0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const long t_in = (long)m * p.a_stride + (long)tap * p.a_dil - p.a_pad;
+                if (m < p.M && t_in >= 0 && t_in < p.a_rows) {
+                    v = *reinterpret_cast<const float4*>(A + t_in * p.lda + c0);
+                    if (p.a_scale) {
+                        const float4 sc = *reinterpret_cast<const float4*>(p.a_scale + c0), sh = *reinterpret_cast<const float4*>(p.a_shift + c0);
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    if (p.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+                As[q4][r] = v.x; As[q4 + 1][r] = v.y; As[q4 + 2][r] = v.z; As[q4 + 3][r] = v.w;
+            }
+            {
+                const int n = n0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < p.N) v = *reinterpret_cast<const float4*>(W + (long)n * p.ldw + k0 + q4);
+                Ws[q4][r] = v.x; Ws[q4 + 1][r] = v.y; Ws[q4 + 2][r] = v.z; Ws[q4 + 3][r] = v.w;
+            }
+        } else {
         // A tile: 64 rows x 16 k (gathered conv taps, optional per-channel affine + ReLU on the way in)
         for (int i = threadIdx.x; i < GT * GK; i += 256) {
             const int r = i / GK, kk = k0 + i % GK, m = m0 + r;
@@ -75,12 +103,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const cbx_sgemm_args p) {
                 Ws[i % GK][i / GK] = v;
             }
         }
+        }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < GK; k++) {
-            float a[4], w[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]), w4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -356,25 +384,32 @@ __global__ void conv2d_kernel(const float* __restrict__ x, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------------ LSTM layer
-// One block per sequence, 4H = blockDim threads... H hidden units: thread j owns gate rows j, H + j, 2H + j, 3H + j.
-// xp [B][T][4H] = x W_ih^T + b_ih + b_hh (one GEMM for all steps); w_hh_t [H][4H] (transposed: coalesced over gate rows).
-__global__ void lstm_layer_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh_t, float* __restrict__ h_seq, float* __restrict__ h_last, int T, int H) {
-    extern __shared__ float hs[];        // [H]
-    const int b = blockIdx.x, j = threadIdx.x;
+// One block per sequence, H threads: thread j accumulates the four consecutive gate rows 4j .. 4j+3 over the hidden state
+// (w_hh_t [H][4H]: one 16-byte load per k, coalesced over j, eight in flight per thread), then combines the four gates of unit j.
+// xp [B][T][4H] = x W_ih^T + b_ih + b_hh (one GEMM for all steps).  The accumulation order per gate row (input projection, then k
+// ascending) is the oracle's.
+__global__ void __launch_bounds__(256) lstm_layer_kernel(const float* __restrict__ xp, const float* __restrict__ w_hh_t, float* __restrict__ h_seq, float* __restrict__ h_last, int T, int H) {
+    extern __shared__ __align__(16) float sm[];
+    float* hs = sm;            // [H]
+    float* gates = sm + H;     // [4H]
+    const int b = blockIdx.x, j = threadIdx.x, G = 4 * H;
     float c = 0.f;
-    if (j < H) hs[j] = 0.f;
+    hs[j] = 0.f;
     __syncthreads();
     for (int t = 0; t < T; t++) {
-        const float* g = xp + ((long)b * T + t) * 4 * H;
-        float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+        float4 acc = *reinterpret_cast<const float4*>(xp + ((long)b * T + t) * G + 4 * j);
+        const float4* w = reinterpret_cast<const float4*>(w_hh_t) + j;
+#pragma unroll 8
         for (int k = 0; k < H; k++) {
+            const float4 wv = __ldg(w + (long)k * H);
             const float hk = hs[k];
-            const float* wr = w_hh_t + (long)k * 4 * H;
-            gi = fmaf(wr[j], hk, gi); gf = fmaf(wr[H + j], hk, gf); gg = fmaf(wr[2 * H + j], hk, gg); go = fmaf(wr[3 * H + j], hk, go);
+            acc.x = fmaf(wv.x, hk, acc.x); acc.y = fmaf(wv.y, hk, acc.y); acc.z = fmaf(wv.z, hk, acc.z); acc.w = fmaf(wv.w, hk, acc.w);
         }
+        *reinterpret_cast<float4*>(gates + 4 * j) = acc;
+        __syncthreads();       // every thread is past its reads of hs; the gates are complete
+        const float gi = gates[j], gf = gates[H + j], gg = gates[2 * H + j], go = gates[3 * H + j];
         c = c / (1.f + expf(-gf)) + tanhf(gg) / (1.f + expf(-gi));
         const float h = tanhf(c) / (1.f + expf(-go));
-        __syncthreads();
         hs[j] = h;
         if (h_seq) h_seq[((long)b * T + t) * H + j] = h;
         __syncthreads();
@@ -484,8 +519,8 @@ int cbx_cond_conv2d(const float* x, const float* w, const float* scale, const fl
 
 int cbx_cond_lstm_layer(const float* xp, const float* w_hh_t, float* h_seq, float* h_last, int B, int T, int H, void* stream) {
     COND_API_BEGIN
-    CBX_REQUIRE(xp && w_hh_t && B > 0 && T > 0 && H > 0 && H <= 1024, "cond lstm: bad arguments");
-    lstm_layer_kernel<<<B, H, H * sizeof(float), (cudaStream_t)stream>>>(xp, w_hh_t, h_seq, h_last, T, H);
+    CBX_REQUIRE(xp && w_hh_t && B > 0 && T > 0 && H > 0 && H <= 256 && H % 4 == 0, "cond lstm: bad arguments (hidden size must fit one block)");
+    lstm_layer_kernel<<<B, H, 5 * H * sizeof(float), (cudaStream_t)stream>>>(xp, w_hh_t, h_seq, h_last, T, H);
     COND_API_END
 }
 

@@ -42,3 +42,20 @@ fb = enc.kaldi_fbank(w16)
 timed("CAMPPlus", lambda: enc.campplus(fb))
 timed("VoiceEncoder (trim + mel + LSTM)", lambda: enc.voice_embed(w16))
 timed("prepare_conditionals (device part)", lambda: enc.prepare_conditionals(wav, 24000))
+# VoiceEncoder sub-stages
+from cbx_b200.conditioning import ve_partials
+import ctypes as C
+from cbx_b200 import lib as L
+timed("  VE: trim_silence", lambda: enc.trim_silence(w16))
+w16t = enc.trim_silence(w16).contiguous()
+n = w16t.shape[0] // 160 + 1
+step, B, target = ve_partials(n)
+timed("  VE: mel (40)", lambda: enc.ve_mel(w16t, pad_to=target))
+mel40, _ = enc.ve_mel(w16t, pad_to=target)
+H = 256
+xp, hs, hl = enc._new(B, 160, 4 * H), enc._new(B, 160, H), enc._new(B, H)
+w_ih, w_hh_t, bias = enc.lstm[0]
+timed(f"  VE: layer-0 input GEMM (B={B})", lambda: enc._gemm(mel40, w_ih, xp, 160, 4 * H, 40, batch=B, a_bs=step * 40, c_bs=160 * 4 * H, bias=bias))
+timed("  VE: one LSTM layer recurrence", lambda: L.check(enc.lib.cbx_cond_lstm_layer(xp.data_ptr(), w_hh_t.data_ptr(), hs.data_ptr(), hl.data_ptr(), B, 160, H, enc._st())))
+w_ih1, _, bias1 = enc.lstm[1]
+timed("  VE: layer-1 input GEMM", lambda: enc._gemm(hs, w_ih1, xp, B * 160, 4 * H, H, bias=bias1))

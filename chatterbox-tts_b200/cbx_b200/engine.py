@@ -511,7 +511,7 @@ class TextToSpeechEngine:
 
     def __init__(self, device: str, cfg: ModelConfig = None, state_dict=None, concurrent_requests: int = None,
                  sampling: SamplingDefaults = None, native_kwargs: dict = None, seed: int = 0, device_sink: bool = False,
-                 backend=None, encoder_state_dict=None):
+                 backend=None, encoder_state_dict=None, alignment_eos: bool = None):
         """`backend` injects an object with NativeEngine's interface (host-logic tests only); the product path
         always builds a NativeEngine on `device` and refuses anything that is not cuda:N."""
         self.device = device
@@ -562,6 +562,10 @@ class TextToSpeechEngine:
         self._encoder_sd = encoder_state_dict     # tokenizer.* / speaker_encoder.* / ve.* (conditioning encoders), else from the checkpoint
         self._cond, self._cond_lock = None, threading.Lock()
         self.device_sink = device_sink   # bench `value` leg: PCM stays in HBM, emit() receives sample counts
+        # alignment-based EOS control of the T3 generators (the model package's AlignmentStreamAnalyzer): whether the
+        # reference's fork runs it inside inference_stream is unknown, and with random-init weights its verdicts mean nothing, so
+        # it is opt-in (CBX_ALIGNMENT_EOS=1 / alignment_eos=True; probe layer CBX_ALIGNMENT_LAYER, upstream 9)
+        self.alignment_eos = (os.environ.get("CBX_ALIGNMENT_EOS", "0") == "1") if alignment_eos is None else bool(alignment_eos)
         self._seq = 0
         self._seq_lock = threading.Lock()
         self._ready = False
@@ -599,6 +603,8 @@ class TextToSpeechEngine:
                 self._encoder_sd = enc_sd
         self.native.load_state_dict(sd)
         self._state_dict = None
+        if self.alignment_eos:
+            self.native.t3_set_alignment_eos(True, int(os.environ.get("CBX_ALIGNMENT_LAYER", "9")))
         tj = os.path.join(model_path, "tokenizer.json")
         self.tokenizer = JsonTokenizer(tj) if os.path.exists(tj) else SyntheticTokenizer(self.cfg.t3.text_vocab)
         cp = os.path.join(model_path, "conds.pt")

@@ -207,6 +207,30 @@ class NativeEngine:
     def t3_set_persistent(self, on: bool):
         L.check(self.lib.cbx_t3_set_persistent(self.h, 1 if on else 0))
 
+    def t3_set_alignment_eos(self, on: bool, layer: int = 9):
+        """Alignment-based EOS control for the generators opened after this call (include/cbx_b200.h)."""
+        L.check(self.lib.cbx_t3_set_alignment_eos(self.h, 1 if on else 0, int(layer)))
+
+    ALIGN_FIELDS = ("on", "i0", "S", "frame_pos", "text_pos", "rows", "started", "started_at", "complete", "completed_at", "has_pre", "ctl", "cur_posn")
+
+    def t3_alignment_peek(self, slot, rows=True):
+        """(state dict, newest alignment row, prefilled BOS row) of a stream's analyzer."""
+        iv, fv = np.zeros(13, np.int32), np.zeros(6, np.float32)
+        L.check(self.lib.cbx_t3_alignment_peek(self.h, slot, iv.ctypes.data, fv.ctypes.data, None, None, _stream_ptr()))
+        st = dict(zip(self.ALIGN_FIELDS, (int(v) for v in iv)))
+        st.update(first4_max=float(fv[0]), prev_last2=float(fv[1]), tail3=[float(v) for v in fv[2:5]], rep_sum=float(fv[5]))
+        if not rows or st["S"] <= 0:
+            return st, None, None
+        cur, pre = np.zeros(st["S"], np.float32), np.zeros(st["S"], np.float32)
+        L.check(self.lib.cbx_t3_alignment_peek(self.h, slot, iv.ctypes.data, fv.ctypes.data, cur.ctypes.data, pre.ctypes.data, _stream_ptr()))
+        return st, cur, pre
+
+    def t3_alignment_poke(self, slot, st):
+        """Test hook: writes back a state dict obtained from t3_alignment_peek."""
+        iv = np.asarray([st[k] for k in self.ALIGN_FIELDS], np.int32)
+        fv = np.asarray([st["first4_max"], st["prev_last2"], *st["tail3"], st["rep_sum"]], np.float32)
+        L.check(self.lib.cbx_t3_alignment_poke(self.h, slot, iv.ctypes.data, fv.ctypes.data, _stream_ptr()))
+
     def t3_poll(self, slot):
         n, d = C.c_int(), C.c_int()
         L.check(self.lib.cbx_t3_poll(self.h, slot, C.byref(n), C.byref(d), _stream_ptr()))

@@ -143,6 +143,7 @@ void cbx_engine_destroy(cbx_engine* e) {
     }
     for (Lane* L : e->lanes) { for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second); cudaFreeHost(L->g_dyn_h); cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
     cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
+    if (e->t3.align_st) { cudaStreamDestroy(e->t3.align_st); cudaEventDestroy(e->t3.align_fork); cudaEventDestroy(e->t3.align_join); }
     delete e;
 }
 
@@ -265,6 +266,69 @@ int cbx_t3_set_persistent(cbx_engine* e, int on) {
     std::lock_guard<std::mutex> g(e->t3_mu);
     CBX_REQUIRE(!on || e->t3.mega_ok, "persistent T3 kernel is not available on this device");
     e->t3.mega = on != 0;
+    CBX_API_END
+}
+
+int cbx_t3_set_alignment_eos(cbx_engine* e, int on, int layer) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && layer >= 0, "bad argument");
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    e->t3.align = on != 0;
+    e->t3.align_layer = layer;
+    CBX_API_END
+}
+
+int cbx_t3_alignment_peek(cbx_engine* e, int slot, int32_t* state_out, float* fstate_out, float* row_out, float* pre_out, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && slot >= 0 && slot < e->cfg.max_streams && state_out && fstate_out, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    AlignState s;
+    CBX_CHECK(cudaMemcpyAsync(&s, e->t3.align_state + slot, sizeof(s), cudaMemcpyDeviceToHost, e->t3_st));
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    const int32_t iv[13] = {s.on, s.i0, s.S, s.frame_pos, s.text_pos, s.T, s.started, s.started_at, s.complete, s.completed_at, s.has_pre, s.ctl, s.cur_posn};
+    const float fv[6] = {s.first4_max, s.prev_last2, s.tail3[0], s.tail3[1], s.tail3[2], s.rep_sum};
+    std::copy(iv, iv + 13, state_out);
+    std::copy(fv, fv + 6, fstate_out);
+    if (row_out && s.S > 0) CBX_CHECK(cudaMemcpyAsync(row_out, e->t3.align_cur + (long)slot * e->t3.align_ld, (size_t)s.S * 4, cudaMemcpyDeviceToHost, e->t3_st));
+    if (pre_out && s.S > 0) CBX_CHECK(cudaMemcpyAsync(pre_out, e->t3.align_pre + (long)slot * e->t3.align_ld, (size_t)s.S * 4, cudaMemcpyDeviceToHost, e->t3_st));
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    CBX_API_END
+}
+
+int cbx_t3_alignment_poke(cbx_engine* e, int slot, const int32_t* iv, const float* fv, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e && slot >= 0 && slot < e->cfg.max_streams && iv && fv, "bad argument");
+    CBX_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    AlignState s{};
+    s.on = iv[0]; s.i0 = iv[1]; s.S = iv[2]; s.frame_pos = iv[3]; s.text_pos = iv[4]; s.T = iv[5]; s.started = iv[6]; s.started_at = iv[7]; s.complete = iv[8];
+    s.completed_at = iv[9]; s.has_pre = iv[10]; s.ctl = iv[11]; s.cur_posn = iv[12];
+    s.first4_max = fv[0]; s.prev_last2 = fv[1]; s.tail3[0] = fv[2]; s.tail3[1] = fv[3]; s.tail3[2] = fv[4]; s.rep_sum = fv[5];
+    CBX_REQUIRE(s.S >= 1 && s.S <= e->cfg.max_text && s.i0 >= 0, "alignment poke: text span out of range");
+    CBX_CHECK(cudaMemcpyAsync(e->t3.align_state + slot, &s, sizeof(s), cudaMemcpyHostToDevice, e->t3_st));
+    CBX_CHECK(cudaStreamSynchronize(e->t3_st));
+    CBX_API_END
+}
+
+int cbx_op_alignment_run(const float* rows_d, int n_rows, int S, int n_pre, int32_t* steps_out_h, void* stream) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(rows_d && steps_out_h && S >= 1 && (n_pre == 0 || n_pre == 1) && n_rows > n_pre, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    AlignState* sd; int *ctl, *slots;
+    CBX_CHECK(cudaMalloc(&sd, sizeof(AlignState)));
+    CBX_CHECK(cudaMalloc(&ctl, 4)); CBX_CHECK(cudaMalloc(&slots, 4));
+    CBX_CHECK(cudaMemsetAsync(slots, 0, 4, st));
+    launch_align_init(sd, ctl, 0, 1, 0, S, n_pre, st);
+    for (int r = n_pre, f = 0; r < n_rows; r++, f++) {
+        AlignStepParams p; p.slots = slots; p.state = sd; p.a_cur = rows_d + (long)r * S; p.a_pre = rows_d; p.ld = S; p.ctl = ctl;
+        launch_align_step(p, 1, st);
+        AlignState s;
+        CBX_CHECK(cudaMemcpyAsync(&s, sd, sizeof(s), cudaMemcpyDeviceToHost, st));
+        CBX_CHECK(cudaStreamSynchronize(st));
+        steps_out_h[f * 4 + 0] = s.ctl; steps_out_h[f * 4 + 1] = s.text_pos; steps_out_h[f * 4 + 2] = s.started; steps_out_h[f * 4 + 3] = s.complete;
+    }
+    cudaFree(sd); cudaFree(ctl); cudaFree(slots);
     CBX_API_END
 }
 

@@ -43,6 +43,11 @@ struct T3Model {
     int* page_table = nullptr; T3SlotState* slot_state = nullptr; int* slot_pos = nullptr; uint8_t* seen = nullptr;
     int* out_tokens = nullptr; int out_stride = 0; float *x, *qkv, *attn, *act, *logits;
     int *d_slots = nullptr, *d_rowmap = nullptr;   // active set staging [max_streams], [2*max_streams]
+    // alignment-based EOS control (off by default; cbx_t3_set_alignment_eos): per-slot analyzer state, decision word and the
+    // newest alignment row(s) over the text span
+    bool align = false; int align_layer = 9; AlignState* align_state = nullptr; int* align_ctl = nullptr;
+    float *align_cur = nullptr, *align_pre = nullptr, *align_q = nullptr; long align_ld = 0;
+    cudaStream_t align_st = nullptr; cudaEvent_t align_fork = nullptr, align_join = nullptr;   // the analyzer runs beside the layers after the probe
     // megakernel state
     bool mega = false, mega_ok = false; MegaState mega_state; MegaLayer* d_layers = nullptr; unsigned long long* ll[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; unsigned int* epoch = nullptr;
     // prefill workspace

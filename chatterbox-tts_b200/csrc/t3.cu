@@ -75,6 +75,17 @@ void t3_alloc(cbx_engine* e) {
     m.logits = e->scratch<float>((long)R * T3_VPAD);
     m.d_slots = e->scratch<int>(S);
     m.d_rowmap = e->scratch<int>(R);
+    m.align_ld = c.max_text + 8;
+    m.align_state = e->scratch<AlignState>(S);
+    m.align_ctl = e->scratch<int>(S);
+    m.align_cur = e->scratch<float>((long)S * m.align_ld);
+    m.align_pre = e->scratch<float>((long)S * m.align_ld);
+    m.align_q = e->scratch<float>((long)R * T3_D);
+    CBX_CHECK(cudaStreamCreateWithFlags(&m.align_st, cudaStreamNonBlocking));
+    CBX_CHECK(cudaEventCreateWithFlags(&m.align_fork, cudaEventDisableTiming));
+    CBX_CHECK(cudaEventCreateWithFlags(&m.align_join, cudaEventDisableTiming));
+    CBX_CHECK(cudaMemset(m.align_state, 0, sizeof(AlignState) * S));
+    CBX_CHECK(cudaMemset(m.align_ctl, 0, sizeof(int) * S));
     m.pf_max = T3_COND + c.max_text + 2;
     const long M = 2L * m.pf_max * T3_PREFILL_BATCH;      // up to T3_PREFILL_BATCH requests, every sequence padded to the longest
     m.pf_x = e->scratch<float>(M * T3_D);
@@ -219,8 +230,10 @@ void t3_open_batch(cbx_engine* e, const T3OpenReq* reqs, int n, int* slots_out, 
         a.speech_pos = m.speech_pos; a.text_ids = m.pf_text + (long)i * (c.max_text + 8); a.Lc = T3_COND; a.L = reqs[i].L; a.Lp = Lp[i]; a.dim = T3_D; a.bos = T3_BOS;
         a.cfg_on = reqs[i].cfg_w > 0.f ? 1 : 0; a.slab = Lmax;
         launch_assemble_embeds(a, st);
+        launch_align_init(m.align_state, m.align_ctl, slots_out[i], m.align ? 1 : 0, T3_COND, reqs[i].L, reqs[i].cfg_w > 0.f ? 1 : 0, st);
     }
     const int M = (int)(n * slab2);
+    const int al = std::min(m.align_layer, c.t3_layers - 1);
     for (int li = 0; li < c.t3_layers; li++) {
         const T3Layer& l = m.layers[li];
         NormParams nn; nn.in = m.pf_x; nn.ld_in = T3_D; nn.rows = M; nn.C = T3_D; nn.gain = l.ln1; nn.rms = 1; nn.eps = 1e-5f; nn.outB = m.pf_xn; nn.ld_outB = T3_D;
@@ -232,6 +245,14 @@ void t3_open_batch(cbx_engine* e, const T3OpenReq* reqs, int n, int* slots_out, 
             r.page_table = m.page_table; r.max_pages = m.max_pages; r.row0 = slots_out[i] * 2; r.inv_freq = m.inv_freq;
             launch_rope_kv_prefill(r, st);
         }
+        if (m.align && li == al)    // the prefilled BOS query is the first row of the alignment matrix (the second BOS is the first decode step)
+            for (int i = 0; i < n; i++) {
+                if (!(reqs[i].cfg_w > 0.f)) continue;
+                AlignAttnParams aa; aa.slot = slots_out[i]; aa.state = m.align_state; aa.q_b = m.pf_qkv + (i * slab2 + (Lp[i] - 1)) * 3 * T3_D; aa.pos = Lp[i] - 1;
+                aa.kv = m.kv + li * m.kv_layer_stride; aa.page_table = m.page_table; aa.max_pages = m.max_pages; aa.out = m.align_pre; aa.ld_out = m.align_ld; aa.H = T3_H;
+                launch_align_attn(aa, 1, st);
+                e->gpu_launches += 1;
+            }
         AttnParams at; at.q = m.pf_qkv; at.k = m.pf_qkv + T3_D; at.v = m.pf_qkv + 2 * T3_D; at.ldq = at.ldk = at.ldv = 3 * T3_D;
         at.q_bs = at.k_bs = at.v_bs = (long)Lmax * 3 * T3_D; at.o = m.pf_att; at.ldo = T3_D; at.o_bs = (long)Lmax * T3_D; at.T = Lmax; at.H = T3_H; at.batch = 2 * n;
         at.causal = 1; at.scale = 0.125f;
@@ -251,7 +272,7 @@ void t3_open_batch(cbx_engine* e, const T3OpenReq* reqs, int n, int* slots_out, 
         s.pos = Lp[i]; s.step = 0; s.max_new = r.max_new; s.done = 0; s.cfg_w = r.cfg_w; s.temp = r.temp; s.rep_pen = r.rep; s.min_p = r.min_p; s.top_p = r.top_p; s.seed = r.seed;
         launch_init_slot(m.slot_state, s, m.slot_pos, slots_out[i], m.seen, T3_VPAD, T3_BOS, m.x, m.speech_emb, m.speech_pos, T3_D, st);
     }
-    e->gpu_launches += 2L * n + (7L + n) * c.t3_layers;
+    e->gpu_launches += 3L * n + (7L + n) * c.t3_layers;
 }
 
 int t3_open(cbx_engine* e, int voice, const int* text_ids_h, int L, float cfg_w, float temp, float rep, float min_p, float top_p,
@@ -267,13 +288,14 @@ static void enqueue_sampler(cbx_engine* e, int n, const float* noise, cudaStream
     SamplerParams s; s.slots = m.d_slots; s.state = m.slot_state; s.slot_pos = m.slot_pos; s.logits = m.logits; s.ld_logits = T3_VPAD;
     s.seen = m.seen; s.seen_stride = T3_VPAD; s.out_tokens = m.out_tokens; s.out_stride = m.out_stride; s.noise = noise; s.noise_stride = T3_V;
     s.x = m.x; s.speech_emb = m.speech_emb; s.speech_pos = m.speech_pos; s.V = T3_V; s.dim = T3_D; s.eos = T3_EOS;
+    s.eos_ctl = m.align ? m.align_ctl : nullptr;
     launch_sampler(s, n, st);
 }
 
 static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t st) {
     T3Model& m = e->t3;
     const int rows = 2 * n;
-    if (m.mega && rows <= 16) {   // whole step = one persistent cooperative kernel + the sampler (instances for up to 16 rows)
+    if (m.mega && rows <= 16 && !m.align) {   // whole step = one persistent cooperative kernel + the sampler (instances for up to 16 rows)
         MegaParams p;
         p.layers = m.d_layers; p.n_layers = e->cfg.t3_layers; p.head_f = m.head_f; p.head_items = T3_VPAD / 16; p.vocab = T3_V; p.final_norm = m.final_norm;
         p.x = m.x; p.logits = m.logits; p.ld_logits = T3_VPAD;
@@ -296,7 +318,7 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         if (tc && g.xb && launch_gemv_tc(g, map, st)) return;
         launch_gemv(g, nwarps, st);
     };
-    const int n_layers = e->cfg.t3_layers;
+    const int n_layers = e->cfg.t3_layers, al = std::min(m.align_layer, n_layers - 1);
     for (int li = 0; li < n_layers; li++) {
         const T3Layer& l = m.layers[li];
         GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1;
@@ -306,7 +328,20 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         gemv(q, l.tm_qkv, 8);
         DecodeAttnParams a; a.qkv = m.qkv; a.out_b = m.attn_b; a.kv = m.kv + li * m.kv_layer_stride; a.kv_half = m.kv_half; a.page_table = m.page_table;
         a.max_pages = m.max_pages; a.slot_pos = m.slot_pos; a.row_map = m.d_rowmap; a.inv_freq = m.inv_freq; a.H = T3_H;
+        if (m.align && li == al) a.q_save = m.align_q;
         launch_decode_attn(a, rows, e->cfg.max_seq, st);
+        if (m.align && li == al) {
+            // alignment row of this frame and the analyzer's decision, on a side branch that joins before the sampler: its inputs
+            // (the saved queries, this layer's K pages, the slot positions) are not written again before the next step
+            CBX_CHECK(cudaEventRecord(m.align_fork, st));
+            CBX_CHECK(cudaStreamWaitEvent(m.align_st, m.align_fork, 0));
+            AlignAttnParams aa; aa.slots = m.d_slots; aa.state = m.align_state; aa.q_rot = m.align_q; aa.kv = a.kv; aa.page_table = m.page_table; aa.max_pages = m.max_pages;
+            aa.slot_pos = m.slot_pos; aa.out = m.align_cur; aa.ld_out = m.align_ld; aa.H = T3_H;
+            launch_align_attn(aa, n, m.align_st);
+            AlignStepParams as; as.slots = m.d_slots; as.state = m.align_state; as.t3 = m.slot_state; as.a_cur = m.align_cur; as.a_pre = m.align_pre; as.ld = m.align_ld; as.ctl = m.align_ctl;
+            launch_align_step(as, n, m.align_st);
+            CBX_CHECK(cudaEventRecord(m.align_join, m.align_st));
+        }
         GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.xb = m.attn_b; o.ldxb = T3_D;
         o.row_map = m.d_rowmap; o.rows = rows; o.out = m.x; o.ld_out = T3_D; o.epi = GEMV_RESID;
         o.out_b = m.xb; o.ld_out_b = T3_D; o.next_gain = l.ln2; o.ss_out = m.ss;
@@ -325,6 +360,7 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
     h.xb = m.xb; h.ldxb = T3_D; h.ss_in = m.ss; h.n_ss = T3_D / 16;
     h.row_map = m.d_rowmap; h.rows = rows; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
     launch_gemv(h, 8, st);
+    if (m.align) CBX_CHECK(cudaStreamWaitEvent(st, m.align_join, 0));
     enqueue_sampler(e, n, noise, st);
 }
 
@@ -341,8 +377,8 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
         CBX_CHECK(cudaStreamSynchronize(st));
         m.h_active = act;
     }
-    const bool mega = m.mega && 2 * n <= 16;
-    const long per_step = mega ? 2 : (5L + (2 * n > 16 ? 1 : 0)) * e->cfg.t3_layers + 2;     // > 16 rows: the down projection runs as two passes
+    const bool mega = m.mega && 2 * n <= 16 && !m.align;
+    const long per_step = mega ? 2 : (5L + (2 * n > 16 ? 1 : 0)) * e->cfg.t3_layers + 2 + (m.align ? 2 : 0);     // > 16 rows: the down projection runs as two passes
     // algorithmic bytes of one step: every weight once for all rows + the KV cache of every row (host-side position estimate)
     double kv_pos = 0;
     for (int s : act) { kv_pos += 2.0 * m.slot_pos_h[s]; m.slot_pos_h[s] += n_steps; }
@@ -350,7 +386,7 @@ void t3_step(cbx_engine* e, const int* slots, int n, int n_steps, const float* n
     if (noise_dev) {
         for (int i = 0; i < n_steps; i++) enqueue_step(e, n, noise_dev ? noise_dev + (long)i * n * T3_V : nullptr, st);
     } else {
-        const int gkey = n + (mega ? 1000 : 0);
+        const int gkey = n + (mega ? 1000 : 0) + (m.align ? 2000 : 0) + 4000 * std::min(m.align_layer, 63);
         auto it = m.step_graphs.find(gkey);
         if (it == m.step_graphs.end()) {
             cudaGraph_t graph;

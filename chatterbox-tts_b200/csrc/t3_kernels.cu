@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
     const int n = pos + 1, npages = (n + PAGE - 1) / PAGE;
     const bool early = PIPE && warp < npages - 1;
     __syncthreads();
+    if (p.q_save && tid < HD) p.q_save[(long)row * (p.H * HD) + h * HD + tid] = qs[tid];
     if (!early && warp < npages) fetch(pte0, ku, vu);
     float m = -INFINITY, lsum = 0.f;
     float acc[32];
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
     const float* lu = lc + p.ld_logits;
     const float w = st->cfg_w, inv_temp = 1.f / st->temp, rp = st->rep_pen;
     const uint8_t* seen = p.seen + (long)slot * p.seen_stride;
+    const int ctl = p.eos_ctl ? p.eos_ctl[slot] : 0;
     float l[SAMP_E];
     float mx = -INFINITY;
 #pragma unroll
@@ -396,6 +398,8 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
         if (i < V) {
             float c = lc[i];
             v = w > 0.f ? c + w * (c - lu[i]) : c;
+            if (ctl & 2) v = i == p.eos ? 32768.f : -32768.f;      // forced end of speech: every logit -2^15, EOS +2^15
+            if ((ctl & 1) && i == p.eos) v = -32768.f;             // EOS suppressed while the text is not finished
             if (seen[i]) v = v < 0.f ? v * rp : v / rp;
             v *= inv_temp;
         }
@@ -574,6 +578,141 @@ __global__ void scale_vec_kernel(float* out, const float* __restrict__ w, float 
     if (i < n) out[i] = w[i] * s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Alignment-based EOS control
+// ------------------------------------------------------------------------------------------------
+// Attention probabilities of the conditional row's newest query over the text span at one layer, averaged over the heads
+// (the analyzer's `step_attention[0].mean(0)` rows).  One CTA per stream, one warp per head: pass 1 reduces the softmax
+// maximum and denominator over every cached position, pass 2 evaluates the text columns (heads summed in ascending order).
+__global__ void __launch_bounds__(512) align_attn_kernel(const AlignAttnParams p) {
+    __shared__ __align__(16) float qs[16 * HD];
+    __shared__ float hm[16], hl[16];
+    pdl_prologue();
+    const int slot = p.slots ? p.slots[blockIdx.x] : p.slot;
+    const AlignState as = p.state[slot];
+    if (!as.on) return;
+    const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5, row = slot * 2;
+    const int pos = p.q_b ? p.pos : p.slot_pos[slot];
+    const int* pt = p.page_table + (long)row * p.max_pages;
+    if (p.q_b) {
+        qs[h * HD + lane] = __bfloat162float(p.q_b[h * HD + lane]) * 0.125f;
+        qs[h * HD + lane + 32] = __bfloat162float(p.q_b[h * HD + lane + 32]) * 0.125f;
+    } else {
+        const float* q = p.q_rot + (long)row * (p.H * HD) + h * HD;
+        qs[h * HD + lane] = q[lane];
+        qs[h * HD + lane + 32] = q[lane + 32];
+    }
+    __syncthreads();
+    auto score = [&](int hh, int pp) {
+        const uint4* kp = reinterpret_cast<const uint4*>(p.kv + (((long)pt[pp / PAGE] * p.H + hh) * PAGE + (pp % PAGE)) * HD);
+        const float* qh = qs + hh * HD;
+        float sc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint4 u = kp[c];
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __bfloat1622float2(b2[e]);
+                sc += f.x * qh[c * 8 + e * 2] + f.y * qh[c * 8 + e * 2 + 1];
+            }
+        }
+        return sc;
+    };
+    float m = -INFINITY, l = 0.f;
+    for (int pp = lane; pp <= pos; pp += 32) {
+        const float sc = score(h, pp), mn = fmaxf(m, sc);
+        l = l * expf(m - mn) + expf(sc - mn);
+        m = mn;
+    }
+    const float M = warp_max(m);
+    l = warp_sum(m == -INFINITY ? 0.f : l * expf(m - M));
+    if (lane == 0) { hm[h] = M; hl[h] = l; }
+    __syncthreads();
+    float* out = p.out + (long)slot * p.ld_out;
+    for (int t = tid; t < as.S; t += blockDim.x) {
+        float acc = 0.f;
+        for (int hh = 0; hh < 16; hh++) acc += expf(score(hh, as.i0 + t) - hm[hh]) / hl[hh];
+        out[t] = acc * 0.0625f;
+    }
+}
+
+// The analyzer's per-frame decision on the row(s) align_attn_kernel produced.  Quantities the analyzer recomputes from the whole
+// alignment matrix every frame are kept as running values (row order = accumulation order).
+__global__ void __launch_bounds__(256) align_step_kernel(const AlignStepParams p) {
+    __shared__ float rv[8], rr[8];
+    __shared__ int ri[8];
+    pdl_prologue();
+    const int slot = p.slots[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    AlignState s = p.state[slot];
+    if (!s.on || (p.t3 && p.t3[slot].done)) return;
+    const int S = s.S, fp = s.frame_pos;
+    const float* cur = p.a_cur + (long)slot * p.ld;
+    // masked row: columns above frame_pos count as 0.  Argmax (first maximum) and the maximum over columns [0, S - 5).
+    float bv = -1.f, rmax = 0.f; int bi = 0x7fffffff;
+    for (int c = tid; c < S; c += blockDim.x) {
+        const float v = c <= fp ? cur[c] : 0.f;
+        if (v > bv) { bv = v; bi = c; }
+        if (c < S - 5) rmax = fmaxf(rmax, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    }
+    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; rr[warp] = rmax; }
+    __syncthreads();
+    if (tid != 0) return;
+    for (int w = 1; w < 8; w++) {
+        if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
+        rmax = fmaxf(rmax, rr[w]);
+    }
+    auto at = [&](const float* r, int c) { return (c >= 0 && c <= fp) ? r[c] : 0.f; };
+    const int n4 = S < 4 ? S : 4;
+    float last2 = 0.f;       // max over the last two rows of the last two columns
+    bool have_prev = s.T > 0;
+    if (s.has_pre) {         // the first chunk holds two rows: the prefilled BOS row and this one, masked alike
+        const float* pre = p.a_pre + (long)slot * p.ld;
+        for (int c = 0; c < n4; c++) s.first4_max = fmaxf(s.first4_max, at(pre, c));
+        s.prev_last2 = fmaxf(at(pre, S - 2), at(pre, S - 1));
+        s.T += 1; s.has_pre = 0; have_prev = true;
+    }
+    for (int c = 0; c < n4; c++) s.first4_max = fmaxf(s.first4_max, at(cur, c));
+    const float cur_last2 = fmaxf(at(cur, S - 2), at(cur, S - 1));
+    last2 = have_prev ? fmaxf(s.prev_last2, cur_last2) : cur_last2;
+    s.prev_last2 = cur_last2;
+    s.T += 1;
+    const int posn = bi;
+    const int d = posn - s.text_pos;
+    if (-4 < d && d < 7) s.text_pos = posn;
+    const bool false_start = !s.started && (last2 > 0.1f || s.first4_max < 0.5f);
+    s.started = !false_start;
+    if (s.started && s.started_at < 0) s.started_at = s.T;
+    const bool was_complete = s.complete && s.completed_at >= 0;
+    s.complete = s.complete || s.text_pos >= S - 3;
+    if (s.complete && s.completed_at < 0) s.completed_at = s.T;
+    if (was_complete) {      // this row's index (T - 1) is >= completed_at
+        for (int c = 0; c < 3; c++) s.tail3[c] += at(cur, S - 3 + c);
+        s.rep_sum += rmax;
+    }
+    const bool long_tail = s.complete && fmaxf(s.tail3[0], fmaxf(s.tail3[1], s.tail3[2])) >= 10.f;
+    const bool repetition = s.complete && s.rep_sum > 5.f;
+    s.ctl = ((long_tail || repetition) ? 2 : 0) | (posn < S - 3 ? 1 : 0);
+    s.cur_posn = posn;
+    s.frame_pos = fp + 1;
+    p.state[slot] = s;
+    p.ctl[slot] = s.ctl;
+}
+
+__global__ void align_init_kernel(AlignState* st, int* ctl, int slot, int on, int i0, int S, int has_pre) {
+    pdl_prologue();
+    AlignState s{};
+    s.on = on; s.i0 = i0; s.S = S; s.has_pre = has_pre; s.started_at = -1; s.completed_at = -1;
+    st[slot] = s;
+    ctl[slot] = 0;
+}
+
 }  // namespace
 
 void t3_kernels_init() {
@@ -643,5 +782,18 @@ void launch_rope_kv_prefill(const RopeKvParams& p, cudaStream_t st) {
 void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
                       float* x, const float* speech_emb, const float* speech_pos, int dim, cudaStream_t st) {
     launch_pdl(init_slot_kernel, dim3(1), dim3(256), 0, st, st_dev, v, slot_pos, slot, seen, seen_stride, bos, x, speech_emb, speech_pos, dim);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_align_attn(const AlignAttnParams& p, int n_streams, cudaStream_t st) {
+    CBX_REQUIRE(p.H == 16, "align: one warp per head of a 16-head trunk");
+    launch_pdl(align_attn_kernel, dim3(n_streams), dim3(512), 0, st, p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_align_step(const AlignStepParams& p, int n_streams, cudaStream_t st) {
+    launch_pdl(align_step_kernel, dim3(n_streams), dim3(256), 0, st, p);
+    CBX_CHECK(cudaGetLastError());
+}
+void launch_align_init(AlignState* st_dev, int* ctl, int slot, int on, int i0, int S, int has_pre, cudaStream_t st) {
+    launch_pdl(align_init_kernel, dim3(1), dim3(1), 0, st, st_dev, ctl, slot, on, i0, S, has_pre);
     CBX_CHECK(cudaGetLastError());
 }

@@ -46,6 +46,7 @@ struct DecodeAttnParams {
     const int* row_map = nullptr;
     const float* inv_freq = nullptr;     // [32]
     int H = 16;
+    float* q_save = nullptr;             // optional [rows_total][H*64]: the rotated, scaled queries (alignment probe layer)
 };
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st);
 
@@ -60,8 +61,46 @@ struct SamplerParams {
     float* x = nullptr;                  // [slots*2][dim] next-step input embeddings
     const float* speech_emb = nullptr; const float* speech_pos = nullptr;
     int V = 0, dim = 0, eos = 0;
+    const int* eos_ctl = nullptr;        // optional [slots]: bit 1 forces EOS, bit 0 suppresses it (alignment control, applied after the CFG mix)
 };
 void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st);
+
+// ---- alignment-based EOS control.  Reference side: the model package's AlignmentStreamAnalyzer, hooked on the attention of one
+// trunk layer inside T3.inference_stream (the generator src/tts_streaming.py:420-435 primes); SURVEY section 8(f).3.
+struct AlignState {     // device-resident per-stream analyzer state
+    int on;             // 0: the stream does not use alignment control
+    int i0, S;          // text span [i0, i0 + S) of the conditional row's sequence
+    int frame_pos;      // curr_frame_pos: columns above it are masked
+    int text_pos;       // text_position
+    int T;              // alignment rows seen so far
+    int started, started_at, complete, completed_at;
+    int has_pre;        // the prefilled BOS row waits in a_pre (consumed by the first step)
+    int ctl;            // last decision: bit 1 force EOS, bit 0 suppress EOS
+    int cur_posn;       // argmax of the last masked row
+    float first4_max;   // max over all rows of columns [0, 4)
+    float prev_last2;   // max of the previous row's last two columns
+    float tail3[3];     // column sums of the last three columns over rows >= completed_at
+    float rep_sum;      // sum over rows >= completed_at of the row maximum over columns [0, S - 5)
+};
+struct AlignAttnParams {
+    const int* slots = nullptr; int slot = -1;      // decode: active slot list (one CTA each); prefill: one slot
+    AlignState* state = nullptr;
+    const float* q_rot = nullptr;                   // decode: rotated queries x 1/8 saved by the decode attention [rows_total][H*64]
+    const bf16* q_b = nullptr; int pos = 0;         // prefill: rotated bf16 query row of position pos
+    const bf16* kv = nullptr;                       // this layer's K pool [page][H][16][64]
+    const int* page_table = nullptr; int max_pages = 0;
+    const int* slot_pos = nullptr;
+    float* out = nullptr; long ld_out = 0;          // [slots][ld_out] head-averaged probabilities over the text span
+    int H = 16;
+};
+void launch_align_attn(const AlignAttnParams& p, int n_streams, cudaStream_t st);
+struct AlignStepParams {
+    const int* slots = nullptr; AlignState* state = nullptr; const T3SlotState* t3 = nullptr;
+    const float* a_cur = nullptr; const float* a_pre = nullptr; long ld = 0;
+    int* ctl = nullptr;                             // [slots]
+};
+void launch_align_step(const AlignStepParams& p, int n_streams, cudaStream_t st);
+void launch_align_init(AlignState* st_dev, int* ctl, int slot, int on, int i0, int S, int has_pre, cudaStream_t st);
 
 struct AssembleParams {
     float* x = nullptr;                  // [2][Lp][dim]

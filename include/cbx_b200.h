@@ -84,6 +84,22 @@ int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps,
 /* selects the decode-step implementation: 0 = per-projection GEMV kernels (default), 1 = one persistent kernel per step
  * (lower latency for one or two streams, but it owns every SM while it runs; also enabled by CBX_T3_MEGA=1) */
 int cbx_t3_set_persistent(cbx_engine* e, int on);
+/* Alignment-based EOS control of the generators opened AFTER this call (off by default).  Reference side: the model package's
+ * AlignmentStreamAnalyzer, hooked on the attention of trunk layer `layer` (upstream: 9) inside the T3.inference_stream generator
+ * that src/tts_streaming.py:420-435 primes -- the attention of the conditional row's newest query over the text span, averaged
+ * over the heads, is tracked frame by frame; EOS is suppressed while the alignment is short of the last three text tokens and
+ * forced after a long tail (>= 10 summed over a final column) or a repetition (> 5 summed row maxima over earlier columns).
+ * The decision is applied to the CFG-mixed logits in the sampler kernel.  Uses the per-projection decode kernels. */
+int cbx_t3_set_alignment_eos(cbx_engine* e, int on, int layer);
+/* blocking read of a stream's analyzer: state_out[13] = {on, i0, S, frame_pos, text_pos, rows, started, started_at, complete,
+ * completed_at, has_pre, ctl (bit 1 force, bit 0 suppress), cur_posn}; fstate_out[6] = {first4_max, prev_last2, tail3[3], rep_sum};
+ * row_out / pre_out (optional, >= S floats): the newest alignment row and the prefilled BOS row (unmasked) */
+int cbx_t3_alignment_peek(cbx_engine* e, int slot, int32_t* state_out, float* fstate_out, float* row_out, float* pre_out, void* stream);
+/* test hook: overwrites a stream's analyzer state (same layout as the peek) -- lets a test place a stream just short of a forced EOS */
+int cbx_t3_alignment_poke(cbx_engine* e, int slot, const int32_t* state, const float* fstate, void* stream);
+/* parity-test entry: the analyzer alone over given alignment rows (device, [n_rows][S]; the first n_pre of them belong to the
+ * first frame together with the row after them).  steps_out[frames][4] = {ctl, text_pos, started, complete} per frame. */
+int cbx_op_alignment_run(const float* rows_d, int n_rows, int S, int n_pre, int32_t* steps_out_h, void* stream);
 /* blocking reads of a stream's progress / tokens / last-step logits (2 x 8194: cond row, uncond row) */
 int cbx_t3_poll(cbx_engine* e, int slot, int* n_generated, int* done, void* stream);
 int cbx_t3_tokens(cbx_engine* e, int slot, int from, int count, int32_t* out_h, void* stream);

@@ -52,9 +52,11 @@ def rms_norm(x, w, eps):
 
 
 # ----------------------------------------------------------------------------- trunk
-def llama_forward(sd, c: T3Config, x, kv=None, prefix="t3.tfmr.", collect=None):
+def llama_forward(sd, c: T3Config, x, kv=None, prefix="t3.tfmr.", collect=None, attn_probe=None):
     """x: (B, S, D) input embeds; kv: list of (k, v) per layer each (B, H, S0, hd) or None.
-    Returns (final-normed hidden (B,S,D), new kv)."""
+    Returns (final-normed hidden (B,S,D), new kv).  attn_probe = (layer, list): the attention probabilities of
+    batch row 0 at that layer, averaged over the heads (S, past + S), are appended to the list (the forward hook
+    of AlignmentStreamAnalyzer)."""
     B, S, D = x.shape
     past = 0 if kv is None else kv[0][0].shape[2]
     pos = torch.arange(past, past + S, device=x.device)
@@ -78,6 +80,8 @@ def llama_forward(sd, c: T3Config, x, kv=None, prefix="t3.tfmr.", collect=None):
             mask = torch.ones(S, past + S, dtype=torch.bool, device=x.device).tril(past)
             att = att.masked_fill(~mask, float("-inf"))
         att = att.softmax(-1)
+        if attn_probe is not None and attn_probe[0] == i:
+            attn_probe[1].append(att[0].mean(0))
         o = (att @ v).transpose(1, 2).reshape(B, S, D)
         x = x + F.linear(o, sd[p + "self_attn.o_proj.weight"])
         h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], c.rms_eps)
@@ -176,6 +180,63 @@ def process_logits(logits2, generated_ids, cfg_weight, temperature, rep_penalty,
     return lg
 
 
+# ----------------------------------------------------------------------------- alignment-based EOS control (8f.3)
+class AlignmentAnalyzer:
+    """Restatement of AlignmentStreamAnalyzer.step of the upstream chatterbox package ([U]: the fork the reference
+    imports is not on this machine and unpinned, so is the version of this heuristic -- parity unpinned; the engine
+    keeps it off by default).  Per frame it appends the head-averaged attention of the newest query over the text
+    span (columns above the frame counter zeroed), tracks the text position (argmax of the newest row when it moved
+    by -3..+6), and decides: bit 0 = suppress EOS (position short of the last three text tokens), bit 1 = force EOS
+    (after completion, a final-column sum >= 10 -- long tail -- or row maxima over the earlier columns summing
+    to > 5 -- repetition).  The first frame holds every prefilled query from the first BOS on (two rows with CFG)."""
+
+    def __init__(self, S: int):
+        self.S = S
+        self.alignment = torch.zeros(0, S)
+        self.curr_frame_pos = 0
+        self.text_position = 0
+        self.started = False
+        self.started_at = None
+        self.complete = False
+        self.completed_at = None
+
+    def step(self, A_chunk: torch.Tensor) -> int:
+        A_chunk = A_chunk.detach().float().cpu().clone()
+        A_chunk[:, self.curr_frame_pos + 1:] = 0
+        self.alignment = torch.cat((self.alignment, A_chunk), dim=0)
+        A = self.alignment
+        T, S = A.shape
+        cur_text_posn = int(A_chunk[-1].argmax())
+        discontinuity = not (-4 < cur_text_posn - self.text_position < 7)
+        if not discontinuity:
+            self.text_position = cur_text_posn
+        false_start = (not self.started) and (float(A[-2:, -2:].max()) > 0.1 or float(A[:, :4].max()) < 0.5)
+        self.started = not false_start
+        if self.started and self.started_at is None:
+            self.started_at = T
+        self.complete = self.complete or self.text_position >= S - 3
+        if self.complete and self.completed_at is None:
+            self.completed_at = T
+        long_tail = self.complete and float(A[self.completed_at:, -3:].sum(dim=0).max()) >= 10
+        rest = A[self.completed_at:, :-5] if self.complete else None
+        repetition = self.complete and rest.numel() > 0 and float(rest.max(dim=1).values.sum()) > 5
+        ctl = (2 if (long_tail or repetition) else 0) | (1 if cur_text_posn < S - 3 else 0)
+        self.curr_frame_pos += 1
+        self.cur_text_posn = cur_text_posn
+        return ctl
+
+    @staticmethod
+    def apply(logits, ctl: int, eos_idx: int):
+        """The analyzer's edit of the step logits (any leading shape): force first, then suppress."""
+        if ctl & 2:
+            logits = -(2 ** 15) * torch.ones_like(logits)
+            logits[..., eos_idx] = 2 ** 15
+        if ctl & 1:
+            logits = logits.clone()
+            logits[..., eos_idx] = -(2 ** 15)
+        return logits
+
+
 def sample_from(filtered_logits, exp_noise):
     """torch.multinomial(softmax(l), 1) restated with explicit Exp(1) noise q:
     argmax(p / q) (ties -> lowest index), the formulation torch itself uses."""
@@ -184,15 +245,31 @@ def sample_from(filtered_logits, exp_noise):
 
 
 def inference_stream(sd, c: T3Config, t3_cond, text_tokens, max_new_tokens, temperature=0.8, cfg_weight=0.5,
-                     rep_penalty=1.2, min_p=0.05, top_p=0.95, noise_fn=None, return_logits=False):
+                     rep_penalty=1.2, min_p=0.05, top_p=0.95, noise_fn=None, return_logits=False, alignment_layer=None,
+                     trace=None):
     """Generator of speech token ids (T3.inference_stream of the fork, driven by
-    src/tts_streaming.py:483-501).  noise_fn(step) -> (V,) Exp(1) noise."""
+    src/tts_streaming.py:483-501).  noise_fn(step) -> (V,) Exp(1) noise.  alignment_layer: run the
+    AlignmentAnalyzer on that trunk layer's attention (upstream: 9) and edit the step logits with its decision;
+    trace (list) receives (alignment rows of the frame, ctl) per step."""
     x = prepare_input_embeds(sd, c, t3_cond, text_tokens, cfg_weight)
-    h, kv = llama_forward(sd, c, x)
+    probe = None
+    if alignment_layer is not None:
+        L = torch.atleast_2d(text_tokens).shape[1]
+        i0 = x.shape[1] - L - (2 if cfg_weight > 0.0 else 1)
+        analyzer = AlignmentAnalyzer(L)
+        probe = (min(alignment_layer, c.n_layers - 1), [])
+    h, kv = llama_forward(sd, c, x, attn_probe=probe)
     generated = [c.start_speech_token]
     for i in range(max_new_tokens):
         logits = speech_logits(sd, h[:, -1])
-        fl = process_logits(logits, generated, cfg_weight, temperature, rep_penalty, min_p, top_p)
+        if probe is not None:
+            att = probe[1].pop()
+            rows = att[i0 + L:, i0:i0 + L] if i == 0 else att[:, i0:i0 + L]
+            ctl = analyzer.step(rows)
+            if trace is not None:
+                trace.append((rows.detach().float().cpu(), ctl))
+        used = logits if probe is None else AlignmentAnalyzer.apply(logits, ctl, c.stop_speech_token)
+        fl =process_logits(used, generated, cfg_weight, temperature, rep_penalty, min_p, top_p)
         tok = sample_from(fl, noise_fn(i))
         generated.append(tok)
         if return_logits:
@@ -203,4 +280,4 @@ def inference_stream(sd, c: T3Config, t3_cond, text_tokens, max_new_tokens, temp
             return
         e = sd["t3.speech_emb.weight"][tok] + sd["t3.speech_pos_emb.emb.weight"][i + 1]
         e = e[None, None].expand(x.shape[0], 1, -1)
-        h, kv = llama_forward(sd, c, e, kv)
+        h, kv = llama_forward(sd, c, e, kv, attn_probe=probe)

@@ -90,3 +90,26 @@ def test_zero_overlap_and_wav(engine):
     assert z.shape[0] > 0
     w = asyncio.run(_collect(engine, text, "w", output_format="wav"))
     assert w.tobytes()[:4] == b"RIFF"
+
+
+def test_alignment_eos_control_through_the_engine(engine):
+    """cbx_t3_set_alignment_eos on the engine's own native handle (what `alignment_eos=True` / CBX_ALIGNMENT_EOS=1 do at load):
+    with random-init weights the attention over the text is flat, so the analyzer only ever SUPPRESSES the stop token -- which
+    these weights never sample -- and the stream's PCM must be bit-identical to the run without the control, while the analyzer
+    has followed the generated frames of the stream's T3 slots."""
+    text = "alpha bravo charlie delta echo foxtrot golf hotel india juliet kilo lima."
+    engine._seq = 7
+    a = asyncio.run(_collect(engine, text, "req-al"))
+    engine.native.t3_set_alignment_eos(True, 9)
+    try:
+        engine._seq = 7
+        b = asyncio.run(_collect(engine, text, "req-al"))
+        states = [engine.native.t3_alignment_peek(s, rows=False)[0] for s in range(engine.native_kwargs["max_streams"])]
+        engine._seq = 7
+    finally:
+        engine.native.t3_set_alignment_eos(False, 9)
+    c = asyncio.run(_collect(engine, text, "req-al"))
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    followed = [st for st in states if st["on"] == 1 and st["rows"] > 20]
+    assert followed, f"no T3 slot was followed by the analyzer: {states}"
+    assert all(st["frame_pos"] == st["rows"] - 1 and st["i0"] == 34 for st in followed)

@@ -24,6 +24,23 @@ def main():
     out = {}
     text = [255] + [(7 * i) % 700 + 1 for i in range(145)] + [0]
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    if only == "align":   # decode step with and without alignment-based EOS control (two extra kernels at the probe layer)
+        for ns in (1, 8):
+            for on in (False, True):
+                eng.t3_set_alignment_eos(on, 9)
+                slots = [eng.t3_open(v, text, seed=i, max_new=1000) for i in range(ns)]
+                eng.t3_step(slots, 20)
+                torch.cuda.synchronize()
+                a, b = ev(), ev()
+                a.record(); eng.t3_step(slots, 200); b.record()
+                torch.cuda.synchronize()
+                out[f"t3_streams{ns}_alignment_{'on' if on else 'off'}"] = {"ms_per_step": a.elapsed_time(b) / 200}
+                if on:
+                    out[f"t3_streams{ns}_alignment_on"]["analyzer"] = eng.t3_alignment_peek(slots[0], rows=False)[0]
+                for s in slots:
+                    eng.t3_close(s)
+        print(json.dumps(out, indent=1))
+        return
     for ns in (() if only == "s3b" else (1, 2, 4, 8)):
         t0 = time.time()
         slots = [eng.t3_open(v, text, seed=i, max_new=1000) for i in range(ns)]

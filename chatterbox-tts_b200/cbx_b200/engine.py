@@ -628,6 +628,11 @@ class TextToSpeechEngine:
         torch.cuda.synchronize()
         self._ready = True
 
+    def healthy(self) -> bool:
+        """False once the GPU context is unusable (sticky device fault); backends without the probe count as healthy."""
+        probe = getattr(self.native, "healthy", None)
+        return True if probe is None else bool(probe())
+
     def shutdown(self):
         if self.scheduler:
             self.scheduler.stop()
@@ -972,6 +977,10 @@ class TextToSpeechEngine:
                      cancellation_token: Optional[CancellationToken] = None) -> AsyncGenerator[bytes, None]:
         if not self._ready:
             raise RuntimeError(f"TTS Engine on GPU {self.gpu_id} is not ready")
+        if not self.healthy():
+            # a device fault is sticky for the process: fail the request up front (the worker's per-job handler logs it and keeps
+            # answering, src/worker.py:54-56) instead of queueing work that can only fail slice by slice
+            raise RuntimeError(f"TTS Engine on GPU {self.gpu_id} lost its CUDA context (device fault): the worker process must be restarted")
         if output_format not in ("raw_pcm", "wav"):
             raise ValueError(f"Unsupported format on the B200 path: {output_format} (containers are muxed by the caller)")
         if cancellation_token is None:

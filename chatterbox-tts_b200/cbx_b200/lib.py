@@ -65,6 +65,7 @@ SIGNATURES = {
     "cbx_t3_logits": (_I, [_P, _I, _P, _P]),
     "cbx_t3_close": (_I, [_P, _I]),
     "cbx_t3_stats": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "cbx_engine_health": (_I, [_P]),
     "cbx_s3gen_infer": (_I, [_P, _I, _P, _I, _P, _L, _P, _P, _P, _P, _P, _U64, _P]),
     "cbx_s3gen_infer_batch": (_I, [_P, C.POINTER(S3GenCall), _I, _P]),
     "cbx_flow_infer": (_I, [_P, _I, _P, _I, _P, _P]),

@@ -249,6 +249,10 @@ class NativeEngine:
     def t3_close(self, slot):
         L.check(self.lib.cbx_t3_close(self.h, slot))
 
+    def healthy(self):
+        """False once the CUDA context has taken a sticky device fault (include/cbx_b200.h::cbx_engine_health)."""
+        return self.lib.cbx_engine_health(self.h) == 0
+
     def t3_stats(self):
         """(free KV pages, open stream slots)"""
         f, o = C.c_int(), C.c_int()

@@ -46,6 +46,8 @@ class Backend:
             sd, self.encoder_sd, self.weights_source = load_checkpoint(ckpt_dir or "", self.cfg, 0)
             self.native = NativeEngine(self.cfg, device=gpu, max_streams=max(8, n), n_lanes=max(2, min(n, 4)))
             self.native.load_state_dict(sd)
+            if os.environ.get("CBX_ALIGNMENT_EOS", "0") == "1":    # the package's AlignmentStreamAnalyzer, opt-in
+                self.native.t3_set_alignment_eos(True, int(os.environ.get("CBX_ALIGNMENT_LAYER", "9")))
         self.max_slots = max(2, getattr(self.native, "n_voices", 16) - 1)
 
     def _dummy_gen(self):

@@ -374,6 +374,15 @@ int cbx_t3_close(cbx_engine* e, int slot) {
     CBX_API_END
 }
 
+int cbx_engine_health(cbx_engine* e) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e, "null engine");
+    CBX_CHECK(cudaSetDevice(e->device));
+    const cudaError_t q = cudaStreamQuery(e->t3_st);      // sticky faults surface on any call; pending work is not an error
+    if (q != cudaSuccess && q != cudaErrorNotReady) CBX_CHECK(q);
+    CBX_API_END
+}
+
 int cbx_t3_stats(cbx_engine* e, int* free_pages, int* open_slots) {
     CBX_API_BEGIN
     CBX_REQUIRE(e && free_pages && open_slots, "null argument");

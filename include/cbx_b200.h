@@ -108,6 +108,11 @@ int cbx_t3_logits(cbx_engine* e, int slot, float* out_h, void* stream);
 int cbx_t3_close(cbx_engine* e, int slot);
 /* allocator state (tests / health checks): free KV pages and open stream slots */
 int cbx_t3_stats(cbx_engine* e, int* free_pages, int* open_slots);
+/* Non-blocking health probe: 0 while the engine's CUDA context is usable.  A device-side fault (a kernel trap on a stuck barrier,
+ * an illegal address) is sticky for the whole process: every later call fails, and the only recovery is a new worker process.
+ * The reference worker keeps serving after a failed request (src/worker.py:54-56 logs and goes on); the host engine uses this
+ * probe to refuse new requests with a clear error instead of failing them one by one. */
+int cbx_engine_health(cbx_engine* e);
 
 /* S3Gen.inference(speech_tokens, ref_dict, cache_source) -> (wav, source)
  *                                                        -- src/tts_streaming.py:316-320, :583-590

@@ -137,3 +137,31 @@ def test_opens_pending_together_are_prefilled_in_one_pass():
         for sc, pcm in zip(scs, res):
             assert zlib.crc32(pcm.tobytes()) == int(GOLD[sc["name"] + "_crc"][0]), (sc["name"], fail)
         assert max(native.batch_sizes) >= 2, native.batch_sizes
+
+
+def test_a_lost_device_context_refuses_new_requests():
+    """cbx_engine_health: after a sticky device fault the engine refuses requests up front with a clear error (the worker's
+    per-job handler logs it and keeps answering, reference src/worker.py:54-56) instead of failing them slice by slice."""
+    async def go():
+        from cbx_b200.engine import TextToSpeechEngine
+        nat = FakeNative()
+        state = {"ok": True}
+        nat.healthy = lambda: state["ok"]
+        eng = TextToSpeechEngine("cpu", backend=nat, concurrent_requests=1)
+        await eng.ainit()
+        sc = SCENARIOS[0]
+        kw = dict(text=scenario_text(sc["words"]), output_format="raw_pcm", voice_id=None, cfg_guidance_weight=0.5, synthesis_temperature=0.8,
+                  text_processing_chunk_size=sc["chunk"], audio_tokens_per_slice=sc["slice"], remove_trailing_milliseconds=sc["trail"],
+                  remove_leading_milliseconds=sc["lead"], chunk_overlap_strategy=sc["overlap"], crossfade_duration_milliseconds=sc["fade"], request_id="h")
+        try:
+            n = 0
+            async for c in eng.stream(**kw):
+                n += len(c)
+            assert n > 0 and eng.healthy()
+            state["ok"] = False
+            with pytest.raises(RuntimeError, match="lost its CUDA context"):
+                async for c in eng.stream(**kw):
+                    pass
+        finally:
+            eng.shutdown()
+    asyncio.run(go())

@@ -55,6 +55,7 @@ def test_stream_is_deterministic_and_sized(engine):
     assert a.shape[0] > 24000 and a.shape[0] % 2 == 0
     assert np.array_equal(a, b), "fixed seed + fixed request id must reproduce the PCM bit for bit"
     assert np.abs(a).max() <= 32767
+    assert engine.healthy() and engine.native.healthy()      # cbx_engine_health: no sticky device fault
 
 
 def test_concurrent_streams_match_sequential(engine):

@@ -319,16 +319,22 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         launch_gemv(g, nwarps, st);
     };
     const int n_layers = e->cfg.t3_layers, al = std::min(m.align_layer, n_layers - 1);
+    // L2 prefetch two kernels ahead along the chain [QKV, attention, O, gate/up, down]: QKV pulls the O weights, attention the
+    // gate/up weights, O the down weights, gate/up the next layer's QKV weights (the head's after the last layer)
+    static const int pf_on = [] { const char* v = getenv("CBX_T3_L2_PREFETCH"); return v ? atoi(v) : 1; }();
+    const size_t B_QKV = (size_t)3 * T3_D * T3_D * 2, B_O = (size_t)T3_D * T3_D * 2, B_GU = (size_t)2 * T3_FFN * T3_D * 2, B_D = (size_t)T3_D * T3_FFN * 2;
     for (int li = 0; li < n_layers; li++) {
         const T3Layer& l = m.layers[li];
         GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1;
         q.row_map = m.d_rowmap; q.rows = rows; q.eps = 1e-5f; q.out = m.qkv; q.ld_out = 3 * T3_D; q.epi = GEMV_STORE;
         if (li == 0) { q.x = m.x; q.ldx_in = T3_D; q.gain = l.ln1; }
         else { q.xb = m.xb; q.ldxb = T3_D; q.ss_in = m.ss; q.n_ss = T3_D / 16; }
+        if (pf_on && !tc) { q.pf_ptr = l.wo_f; q.pf_bytes = B_O; }
         gemv(q, l.tm_qkv, 8);
         DecodeAttnParams a; a.qkv = m.qkv; a.out_b = m.attn_b; a.kv = m.kv + li * m.kv_layer_stride; a.kv_half = m.kv_half; a.page_table = m.page_table;
         a.max_pages = m.max_pages; a.slot_pos = m.slot_pos; a.row_map = m.d_rowmap; a.inv_freq = m.inv_freq; a.H = T3_H;
         if (m.align && li == al) a.q_save = m.align_q;
+        if (pf_on && !tc) { a.pf_ptr = l.wgu_f; a.pf_bytes = B_GU; }
         launch_decode_attn(a, rows, e->cfg.max_seq, st);
         if (m.align && li == al) {
             // alignment row of this frame and the analyzer's decision, on a side branch that joins before the sampler: its inputs
@@ -345,10 +351,15 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.xb = m.attn_b; o.ldxb = T3_D;
         o.row_map = m.d_rowmap; o.rows = rows; o.out = m.x; o.ld_out = T3_D; o.epi = GEMV_RESID;
         o.out_b = m.xb; o.ld_out_b = T3_D; o.next_gain = l.ln2; o.ss_out = m.ss;
+        if (pf_on && !tc) { o.pf_ptr = l.wd_f; o.pf_bytes = B_D; }
         gemv(o, l.tm_o, 16);
         GemvParams gu; gu.Wf = l.wgu_f; gu.N = 2 * T3_FFN; gu.K = T3_D; gu.n_strips = 2 * T3_FFN / 16; gu.strips_per_cta = gu_strips;
         gu.xb = m.xb; gu.ldxb = T3_D; gu.ss_in = m.ss; gu.n_ss = T3_D / 16;
         gu.row_map = m.d_rowmap; gu.rows = rows; gu.eps = 1e-5f; gu.out_b = m.act_b; gu.ld_out_b = T3_FFN; gu.epi = GEMV_GLU;
+        if (pf_on && !tc) {
+            if (li + 1 < n_layers) { gu.pf_ptr = m.layers[li + 1].wqkv_f; gu.pf_bytes = B_QKV; }
+            else { gu.pf_ptr = m.head_f; gu.pf_bytes = (size_t)T3_VPAD * T3_D * 2; }
+        }
         gemv(gu, l.tm_gu, 8);
         GemvParams d; d.Wf = l.wd_f; d.N = T3_D; d.K = T3_FFN; d.n_strips = T3_D / 16; d.strips_per_cta = 1; d.xb = m.act_b; d.ldxb = T3_FFN;
         d.row_map = m.d_rowmap; d.rows = rows; d.out = m.x; d.ld_out = T3_D; d.epi = GEMV_RESID;

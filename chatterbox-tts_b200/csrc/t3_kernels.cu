@@ -8,6 +8,13 @@
 
 namespace {
 
+// This CTA's share of an L2 prefetch of [ptr, ptr + bytes): one 128-byte line per instruction, fire and forget.
+__device__ __forceinline__ void l2_prefetch_slice(const void* ptr, size_t bytes, int cta, int n_cta, int tid, int n_thr) {
+    const size_t lines = bytes >> 7, per = (lines + n_cta - 1) / n_cta, l0 = (size_t)cta * per, l1 = l0 + per < lines ? l0 + per : lines;
+    const char* base = static_cast<const char*>(ptr);
+    for (size_t i = l0 + tid; i < l1; i += n_thr) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (i << 7)));
+}
+
 // ------------------------------------------------------------------------------------------------
 // GEMV: y[r][f] = sum_k W[f][k] * xin[r][k] for r < rows (<= 8*NT).  W is stored in mma.m16n8k16
 // A-fragment order: tile (strip s, ktile kt) = 32 lanes x 8 bf16 (512 B, contiguous), tiles ordered
@@ -38,6 +45,7 @@ __global__ void __launch_bounds__(512) gemv_kernel(const GemvParams p) {
         for (int u = 0; u < 8; u++) wpre[u] = (strip0 < p.n_strips && u < perp) ? __ldg(wp0 + (size_t)u * 32) : make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid < R) rmap[tid] = tid < p.rows ? p.row_map[tid] : 0;
+    if (p.pf_ptr) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, blockIdx.x, gridDim.x, tid, blockDim.x);
     __syncthreads();
     pdl_wait();
     // residual epilogue: the old value of this thread's output element is requested now, not after the main loop
@@ -253,6 +261,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
         for (int c = 0; c < 4; c++) { k[c] = kp[c]; v[c] = vp[c]; }
     };
     if (PIPE) fetch(pte0, ku, vu);
+    if (p.pf_ptr) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, tid, blockDim.x);
     pdl_wait();
     const int pos = p.slot_pos[slot];
     const float* qkv = p.qkv + (long)row * (3 * p.H * HD);

@@ -18,6 +18,9 @@ struct GemvParams {
     bf16* out_b = nullptr; long ld_out_b = 0;     // GLU: bf16 activations (instead of out); RESID: bf16(x_new * next_gain)
     const float* next_gain = nullptr;             // RESID: gain of the RMSNorm that consumes the updated residual row
     float* ss_out = nullptr;                      // RESID: [rows_total][n_strips] sum of squares of this strip's 16 new values
+    // weights of a LATER kernel of the step, pulled into L2 by this one before it waits for its predecessor: HBM keeps streaming
+    // through the dependency latency of the chain, the later kernel's own loads hit L2
+    const void* pf_ptr = nullptr; size_t pf_bytes = 0;
 };
 void launch_gemv(const GemvParams& p, int nwarps, cudaStream_t st);
 // tcgen05 form for batched rows (t3_gemv_tc.cu): row-major weights through a TMA descriptor built once per weight
@@ -47,6 +50,7 @@ struct DecodeAttnParams {
     const float* inv_freq = nullptr;     // [32]
     int H = 16;
     float* q_save = nullptr;             // optional [rows_total][H*64]: the rotated, scaled queries (alignment probe layer)
+    const void* pf_ptr = nullptr; size_t pf_bytes = 0;   // as in GemvParams
 };
 void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaStream_t st);
 

@@ -129,6 +129,11 @@ class T3Scheduler(threading.Thread):
         self.open_q = collections.deque()
         self.open_gather_s = float(os.environ.get("CBX_T3_OPEN_GATHER_MS", "0.5")) * 1e-3
         self.unhealthy: Optional[BaseException] = None   # a native slot could not be closed: its pages are lost, refuse new work
+        # T3 stream priority per decode round (native.t3_set_priority): high_priority() is asked before every round.  The engine
+        # wires it to "no first slice of a request is waiting for S3Gen": T3 runs ahead of the wide S3Gen grids (throughput) except
+        # while a request's first audio is being synthesised (first-chunk latency).
+        self.high_priority = None
+        self._prio = None
         self.opener = threading.Thread(target=self._opener, daemon=True, name="cbx-t3-opener")
         self.opener.start()
         self.start()
@@ -241,6 +246,11 @@ class T3Scheduler(threading.Thread):
             try:
                 t_busy = time.time()
                 with self._ctx():
+                    if self.high_priority is not None:
+                        want = bool(self.high_priority())
+                        if want != self._prio:
+                            self.native.t3_set_priority(want)
+                            self._prio = want
                     self.native.t3_step([s.slot for s in live], self.k)
                     for s in live:
                         n, done = self.native.t3_poll(s.slot)
@@ -346,6 +356,13 @@ class S3GenBatcher:
         self.window = os.environ.get("CBX_HIFT_WINDOW", "1") != "0"
         self.gather_always = os.environ.get("CBX_S3GEN_GATHER_ALWAYS", "0") == "1"      # experiment: also gather when jobs were already pending
         self.urgent_window_s = float(os.environ.get("CBX_S3GEN_URGENT_MS", "15")) * 1e-3   # upper bound; the emitter ends it
+        self._urgent = []                      # urgent jobs (first audio of a request) submitted and not finished yet
+        # imminent(): how many OTHER requests are about to submit their first slice (their T3 streams are within two decode rounds
+        # of it).  A gather window that holds a first slice stays open for them (bounded): requests that arrived together but
+        # whose prefills fell into different passes decode one round apart, and "one alone, seven in the next batch" costs the
+        # seven a whole extra call (first chunk 107 / 181 ms instead of ~125 for all)
+        self.imminent = None
+        self.urgent_gather_s = float(os.environ.get("CBX_S3GEN_URGENT_GATHER_MS", "15")) * 1e-3
         self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
         for t in self.threads:
             t.start()
@@ -354,8 +371,17 @@ class S3GenBatcher:
         job = _S3Job(voice, toks, dep, seed, urgent, emit_from if self.window else 0)
         with self.cv:
             self.jobs.append(job)
+            if urgent:
+                self._urgent.append(job)
             self.cv.notify_all()
         return job
+
+    def urgent_inflight(self) -> bool:
+        """True while some request's first slice is queued or on the GPU (the T3 scheduler then yields the SMs to it)."""
+        with self.cv:
+            if self._urgent:
+                self._urgent = [j for j in self._urgent if not j.done.is_set()]
+            return bool(self._urgent)
 
     def infer(self, voice, toks, cache_source, seed):
         """Blocking single call (cache_source given as a finished tensor)."""
@@ -396,10 +422,14 @@ class S3GenBatcher:
                     if idle and self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch:
                         # every submit wakes this wait: keep gathering until the window (counted from the first job) closes
                         t_end = time.time() + self.gather_s
+                        t_cap = time.time() + self.urgent_gather_s
                         while self.running and len(self.jobs) < self.max_batch:
-                            left = t_end - time.time()
+                            now = time.time()
+                            left = t_end - now
                             if left <= 0:
-                                break
+                                if self.imminent is None or now >= t_cap or not any(j.urgent for j in self.jobs) or self.imminent() <= 0:
+                                    break
+                                left = min(0.001, t_cap - now)
                             self.cv.wait(left)
                     batch = self._take() if self.jobs else []
                     if batch:
@@ -566,6 +596,7 @@ class TextToSpeechEngine:
         # reference's fork runs it inside inference_stream is unknown, and with random-init weights its verdicts mean nothing, so
         # it is opt-in (CBX_ALIGNMENT_EOS=1 / alignment_eos=True; probe layer CBX_ALIGNMENT_LAYER, upstream 9)
         self.alignment_eos = (os.environ.get("CBX_ALIGNMENT_EOS", "0") == "1") if alignment_eos is None else bool(alignment_eos)
+        self._first_pending, self._fp_lock = {}, threading.Lock()   # chunk-0 T3 streams whose first slice is not submitted yet
         self._seq = 0
         self._seq_lock = threading.Lock()
         self._ready = False
@@ -619,6 +650,13 @@ class TextToSpeechEngine:
         # up to 16 streams (32 rows) decode in ONE pass over the weights; more are rotated in groups
         self.scheduler = T3Scheduler(self.native, max_batch=min(int(os.environ.get("CBX_T3_MAX_BATCH", "16")), self.native_kwargs["max_streams"]))
         self.s3gen = S3GenBatcher(self.native)
+        self.s3gen.imminent = self._imminent_first_slices
+        # CBX_T3_PRIORITY_MODE: auto (default) = T3 on its high-priority stream except while a first slice is in S3Gen, high / low = pinned
+        mode = os.environ.get("CBX_T3_PRIORITY_MODE", "auto")
+        if mode == "auto":
+            self.scheduler.high_priority = lambda: not self.s3gen.urgent_inflight()
+        elif mode == "high":
+            self.scheduler.high_priority = lambda: True
         self.t3_slots = PrioritySlots(self.native_kwargs["max_streams"] - 1)   # one slot stays free for warm-up / direct opens
         # warm-up, as the reference does (:274-326): 4 T3 tokens with cfg 0, one tiny S3Gen call
         text = [self.cfg.t3.start_text_token] + self.tokenizer.text_to_tokens("compiling")[0].tolist() + [self.cfg.t3.stop_text_token]
@@ -627,6 +665,10 @@ class TextToSpeechEngine:
         self.native.s3gen_infer(self.voice_cache["default"], [0, 0, 0])
         torch.cuda.synchronize()
         self._ready = True
+
+    def _imminent_first_slices(self) -> int:
+        with self._fp_lock:
+            return sum(1 for st, need in self._first_pending.values() if st.error is None and not st.cancelled and len(st.tokens) >= need - 14)
 
     def healthy(self) -> bool:
         """False once the GPU context is unusable (sticky device fault); backends without the probe count as healthy."""
@@ -829,6 +871,8 @@ class TextToSpeechEngine:
                     have_slot = False
                     if ci == 0:
                         trace("t3_open")
+                        with self._fp_lock:
+                            self._first_pending[id(s)] = (s, slice_len + look_ahead)
                     is_first_chunk, is_last_chunk = ci == 0, ci == len(chunks) - 1
                     consumed, slice_idx, acc, prev_job = 0, 0, [], None
                     while not stop.is_set():
@@ -866,6 +910,9 @@ class TextToSpeechEngine:
                         job = self.s3gen.submit(voice, toks, prev_job if overlap == "full" else None, base_seed + 7919 * ci + slice_idx,
                                                 urgent=(ci == 0 and first_slice),
                                                 emit_from=960 * len(prev_job.toks) if (overlap == "full" and prev_job is not None) else 0)
+                        if ci == 0 and first_slice:
+                            with self._fp_lock:
+                                self._first_pending.pop(id(s), None)
                         prev_job = job
                         jobs.append(job)
                         outq[ci].put((job, first_slice, last))
@@ -876,6 +923,9 @@ class TextToSpeechEngine:
                 finally:
                     if ci == 0:
                         first_slice_ready.set()
+                        if streams[ci] is not None:
+                            with self._fp_lock:
+                                self._first_pending.pop(id(streams[ci]), None)
                     if have_slot:
                         self.t3_slots.release()
                     if streams[ci] is not None and not streams[ci].finished:

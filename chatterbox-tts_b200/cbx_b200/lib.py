@@ -56,6 +56,7 @@ SIGNATURES = {
     "cbx_t3_open_batch": (_I, [_P, C.POINTER(T3OpenReq), _I, _P, _P]),
     "cbx_t3_step": (_I, [_P, _P, _I, _I, _P, _P]),
     "cbx_t3_set_persistent": (_I, [_P, _I]),
+    "cbx_t3_set_priority": (_I, [_P, _I]),
     "cbx_t3_set_alignment_eos": (_I, [_P, _I, _I]),
     "cbx_t3_alignment_peek": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "cbx_t3_alignment_poke": (_I, [_P, _I, _P, _P, _P]),

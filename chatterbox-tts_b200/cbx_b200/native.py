@@ -207,6 +207,10 @@ class NativeEngine:
     def t3_set_persistent(self, on: bool):
         L.check(self.lib.cbx_t3_set_persistent(self.h, 1 if on else 0))
 
+    def t3_set_priority(self, high: bool):
+        """T3 work on the engine's high- or low-priority stream (include/cbx_b200.h::cbx_t3_set_priority)."""
+        L.check(self.lib.cbx_t3_set_priority(self.h, 1 if high else 0))
+
     def t3_set_alignment_eos(self, on: bool, layer: int = 9):
         """Alignment-based EOS control for the generators opened after this call (include/cbx_b200.h)."""
         L.check(self.lib.cbx_t3_set_alignment_eos(self.h, 1 if on else 0, int(layer)))

@@ -87,12 +87,17 @@ int cbx_engine_create(const cbx_config* cfg, int device, cbx_engine** out) {
     gemm_init(); attention_init();
     t3_build(e); flow_build(e); hift_build(e);
     t3_alloc(e);
-    {   // CBX_T3_PRIORITY=1 runs T3 at the highest stream priority (its ~150 short dependent kernels per step queue behind the
-        // wide S3Gen launches).  Off by default: measured on the pipelined paragraph it lowers throughput (38 vs 44 audio-s/s)
+    {   // T3's ~150 short dependent kernels per step queue behind the wide S3Gen launches of the other streams.  Two streams, lowest
+        // and highest priority; the host moves T3 between them (cbx_t3_set_priority): high while no first slice of a request is
+        // waiting for S3Gen (throughput), low while one is (first-chunk latency).  CBX_T3_PRIORITY=1 / 0 pins the initial choice.
         int lo = 0, hi = 0;
         CBX_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CBX_CHECK(cudaStreamCreateWithPriority(&e->t3_st_prio[0], cudaStreamNonBlocking, lo));
+        CBX_CHECK(cudaStreamCreateWithPriority(&e->t3_st_prio[1], cudaStreamNonBlocking, hi));
+        CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_sw, cudaEventDisableTiming));
         const char* pr = getenv("CBX_T3_PRIORITY");
-        CBX_CHECK(cudaStreamCreateWithPriority(&e->t3_st, cudaStreamNonBlocking, (pr && pr[0] == '1') ? hi : lo));
+        e->t3_prio = (pr && pr[0] == '1') ? 1 : 0;
+        e->t3_st = e->t3_st_prio[e->t3_prio];
     }
     CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_in, cudaEventDisableTiming));
     CBX_CHECK(cudaEventCreateWithFlags(&e->t3_ev_out, cudaEventDisableTiming));
@@ -142,7 +147,7 @@ void cbx_engine_destroy(cbx_engine* e) {
         for (auto& ev : L->ev_call) cudaEventDestroy(ev);
     }
     for (Lane* L : e->lanes) { for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second); cudaFreeHost(L->g_dyn_h); cudaStreamDestroy(L->st); cudaEventDestroy(L->ev_in); cudaEventDestroy(L->ev_out); delete L; }
-    cudaStreamDestroy(e->t3_st); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
+    cudaStreamDestroy(e->t3_st_prio[0]); cudaStreamDestroy(e->t3_st_prio[1]); cudaEventDestroy(e->t3_ev_sw); cudaEventDestroy(e->t3_ev_in); cudaEventDestroy(e->t3_ev_out);
     if (e->t3.align_st) { cudaStreamDestroy(e->t3.align_st); cudaEventDestroy(e->t3.align_fork); cudaEventDestroy(e->t3.align_join); }
     delete e;
 }
@@ -266,6 +271,21 @@ int cbx_t3_set_persistent(cbx_engine* e, int on) {
     std::lock_guard<std::mutex> g(e->t3_mu);
     CBX_REQUIRE(!on || e->t3.mega_ok, "persistent T3 kernel is not available on this device");
     e->t3.mega = on != 0;
+    CBX_API_END
+}
+
+int cbx_t3_set_priority(cbx_engine* e, int high) {
+    CBX_API_BEGIN
+    CBX_REQUIRE(e, "null engine");
+    std::lock_guard<std::mutex> g(e->t3_mu);
+    const int want = high ? 1 : 0;
+    if (want != e->t3_prio) {   // later T3 work is ordered after everything already queued on the other stream
+        CBX_CHECK(cudaSetDevice(e->device));
+        CBX_CHECK(cudaEventRecord(e->t3_ev_sw, e->t3_st));
+        CBX_CHECK(cudaStreamWaitEvent(e->t3_st_prio[want], e->t3_ev_sw, 0));
+        e->t3_st = e->t3_st_prio[want];
+        e->t3_prio = want;
+    }
     CBX_API_END
 }
 

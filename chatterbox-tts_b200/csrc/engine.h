@@ -117,6 +117,7 @@ struct cbx_engine {
     T3Model t3; FlowModel flow; HiftModel hift;
     std::vector<Voice> voices; std::mutex voice_mu;
     std::mutex t3_mu; cudaStream_t t3_st; cudaEvent_t t3_ev_in, t3_ev_out;
+    cudaStream_t t3_st_prio[2] = {nullptr, nullptr}; cudaEvent_t t3_ev_sw = nullptr; int t3_prio = 0;   // T3 work moves between a low- and a high-priority stream (cbx_t3_set_priority)
     std::vector<Lane*> lanes; std::mutex lane_pick_mu; int lane_rr = 0;
     std::vector<Lane*> batch_lanes;   // workspaces of cbx_s3gen_infer_batch (FLOW_MAXB calls each): two batches can be in flight
     std::atomic<long> gpu_launches{0};   // statistics only, bumped from the T3, S3Gen and request threads

@@ -84,6 +84,11 @@ int cbx_t3_step(cbx_engine* e, const int32_t* slots_h, int n_slots, int n_steps,
 /* selects the decode-step implementation: 0 = per-projection GEMV kernels (default), 1 = one persistent kernel per step
  * (lower latency for one or two streams, but it owns every SM while it runs; also enabled by CBX_T3_MEGA=1) */
 int cbx_t3_set_persistent(cbx_engine* e, int on);
+/* Moves the engine's T3 work to its high- (1) or low-priority (0) CUDA stream; work already queued stays ordered before what follows.
+ * The decode step is a chain of ~150 short kernels that queue behind the wide S3Gen grids of the other streams: high priority buys
+ * throughput (T3 runs ahead, S3Gen batches fill), low priority keeps a request's first S3Gen call fast.  The host scheduler switches
+ * per decode batch (low while a first slice is pending).  No reference counterpart (torch streams there have one priority). */
+int cbx_t3_set_priority(cbx_engine* e, int high);
 /* Alignment-based EOS control of the generators opened AFTER this call (off by default).  Reference side: the model package's
  * AlignmentStreamAnalyzer, hooked on the attention of trunk layer `layer` (upstream: 9) inside the T3.inference_stream generator
  * that src/tts_streaming.py:420-435 primes -- the attention of the conditional row's newest query over the text span, averaged

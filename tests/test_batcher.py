@@ -212,3 +212,43 @@ def test_scheduler_can_align_streams_that_open_together(monkeypatch):
     assert len(first_aligned) == 4            # all four streams in the first decode round
     assert len(first_plain) < 4               # without alignment the first stream runs ahead of the others' prefills
     assert sorted(map(tuple, toks_aligned)) == sorted(map(tuple, toks_plain))   # same tokens either way
+
+
+def test_gather_window_waits_for_imminent_first_slices():
+    """A first slice that opens a gather window is held (bounded) while other requests are about to submit theirs: requests that
+    decode one T3 round apart still share ONE batch; a lone request (nothing imminent) is not delayed beyond the short window;
+    the extension is capped."""
+    nat = BatchNative()
+    b = S3GenBatcher(nat, max_batch=8, workers=1)
+    b.gather_s, b.urgent_gather_s = 0.003, 0.2
+    pending = {"n": 1}
+    b.imminent = lambda: pending["n"]
+    try:
+        t0 = time.time()
+        j0 = b.submit(0, _toks(35), None, 1, urgent=True)
+        time.sleep(0.03)                       # ten short windows later the second request's first slice arrives
+        j1 = b.submit(0, _toks(35, 3), None, 2, urgent=True)
+        pending["n"] = 0
+        j0.consumed.set(); j1.consumed.set()
+        j0.wait(); j1.wait()
+        assert nat.batches[0] == [(35, None), (35, None)], nat.batches
+        # nothing imminent: only the short window
+        t1 = time.time()
+        j2 = b.submit(0, _toks(35, 4), None, 3, urgent=True)
+        j2.consumed.set()
+        j2.wait()
+        assert time.time() - t1 < 0.1 and len(nat.batches) == 2
+        # imminent forever: the cap ends the wait
+        pending["n"] = 5
+        t2 = time.time()
+        j3 = b.submit(0, _toks(35, 5), None, 4, urgent=True)
+        j3.consumed.set()
+        j3.wait()
+        assert 0.15 < time.time() - t2 < 1.0
+        # a window without a first slice in it does not wait for imminent ones
+        t3 = time.time()
+        j4 = b.submit(0, _toks(35, 6), None, 5)
+        j4.wait()
+        assert time.time() - t3 < 0.1
+    finally:
+        b.stop()

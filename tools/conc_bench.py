@@ -36,6 +36,12 @@ for lanes in lanes_list:
             return nb, first
         await asyncio.gather(*[one(i) for i in range(streams)])
         torch.cuda.synchronize()
+        for w in range(int(os.environ.get("CONC_EXTRA_WAVES", "0"))):     # more waves back to back: first chunks and batch sizes per wave
+            nb0 = dict(eng.s3gen.batches)
+            r = await asyncio.gather(*[one(i) for i in range(streams)])
+            torch.cuda.synchronize()
+            print(json.dumps({"wave": w, "first_chunk_ms": sorted(round(x[1], 1) for x in r),
+                              "s3gen_batches": {k: v - nb0.get(k, 0) for k, v in sorted(eng.s3gen.batches.items()) if v - nb0.get(k, 0)}}), flush=True)
         b0, r0, n0 = eng.s3gen.busy_s, eng.scheduler.busy_s, dict(eng.s3gen.batches)
         eng.scheduler.row_hist.clear()
         t0 = time.time()

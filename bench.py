@@ -504,7 +504,7 @@ def run_b200(args):
         firsts = [f for f in firsts if f is not None]
         line = {"metric": "audio_sec_per_sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": bench_config(), "engine": {"chunk_parallelism": eng.chunk_parallelism, "audio_s_per_step": audio_s / args.steps / world},
+                "config": bench_config(), "engine": {"chunk_parallelism": eng.chunk_parallelism, "chunk_parallelism_short_requests": eng.chunk_parallelism_short, "audio_s_per_step": audio_s / args.steps / world},
                 "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(4 * (WORDS * 6 + WORDS * TOK_PER_WORD * 4)), "d2h_bytes_per_step": int(e2e_bytes / args.steps + 4 * WORDS * TOK_PER_WORD),
                         "first_chunk_ms_p50": statistics.median(firsts) if firsts else None, "rtf": (e2e_ms_max / 1e3) / max(e2e_audio, 1e-9)},

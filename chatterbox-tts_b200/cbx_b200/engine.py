@@ -568,6 +568,10 @@ class TextToSpeechEngine:
         self.native_kwargs = dict(max_streams=max(int(os.environ.get("CBX_MAX_STREAMS", "16")), n), n_lanes=2)
         # text chunks of one request that may be in flight at once (T3 decoding + S3Gen), ahead of the chunk being emitted
         self.chunk_parallelism = int(os.environ.get("CBX_CHUNK_PARALLELISM", "8"))
+        # a request whose chunks ALL fit in this many streams starts them all (after chunk 0's first slice): there is no steady
+        # state to protect, T3 finishes in one go and S3Gen batches fill.  Measured: 200-word paragraph (10 chunks) 71.4 -> 74.0
+        # audio-s/s end to end; a 2000-word document is better off with 8 in flight (64.3 vs 60.4 at 16)
+        self.chunk_parallelism_short = int(os.environ.get("CBX_CHUNK_PARALLELISM_SHORT", "16"))
         # later chunks of a request start when chunk 0's first slice is on its way: "audio" = its PCM has been sent (lowest
         # first-chunk latency), "tokens" = its tokens are decoded (their prefills overlap the first S3Gen call: +throughput)
         # "auto": "audio" for a request that is alone on the GPU, "tokens" when others are in flight.  Measured at 8 streams:
@@ -579,7 +583,7 @@ class TextToSpeechEngine:
         self._inflight_lock = threading.Lock()
         # one worker thread per text chunk in flight: every request can have chunk_parallelism of them (most just wait for a T3
         # slot or for tokens), so the pool is sized for that product and a new request never queues behind waiting chunks
-        self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=max(32, n * (self.chunk_parallelism + 1)), thread_name_prefix="cbx-chunk")
+        self.chunk_executor = concurrent.futures.ThreadPoolExecutor(max_workers=max(32, n * (max(self.chunk_parallelism, self.chunk_parallelism_short) + 1)), thread_name_prefix="cbx-chunk")
         self.s3gen: Optional[S3GenBatcher] = None
         self._pinned_pool: queue.Queue = queue.Queue()
         self.t3_slots: Optional[PrioritySlots] = None
@@ -848,7 +852,8 @@ class TextToSpeechEngine:
             streams = [None] * len(chunks)
             outq = [queue.Queue() for _ in chunks]           # per chunk: (cur, last) items, then None (or an exception)
             first_slice_ready = threading.Event()            # chunk 0's first slice has been synthesised (or chunk 0 is done)
-            window = threading.Semaphore(max(1, self.chunk_parallelism))   # chunks in flight ahead of the emitter
+            par = len(chunks) if self.chunk_parallelism < len(chunks) <= self.chunk_parallelism_short else self.chunk_parallelism
+            window = threading.Semaphore(max(1, par))   # chunks in flight ahead of the emitter
             stop = threading.Event()
 
             def chunk_worker(ci):

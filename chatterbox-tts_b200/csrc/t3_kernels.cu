@@ -233,18 +233,18 @@ constexpr int PAGE = 16, HD = 64;
 // Flash-decoding form: each of the 8 warps streams whole KV pages (K and V of a page are fetched together) and keeps an
 // online-softmax partial (m, l, o[64]); the partials are merged in shared memory -- two block barriers and two global
 // round trips instead of five and three.
-template <bool PIPE>
-__global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams p) {
+template <bool PIPE, int NW>
+__global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const DecodeAttnParams p) {
     __shared__ float qs[HD];
-    __shared__ float wm[8], wl[8];
-    __shared__ float wo[8 * HD];
+    __shared__ float wm[NW], wl[NW];
+    __shared__ float wo[NW * HD];
     const int h = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the row map and the page table are written by the host between steps only: read them before waiting for the QKV kernel
     pdl_launch_dependents();
     const int row = p.row_map[r];
     const int slot = row >> 1;
     const int* pt = p.page_table + (long)row * p.max_pages;
-    int pte0 = warp < p.max_pages ? pt[warp] : 0, pte1 = warp + 8 < p.max_pages ? pt[warp + 8] : 0;
+    int pte0 = warp < p.max_pages ? pt[warp] : 0, pte1 = warp + NW < p.max_pages ? pt[warp + NW] : 0;
     bf16* kpool = p.kv;
     bf16* vpool = p.kv + p.kv_half;
     const int pp = lane >> 1, half = lane & 1;
@@ -288,12 +288,12 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
     float acc[32];
 #pragma unroll
     for (int d = 0; d < 32; d++) acc[d] = 0.f;
-    for (int pg = warp; pg < npages; pg += 8) {
-        const int nx = pg + 8;
+    for (int pg = warp; pg < npages; pg += NW) {
+        const int nx = pg + NW;
         int pte2 = 0;
         if (PIPE) {
             if (nx < npages) fetch(pte1, kn, vn);
-            pte2 = nx + 8 < npages ? pt[nx + 8] : 0;
+            pte2 = nx + NW < npages ? pt[nx + NW] : 0;
         } else if (pg != warp) fetch(pt[pg], ku, vu);
         float sc = 0.f;
 #pragma unroll
@@ -345,10 +345,10 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const DecodeAttnParams
     if (tid < HD) {
         float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < 8; w++) M = fmaxf(M, wm[w]);
+        for (int w = 0; w < NW; w++) M = fmaxf(M, wm[w]);
         float Lt = 0.f, O = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
+        for (int w = 0; w < NW; w++) {
             const float e = wm[w] == -INFINITY ? 0.f : expf(wm[w] - M);
             Lt += wl[w] * e; O += wo[w * HD + tid] * e;
         }
@@ -770,8 +770,14 @@ void launch_decode_attn(const DecodeAttnParams& p, int rows, int max_pos, cudaSt
     // bit-identical results.
     static const int pipe_env = [] { const char* v = getenv("CBX_T3_ATTN_PIPE"); return v ? atoi(v) : -1; }();
     const bool pipe = pipe_env >= 0 ? pipe_env != 0 : rows <= 8;
-    if (pipe) launch_pdl(decode_attn_kernel<true>, dim3(p.H, rows), dim3(256), 0, st, p);
-    else launch_pdl(decode_attn_kernel<false>, dim3(p.H, rows), dim3(256), 0, st, p);
+    // 122 registers x 256 threads = two CTAs per SM = 296 resident: from 19 rows (304 CTAs) the grid would take a second wave
+    // (measured: 18 rows 1.23 ms per step, 20 rows 1.41).  Beyond that, four-warp CTAs (four per SM, 592 resident) keep every
+    // (row, head) resident at once; each warp walks twice the pages.  The merge order over warps differs between the two shapes,
+    // so the choice depends on the batch's row count only through this fixed threshold (results for <= 18 rows are unchanged).
+    static const int nw4_rows = [] { const char* v = getenv("CBX_T3_ATTN_NW4_ROWS"); return v ? atoi(v) : 19; }();
+    if (rows >= nw4_rows) launch_pdl(decode_attn_kernel<false, 4>, dim3(p.H, rows), dim3(128), 0, st, p);
+    else if (pipe) launch_pdl(decode_attn_kernel<true, 8>, dim3(p.H, rows), dim3(256), 0, st, p);
+    else launch_pdl(decode_attn_kernel<false, 8>, dim3(p.H, rows), dim3(256), 0, st, p);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st) {

@@ -17,7 +17,8 @@ from cbx_b200.weights import random_state_dict, synthetic_conditionals
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     cfg = ModelConfig()
-    eng = NativeEngine(cfg, max_streams=8, n_lanes=1)
+    stream_counts = tuple(int(x) for x in os.environ.get("MICRO_STREAMS", "1,2,4,8").split(","))
+    eng = NativeEngine(cfg, max_streams=max(8, max(stream_counts)), n_lanes=1)
     eng.load_state_dict(random_state_dict(cfg, 0))
     conds = synthetic_conditionals(cfg)
     v = eng.voice_put("default", conds["t3"], conds["gen"])
@@ -41,7 +42,7 @@ def main():
                     eng.t3_close(s)
         print(json.dumps(out, indent=1))
         return
-    for ns in (() if only == "s3b" else (1, 2, 4, 8)):
+    for ns in (() if only == "s3b" else stream_counts):
         t0 = time.time()
         slots = [eng.t3_open(v, text, seed=i, max_new=1000) for i in range(ns)]
         torch.cuda.synchronize()

@@ -270,7 +270,7 @@ void t3_open_batch(cbx_engine* e, const T3OpenReq* reqs, int n, int* slots_out, 
         const T3OpenReq& r = reqs[i];
         T3SlotState s{};
         s.pos = Lp[i]; s.step = 0; s.max_new = r.max_new; s.done = 0; s.cfg_w = r.cfg_w; s.temp = r.temp; s.rep_pen = r.rep; s.min_p = r.min_p; s.top_p = r.top_p; s.seed = r.seed;
-        launch_init_slot(m.slot_state, s, m.slot_pos, slots_out[i], m.seen, T3_VPAD, T3_BOS, m.x, m.speech_emb, m.speech_pos, T3_D, st);
+        launch_init_slot(m.slot_state, s, m.slot_pos, slots_out[i], m.seen, T3_VPAD, T3_BOS, m.x, m.speech_emb, m.speech_pos, T3_D, m.xb, m.ss, m.layers[0].ln1, st);
     }
     e->gpu_launches += 3L * n + (7L + n) * c.t3_layers;
 }
@@ -289,6 +289,7 @@ static void enqueue_sampler(cbx_engine* e, int n, const float* noise, cudaStream
     s.seen = m.seen; s.seen_stride = T3_VPAD; s.out_tokens = m.out_tokens; s.out_stride = m.out_stride; s.noise = noise; s.noise_stride = T3_V;
     s.x = m.x; s.speech_emb = m.speech_emb; s.speech_pos = m.speech_pos; s.V = T3_V; s.dim = T3_D; s.eos = T3_EOS;
     s.eos_ctl = m.align ? m.align_ctl : nullptr;
+    s.xb = m.xb; s.ss = m.ss; s.gain0 = m.layers[0].ln1;
     launch_sampler(s, n, st);
 }
 
@@ -327,7 +328,9 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         const T3Layer& l = m.layers[li];
         GemvParams q; q.Wf = l.wqkv_f; q.N = 3 * T3_D; q.K = T3_D; q.n_strips = 3 * T3_D / 16; q.strips_per_cta = 1;
         q.row_map = m.d_rowmap; q.rows = rows; q.eps = 1e-5f; q.out = m.qkv; q.ld_out = 3 * T3_D; q.epi = GEMV_STORE;
-        if (li == 0) { q.x = m.x; q.ldx_in = T3_D; q.gain = l.ln1; }
+        // layer 0 reads the fp32 row the sampler wrote; on the tcgen05 path (>= 17 rows, where 32 fp32 rows per CTA would spill in
+        // the staging) it takes the bf16 hand-over form the sampler / slot init wrote beside it
+        if (li == 0 && !tc) { q.x = m.x; q.ldx_in = T3_D; q.gain = l.ln1; }
         else { q.xb = m.xb; q.ldxb = T3_D; q.ss_in = m.ss; q.n_ss = T3_D / 16; }
         if (pf_on && !tc) { q.pf_ptr = l.wo_f; q.pf_bytes = B_O; }
         gemv(q, l.tm_qkv, 8);

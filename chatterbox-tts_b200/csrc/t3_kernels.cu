@@ -383,6 +383,21 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
     return r;
 }
 
+// The bf16 hand-over form of a new input row (both CFG rows of `slot`): bf16(v * gain0[d]) and the sum of squares of every 16
+// columns (16 consecutive lanes).  Called by whole warps.
+__device__ __forceinline__ void write_handover(bf16* xb, float* ss, const float* gain0, int slot, int d, int dim, float v) {
+    const bf16 b = __float2bfloat16(v * gain0[d]);
+    xb[(long)(slot * 2) * dim + d] = b;
+    xb[(long)(slot * 2 + 1) * dim + d] = b;
+    float s = v * v;
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4); s += __shfl_xor_sync(0xffffffffu, s, 8);
+    if ((d & 15) == 0) {
+        ss[(long)(slot * 2) * (dim / 16) + (d >> 4)] = s;
+        ss[(long)(slot * 2 + 1) * (dim / 16) + (d >> 4)] = s;
+    }
+}
+
 __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) {
     pdl_prologue();
     __shared__ float red[32];
@@ -503,10 +518,11 @@ __global__ void __launch_bounds__(SAMP_T) sampler_kernel(const SamplerParams p) 
     const int tok = besti[0];
     const int step = st->step;
     // next input embedding (both CFG rows): speech_emb[tok] + speech_pos[step+1]
-    for (int d = tid; d < p.dim; d += SAMP_T) {
+    for (int d = tid; d < p.dim; d += SAMP_T) {      // dim is a multiple of 32: whole warps
         float v = p.speech_emb[(long)tok * p.dim + d] + p.speech_pos[(long)(step + 1) * p.dim + d];
         p.x[(long)(slot * 2) * p.dim + d] = v;
         p.x[(long)(slot * 2 + 1) * p.dim + d] = v;
+        if (p.xb) write_handover(p.xb, p.ss, p.gain0, slot, d, p.dim, v);
     }
     __syncthreads();
     if (tid == 0) {
@@ -563,13 +579,14 @@ __global__ void rope_kv_prefill_kernel(const RopeKvParams p) {
 }
 
 __global__ void init_slot_kernel(T3SlotState* st, T3SlotState v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
-                                 float* x, const float* speech_emb, const float* speech_pos, int dim) {
+                                 float* x, const float* speech_emb, const float* speech_pos, int dim, bf16* xb, float* ss, const float* gain0) {
     pdl_prologue();
     for (int i = threadIdx.x; i < seen_stride; i += blockDim.x) seen[(long)slot * seen_stride + i] = (i == bos) ? 1 : 0;
     for (int d = threadIdx.x; d < dim; d += blockDim.x) {
         float e = speech_emb[(long)bos * dim + d] + speech_pos[d];
         x[(long)(slot * 2) * dim + d] = e;
         x[(long)(slot * 2 + 1) * dim + d] = e;
+        if (xb) write_handover(xb, ss, gain0, slot, d, dim, e);
     }
     if (threadIdx.x == 0) { st[slot] = v; slot_pos[slot] = v.pos; }
 }
@@ -795,8 +812,9 @@ void launch_rope_kv_prefill(const RopeKvParams& p, cudaStream_t st) {
     CBX_CHECK(cudaGetLastError());
 }
 void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
-                      float* x, const float* speech_emb, const float* speech_pos, int dim, cudaStream_t st) {
-    launch_pdl(init_slot_kernel, dim3(1), dim3(256), 0, st, st_dev, v, slot_pos, slot, seen, seen_stride, bos, x, speech_emb, speech_pos, dim);
+                      float* x, const float* speech_emb, const float* speech_pos, int dim, bf16* xb, float* ss, const float* gain0, cudaStream_t st) {
+    CBX_REQUIRE(dim % 32 == 0, "init_slot: the hand-over rows are written by whole warps");
+    launch_pdl(init_slot_kernel, dim3(1), dim3(256), 0, st, st_dev, v, slot_pos, slot, seen, seen_stride, bos, x, speech_emb, speech_pos, dim, xb, ss, gain0);
     CBX_CHECK(cudaGetLastError());
 }
 void launch_align_attn(const AlignAttnParams& p, int n_streams, cudaStream_t st) {

@@ -65,6 +65,9 @@ struct SamplerParams {
     float* x = nullptr;                  // [slots*2][dim] next-step input embeddings
     const float* speech_emb = nullptr; const float* speech_pos = nullptr;
     int V = 0, dim = 0, eos = 0;
+    // the same rows in the decode step's bf16 hand-over form (layer 0 of the NEXT step on the tcgen05 path): bf16(x * gain0) and
+    // per-16-column sums of squares
+    bf16* xb = nullptr; float* ss = nullptr; const float* gain0 = nullptr;
     const int* eos_ctl = nullptr;        // optional [slots]: bit 1 forces EOS, bit 0 suppresses it (alignment control, applied after the CFG mix)
 };
 void launch_sampler(const SamplerParams& p, int n_streams, cudaStream_t st);
@@ -125,7 +128,7 @@ struct RopeKvParams {
 };
 void launch_rope_kv_prefill(const RopeKvParams& p, cudaStream_t st);
 void launch_init_slot(T3SlotState* st_dev, const T3SlotState& v, int* slot_pos, int slot, uint8_t* seen, int seen_stride, int bos,
-                      float* x, const float* speech_emb, const float* speech_pos, int dim, cudaStream_t st);
+                      float* x, const float* speech_emb, const float* speech_pos, int dim, bf16* xb, float* ss, const float* gain0, cudaStream_t st);
 void t3_kernels_init();
 void launch_prompt_embed(float* out, const float* emb, const float* pos, const int* ids, int n, int D, cudaStream_t st);
 void launch_scale_vec(float* out, const float* w, float s, int n, cudaStream_t st);

@@ -483,3 +483,28 @@ def test_t3_open_batch_matches_single_opens(tiny, tiny_cfg, dev):
         assert batch[k][1] == single[k][1], f"stream {k}: sampled ids differ"
         assert torch.equal(batch[k][0], single[k][0]), f"stream {k}: logits differ by {float((batch[k][0] - single[k][0]).abs().max())}"
     eng.voice_drop("w2")
+
+
+def test_t3_priority_switch_keeps_the_stream_order(tiny, tiny_cfg, dev):
+    """cbx_t3_set_priority moves T3 between a low- and a high-priority CUDA stream; work queued before a switch must stay ordered
+    before what follows: the same streams stepped with a switch before every call produce the tokens of the unswitched run."""
+    eng, sd_dev, conds, voice = tiny
+    texts = [_text(8 + 5 * i, seed=40 + i)[0].numpy() for i in range(3)]
+
+    def run(switching):
+        slots = [eng.t3_open(voice, t, seed=9 + i, max_new=48) for i, t in enumerate(texts)]
+        for k in range(12):
+            if switching:
+                eng.t3_set_priority(k % 2 == 0)
+            eng.t3_step(slots, 4)          # no host sync between the calls: the hand-over is an event on the device
+        toks = [eng.t3_tokens(s, 0, 48).tolist() for s in slots]
+        for s in slots:
+            eng.t3_close(s)
+        return toks
+    try:
+        base = run(False)
+        assert run(True) == base
+        eng.t3_set_priority(True)
+        assert run(False) == base
+    finally:
+        eng.t3_set_priority(False)

@@ -45,7 +45,7 @@ struct T3Model {
     int *d_slots = nullptr, *d_rowmap = nullptr;   // active set staging [max_streams], [2*max_streams]
     // alignment-based EOS control (off by default; cbx_t3_set_alignment_eos): per-slot analyzer state, decision word and the
     // newest alignment row(s) over the text span
-    bool align = false; int align_layer = 9; AlignState* align_state = nullptr; int* align_ctl = nullptr;
+    bool align = false, align_joined = false; int align_layer = 9; AlignState* align_state = nullptr; int* align_ctl = nullptr;
     float *align_cur = nullptr, *align_pre = nullptr, *align_q = nullptr; long align_ld = 0;
     cudaStream_t align_st = nullptr; cudaEvent_t align_fork = nullptr, align_join = nullptr;   // the analyzer runs beside the layers after the probe
     // megakernel state

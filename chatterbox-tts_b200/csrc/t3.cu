@@ -81,7 +81,11 @@ void t3_alloc(cbx_engine* e) {
     m.align_cur = e->scratch<float>((long)S * m.align_ld);
     m.align_pre = e->scratch<float>((long)S * m.align_ld);
     m.align_q = e->scratch<float>((long)R * T3_D);
-    CBX_CHECK(cudaStreamCreateWithFlags(&m.align_st, cudaStreamNonBlocking));
+    {   // highest priority: the sampler waits for this branch, and its two small kernels must not queue behind S3Gen's wide grids
+        int lo = 0, hi = 0;
+        CBX_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CBX_CHECK(cudaStreamCreateWithPriority(&m.align_st, cudaStreamNonBlocking, hi));
+    }
     CBX_CHECK(cudaEventCreateWithFlags(&m.align_fork, cudaEventDisableTiming));
     CBX_CHECK(cudaEventCreateWithFlags(&m.align_join, cudaEventDisableTiming));
     CBX_CHECK(cudaMemset(m.align_state, 0, sizeof(AlignState) * S));
@@ -342,14 +346,19 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
         if (m.align && li == al) {
             // alignment row of this frame and the analyzer's decision, on a side branch that joins before the sampler: its inputs
             // (the saved queries, this layer's K pages, the slot positions) are not written again before the next step
-            CBX_CHECK(cudaEventRecord(m.align_fork, st));
-            CBX_CHECK(cudaStreamWaitEvent(m.align_st, m.align_fork, 0));
+            static const int inline_branch = [] { const char* v = getenv("CBX_T3_ALIGN_INLINE"); return v ? atoi(v) : 0; }();
+            cudaStream_t ast = inline_branch ? st : m.align_st;
+            if (!inline_branch) {
+                CBX_CHECK(cudaEventRecord(m.align_fork, st));
+                CBX_CHECK(cudaStreamWaitEvent(m.align_st, m.align_fork, 0));
+            }
             AlignAttnParams aa; aa.slots = m.d_slots; aa.state = m.align_state; aa.q_rot = m.align_q; aa.kv = a.kv; aa.page_table = m.page_table; aa.max_pages = m.max_pages;
             aa.slot_pos = m.slot_pos; aa.out = m.align_cur; aa.ld_out = m.align_ld; aa.H = T3_H;
-            launch_align_attn(aa, n, m.align_st);
+            launch_align_attn(aa, n, ast);
             AlignStepParams as; as.slots = m.d_slots; as.state = m.align_state; as.t3 = m.slot_state; as.a_cur = m.align_cur; as.a_pre = m.align_pre; as.ld = m.align_ld; as.ctl = m.align_ctl;
-            launch_align_step(as, n, m.align_st);
-            CBX_CHECK(cudaEventRecord(m.align_join, m.align_st));
+            launch_align_step(as, n, ast);
+            if (!inline_branch) CBX_CHECK(cudaEventRecord(m.align_join, m.align_st));
+            m.align_joined = inline_branch != 0;
         }
         GemvParams o; o.Wf = l.wo_f; o.N = T3_D; o.K = T3_D; o.n_strips = T3_D / 16; o.strips_per_cta = 1; o.xb = m.attn_b; o.ldxb = T3_D;
         o.row_map = m.d_rowmap; o.rows = rows; o.out = m.x; o.ld_out = T3_D; o.epi = GEMV_RESID;
@@ -374,7 +383,7 @@ static void enqueue_step(cbx_engine* e, int n, const float* noise, cudaStream_t 
     h.xb = m.xb; h.ldxb = T3_D; h.ss_in = m.ss; h.n_ss = T3_D / 16;
     h.row_map = m.d_rowmap; h.rows = rows; h.eps = 1e-5f; h.out = m.logits; h.ld_out = T3_VPAD; h.epi = GEMV_STORE;
     launch_gemv(h, 8, st);
-    if (m.align) CBX_CHECK(cudaStreamWaitEvent(st, m.align_join, 0));
+    if (m.align && !m.align_joined) CBX_CHECK(cudaStreamWaitEvent(st, m.align_join, 0));
     enqueue_sampler(e, n, noise, st);
 }
 

@@ -26,7 +26,7 @@ def main():
     text = [255] + [(7 * i) % 700 + 1 for i in range(145)] + [0]
     ev = lambda: torch.cuda.Event(enable_timing=True)
     if only == "align":   # decode step with and without alignment-based EOS control (two extra kernels at the probe layer)
-        for ns in (1, 8):
+        for ns in stream_counts:
             for on in (False, True):
                 eng.t3_set_alignment_eos(on, 9)
                 slots = [eng.t3_open(v, text, seed=i, max_new=1000) for i in range(ns)]

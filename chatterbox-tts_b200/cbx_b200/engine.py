@@ -362,6 +362,7 @@ class S3GenBatcher:
         # whose prefills fell into different passes decode one round apart, and "one alone, seven in the next batch" costs the
         # seven a whole extra call (first chunk 107 / 181 ms instead of ~125 for all)
         self.imminent = None
+        self.lone = None                       # lone(): True while a single request is in flight (no gather window then)
         self.urgent_gather_s = float(os.environ.get("CBX_S3GEN_URGENT_GATHER_MS", "15")) * 1e-3
         self.threads = [threading.Thread(target=self.run, daemon=True, name=f"cbx-s3gen-batcher-{i}") for i in range(n if self.can_batch else 1)]
         for t in self.threads:
@@ -419,7 +420,9 @@ class S3GenBatcher:
                 batch = []
                 idle = (not self.jobs) or self.gather_always      # nothing accumulated while the previous batch ran: the next job opens a gather window
                 while self.running:
-                    if idle and self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch:
+                    # the first slice of a request that is alone on the engine has nobody to wait for (its other chunks start after it)
+                    alone = self.lone is not None and len(self.jobs) == 1 and self.jobs[0].urgent and self.lone()
+                    if idle and self.jobs and self.can_batch and self.gather_s > 0 and len(self.jobs) < self.max_batch and not alone:
                         # every submit wakes this wait: keep gathering until the window (counted from the first job) closes
                         t_end = time.time() + self.gather_s
                         t_cap = time.time() + self.urgent_gather_s
@@ -655,6 +658,7 @@ class TextToSpeechEngine:
         self.scheduler = T3Scheduler(self.native, max_batch=min(int(os.environ.get("CBX_T3_MAX_BATCH", "16")), self.native_kwargs["max_streams"]))
         self.s3gen = S3GenBatcher(self.native)
         self.s3gen.imminent = self._imminent_first_slices
+        self.s3gen.lone = lambda: self._inflight <= 1
         # CBX_T3_PRIORITY_MODE: auto (default) = T3 on its high-priority stream except while a first slice is in S3Gen, high / low = pinned
         mode = os.environ.get("CBX_T3_PRIORITY_MODE", "auto")
         if mode == "auto":

@@ -11,7 +11,10 @@ from cbx_b200.engine import TextToSpeechEngine, SamplingDefaults
 async def main():
     if os.environ.get('FC_GC') == '0':
         import gc; gc.collect(); gc.freeze(); gc.disable()
-    eng = TextToSpeechEngine("cuda:0", concurrent_requests=8, sampling=SamplingDefaults(tokens_per_word=bench.TOK_PER_WORD), seed=0)
+    from cbx_b200.config import ModelConfig
+    from cbx_b200.weights import random_state_dict
+    eng = TextToSpeechEngine("cuda:0", concurrent_requests=8, sampling=SamplingDefaults(tokens_per_word=bench.TOK_PER_WORD), seed=0,
+                             state_dict=random_state_dict(ModelConfig(), 0))
     await eng.ainit()
     text = bench.synthetic_text(bench.WORDS)
     for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):

@@ -165,3 +165,37 @@ def test_a_lost_device_context_refuses_new_requests():
         finally:
             eng.shutdown()
     asyncio.run(go())
+
+
+def test_t3_priority_follows_the_first_slice():
+    """The scheduler asks `high_priority()` before every decode round and tells the native engine only about CHANGES; wired as in
+    the product path (high unless a request's first slice is queued or running in S3Gen) a request starts its decode on the
+    high-priority stream, drops to low while its first slice is synthesised and returns to high afterwards."""
+    async def go():
+        from cbx_b200.engine import TextToSpeechEngine
+        nat = FakeNative()
+        calls = []
+        nat.t3_set_priority = lambda high: calls.append(bool(high))
+        eng = TextToSpeechEngine("cpu", backend=nat, concurrent_requests=1)
+        await eng.ainit()
+        seen = []
+
+        def high():
+            v = not eng.s3gen.urgent_inflight()
+            seen.append(v)
+            return v
+        eng.scheduler.high_priority = high
+        sc = SCENARIOS[-1]
+        try:
+            async for _ in eng.stream(text=scenario_text(sc["words"]), output_format="raw_pcm", voice_id=None, cfg_guidance_weight=0.5,
+                                      synthesis_temperature=0.8, text_processing_chunk_size=sc["chunk"], audio_tokens_per_slice=sc["slice"],
+                                      remove_trailing_milliseconds=sc["trail"], remove_leading_milliseconds=sc["lead"],
+                                      chunk_overlap_strategy=sc["overlap"], crossfade_duration_milliseconds=sc["fade"], request_id="prio"):
+                pass
+        finally:
+            eng.shutdown()
+        assert calls and calls[0] is True, "the first decode rounds run on the high-priority stream"
+        assert all(a != b for a, b in zip(calls, calls[1:])), "only changes are sent to the native engine"
+        assert len(seen) > len(calls), "asked every round, told only on change"
+        assert not eng.s3gen.urgent_inflight()
+    asyncio.run(go())
